@@ -1,0 +1,5 @@
+"""ORACLE -- CPU restatement of the reference (aspuru-guzik-group/waveflow) hot path.
+
+TEST INFRASTRUCTURE ONLY.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+--impl reference legs may import this package; the product (waveflow_b200/) never does.
+"""
