@@ -1,0 +1,185 @@
+/*
+ * waveflow_b200 -- C ABI of the B200 (sm_100a) hot path of aspuru-guzik-group/waveflow.
+ *
+ * The reference is pure Python/JAX and has no FFI of its own; its operator boundary is the closure protocol
+ * (SURVEY.md section 8b).  Each entry point below replaces one reference function (cited as file:line relative to
+ * /root/reference/waveflow) and is what an XLA-FFI / ctypes binding for that function would call.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host; the caller owns and allocates every buffer;
+ *   - all arrays are dense row-major float32 unless stated; sizes are int64_t; nothing is allocated or freed here;
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*), re-entrant and CUDA-graph capturable;
+ *   - return value: 0 = OK, <0 = WF_ERR_* (invalid argument / unsupported configuration), >0 = cudaError_t.
+ *   - "table" arguments are the reference's cached basis tables [4][P][T] (isplines_jax.py:112-131) re-laid-out by
+ *     wf_table_layout_host() -- see that function.
+ */
+#ifndef WAVEFLOW_B200_H
+#define WAVEFLOW_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WF_OK 0
+#define WF_ERR_INVALID_ARG (-1)
+#define WF_ERR_UNSUPPORTED (-2)
+#define WF_ERR_NO_DEVICE (-3)
+
+#define WF_MAX_P 32        /* max number of spline bases per element handled by the fused kernels            */
+#define WF_HIDDEN 64       /* conditioner width, fixed by the reference (model_factory.py:38,72)              */
+#define WF_WIN 8           /* local-support window of the compact node records                                */
+#define WF_MAX_D 8         /* max flow dimension of the fused kernels                                         */
+#define WF_MAX_LAYERS 16
+
+/* spline kinds */
+#define WF_KIND_I 0
+#define WF_KIND_M 1
+#define WF_KIND_B 2
+
+/* ABI / build info: returns WF_ABI_VERSION; writes the compiled SM arch (e.g. 100) to *sm_arch if non-null. */
+#define WF_ABI_VERSION 1
+int wf_abi_version(int* sm_arch);
+/* Human-readable text for a status code returned by any wf_* call (static storage). */
+const char* wf_status_string(int status);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Table layouts (host helper, pure C, no CUDA): converts the reference layout tab[4][P][T] (float32) to
+ *   dense_t  [T][4][PP]      PP = P rounded up to a multiple of 4, zero padded   (transposed: one node = one row)
+ *   rec      [T][4][WF_WIN]  compact local-support records; rec[m][nd][j] = tab[nd][lo[m]+j][m]
+ *   lo       [T] int32       first basis whose value at node m is not the "prefix" value
+ * prefix value of basis q < lo[m] is (nd==0 && kind==WF_KIND_I) ? 1 : 0; bases q >= lo[m]+WF_WIN are 0.
+ * Returns WF_ERR_UNSUPPORTED (and leaves rec/lo untouched) if some node has more than WF_WIN-1 non-prefix entries or the
+ * windows of adjacent nodes shift by more than one basis -- callers then use the dense kernels only.
+ * rec/lo may be NULL to request only dense_t.
+ * ------------------------------------------------------------------------------------------------------------------ */
+int wf_table_layout_host(const float* tab_host, int kind, int P, int T, float* dense_t_host, float* rec_host,
+                         int32_t* lo_host);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Spline operators at the reference's operator boundary.
+ * ------------------------------------------------------------------------------------------------------------------ */
+
+/* apply_fun_vec / apply_fun_vec_grad of ISpline_fun, MSpline_fun (isplines_jax.py:139-149, msplines_jax.py:116-126) and,
+ * with pre-mixed coefficients, of BSpline_fun:   out_k[m] = sum_q c[m][q] * basis_q^{(nd0+k)}(x[m]),  k = 0..n_out-1,
+ * each basis value being the reference's table interpolation (isplines_jax.py:45-56; derivative = next table, :60-66;
+ * table index nd > 3 clamps to 3).  Generic path: any x (JAX gather clamp/wrap semantics), any P <= 64.
+ *   out[k] may be NULL to skip an order.  out_logd (nullable) = log(out[1] + 1e-7) (made.py:79), requires n_out >= 2. */
+int wf_spline_apply_dense(const float* dense_t, int T, int P, const float* c, const float* x, int64_t M, int nd0,
+                          int n_out, float* const* out_host /* n_out device pointers in a host array */,
+                          float* out_logd, void* stream);
+
+/* Fused value + derivative + log-derivative of a LOCALLY SUPPORTED table spline (I or M tables, nd 0 and 1) -- the
+ * HBM-bound "spline + log-det" operator: persistent CTAs, coefficient tiles staged with cp.async.bulk (TMA), node
+ * records resident in shared memory.  Same results as wf_spline_apply_dense(nd0=0,n_out=2) up to summation order of
+ * exact zeros.  out_val / out_grad / out_logd are each nullable. */
+int wf_spline_apply_local(const float* rec, const int32_t* lo, const float* dense_t, int kind, int T, int P,
+                          const float* c, const float* x, int64_t M, float* out_val, float* out_grad, float* out_logd,
+                          void* stream);
+
+/* BSpline_fun.apply_fun_vec (bsplines_jax.py:127-141): c = w @ ob_to_b; c /= ||c||_2; out = sum_j c_j OB_j^{(nd)}(x).
+ * ob_dense_t is the [T][4][PP] layout of the orthonormalised tables, ob_to_b is [P][P] row-major. */
+int wf_bspline_apply(const float* ob_dense_t, const float* ob_to_b, int T, int P, const float* w, const float* x,
+                     int64_t M, int nd, float* out, void* stream);
+
+/* remove_bias (isplines_jax.py:196-202 for WF_KIND_I, msplines_jax.py:186-192 for WF_KIND_M). out may alias p. */
+int wf_remove_bias(int kind, int k, int P, const float* p, int64_t M, float* out, void* stream);
+
+/* enforce_boundary_conditions (isplines_jax.py:158-194, msplines_jax.py:156-184, bsplines_jax.py:173-199).
+ * The constraint dictionaries are passed as parallel host arrays in dict order; bv_left_host[i*4 + j] (j <= nd_i) are
+ * the boundary basis values basis_j^{(nd_i)}(0) and bv_right_host[i*4 + j] = basis_{P-1-j}^{(nd_i)}(1), i.e. exactly
+ * the I_cached(0.0, ...) / I_cached(1.0, ...) constants the reference closes over.  nd_i <= 3.
+ * Final normalisation: /sum (I, M) or /||.||_2 (B).  For WF_KIND_I a right constraint {0: 1.0} sets w[P-1] = 0. */
+int wf_enforce_bc(int kind, int P, int n_left, const int* nd_left_host, const float* val_left_host,
+                  const float* bv_left_host, int n_right, const int* nd_right_host, const float* val_right_host,
+                  const float* bv_right_host, const float* w, int64_t M, float* out, void* stream);
+
+/* reverse_fun_vec (isplines_jax.py:153-156) = utils/helpers.py:150-166 bisection on [0,1] of sum_q c_q I_q(x) - y with
+ * tolerance tol; returns the LOWER bracket.  n_iter (nullable, int32 [M]) receives the iteration count per element. */
+int wf_spline_reverse(const float* dense_t, int T, int P, const float* c, const float* y, int64_t M, float tol,
+                      float* out, int32_t* n_iter, void* stream);
+
+/* unconstrained_RQS (flows/bijections/neural_splines.py:16-71,74-184): rational-quadratic spline with K bins on
+ * [-tail_bound, tail_bound], identity tails.  inputs [M], uw/uh [M][K], ud [M][K-1] (unnormalised); inverse != 0 runs
+ * the inverse branch and returns -logabsdet.  bin_idx (nullable, int32 [M]) receives the located bin (-1 in the tails). */
+int wf_rqs_apply(const float* inputs, const float* uw, const float* uh, const float* ud, int64_t M, int K,
+                 float tail_bound, int inverse, float* outputs, float* logabsdet, int32_t* bin_idx, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Fused flows.
+ * ------------------------------------------------------------------------------------------------------------------ */
+
+/* Static description of a model built by model_factory.get_model / get_waveflow_model (model_factory.py:96-146). */
+typedef struct wf_live_model {
+  int32_t D;            /* flow dimension (2..WF_MAX_D)                                                           */
+  int32_t n_layers;     /* number of (IMADE, Reverse) pairs                                                        */
+  int32_t T;            /* mesh points of the tables (2000)                                                        */
+  int32_t P_I, k_I;     /* I-spline bases / degree                                                                 */
+  int32_t prior_kind;   /* WF_KIND_B (Waveflow), WF_KIND_M (MFlow), -1: uniform prior on [0,1] (Flow/IFlow)        */
+  int32_t P_P, k_P;     /* prior bases / degree                                                                    */
+  int32_t has_box;      /* 1: BoxTransformLayer first (made.py:108-204)                                            */
+  int32_t coord_mean;   /* 1: xu_coord_type == 'mean', 0: 'first'                                                  */
+  int32_t bc_I;         /* bit0: left {0:0}, bit1: right {0:1}   (other constraint sets: operator-level path only) */
+  int32_t bc_P;         /* bit0: left {0:0}, bit1: right {0:0}                                                     */
+  float box;            /* box_side L                                                                              */
+  float reg;            /* spline_regularization (made.py:68)                                                      */
+  float tol;            /* reverse_fun_tol (made.py:44)                                                            */
+  float reserved;
+} wf_live_model;
+
+/* Packed weights (device, float32), one block per conditioner, IMADE nets first then the prior net; per net
+ *   W1m [D][64] | b1 [64] | W2m [64][64] | b2 [64] | W3p [64][D][32] | b3p [D][32]
+ * W*m have the MADE masks already applied (model_factory.py:8-19,31-33); W3p/b3p are the third layer re-ordered so
+ * that the P coefficients of dimension d are contiguous (p[n,d,q] = o[n, q*D + d], model_factory.py:59-60) and padded
+ * with zeros to 32.  Size per net: wf_live_net_floats(D). */
+int64_t wf_live_net_floats(int D);
+
+/* Outputs selector bits of wf_live_forward */
+#define WF_OUT_U 1        /* u [N][D]: flow output in the unit cube (Serial.direct_fun)                            */
+#define WF_OUT_LOGDET 2   /* log|det J| [N]                                                                         */
+#define WF_OUT_LOGPDF 4   /* MFlow.log_pdf / Waveflow.log_pdf [N] (distributions.py:139-163, wavefunctions.py:33-52) */
+#define WF_OUT_PSI 8      /* Waveflow.psi [N] (wavefunctions.py:54-71)                                              */
+
+/* Fused forward pass: BoxTransformLayer -> (IMADE, Reverse) x L -> prior, one thread per sample, no intermediate leaves
+ * the SM.  tab_I / tab_P are [T][4][32] dense_t layouts (WF_MAX_P padded); for the B prior tab_P is the OB table and
+ * ob_to_b [P_P][P_P].  Any of the outputs may be NULL. */
+int wf_live_forward(const wf_live_model* model_host, const float* weights, const float* tab_I, const float* tab_P,
+                    const float* ob_to_b, const float* x, int64_t N, float* u, float* logdet, float* logpdf,
+                    float* psi, void* stream);
+
+/* Local energy with a fused forward-mode Laplacian (replaces jax.hessian in utils/physics.py:50-52,79-93 and the
+ * E_loc of vqmc.py:198-200):  psi, H psi = -1/2 lap psi + V psi, E_loc = H psi / (psi + 1e-8), with V the soft-Coulomb
+ * potential of physics.py:60-76 for `n_protons` protons at positions protons[n_protons] (1 space dimension).
+ * Optional outputs (nullable): psi[N], hpsi[N], eloc[N], grad[N][D] (d psi / dx), lap[N].
+ * sums (nullable, double[4], must be zeroed by the caller): += {sum E_loc, sum E_loc^2, count, sum psi^2}. */
+int wf_local_energy(const wf_live_model* model_host, const float* weights, const float* tab_I, const float* tab_P,
+                    const float* ob_to_b, const float* protons, int n_protons, const float* x, int64_t N, float* psi,
+                    float* hpsi, float* eloc, float* grad, float* lap, double* sums, void* stream);
+
+/* Serial.inverse_fun for the live flow (bijections.py:462-463): (Reverse, IMADE.inverse) x L then the box inverse.
+ * exact == 0 reproduces the reference (made.py:85-100: coefficients conditioned on the layer INPUT, quirk Q1; bisection
+ * of helpers.py:150-166; box inverse of made.py:186-197, D=2 only for 'mean').  exact != 0 conditions each dimension on
+ * the already-inverted prefix (a true inverse). */
+int wf_live_inverse(const wf_live_model* model_host, const float* weights, const float* tab_I, const float* u,
+                    int64_t N, int exact, float* x, void* stream);
+
+/* Rejection sampler of the prior + inverse flow = Waveflow.sample / MFlow.sample (wavefunctions.py:74-107,
+ * distributions.py:165-190, bsplines_jax.py:144-171, msplines_jax.py:129-154).  Counter-based Philox streams keyed by
+ * (seed, sample index); NOT bit-compatible with JAX's threefry stream (statistical parity only).
+ * b_to_ob [P_P][P_P] is only read for the B prior (ymax bound, bsplines_jax.py:163-165).
+ * u_out (nullable) receives the prior-space samples. */
+int wf_live_sample(const wf_live_model* model_host, const float* weights, const float* tab_I, const float* tab_P,
+                   const float* ob_to_b, const float* b_to_ob, uint64_t seed, int64_t N, int exact, float* x,
+                   float* u_out, void* stream);
+
+/* Serial(NeuralSplineCoupling x L).direct_fun / inverse_fun (neural_splines.py:244-296), fused over all layers.
+ * weights: per layer f1 then f2, each  W1 [D/2][Hd] | b1 [Hd] | W2 [Hd][Hd] | b2 [Hd] | W3 [Hd][(3K-1)*D/2] | b3.
+ * Supported: D even <= 8, K <= 32, Hd <= 64. */
+int wf_rqs_coupling_flow(const float* weights, int n_layers, int D, int K, int Hd, float tail_bound, int inverse,
+                         const float* x, int64_t N, float* y, float* logdet, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WAVEFLOW_B200_H */

@@ -1,0 +1,125 @@
+"""ctypes binding of the C ABI in include/waveflow_b200.h (libwaveflow_b200.so, sm_100a).
+
+There is NO CPU fallback: importing this module without the shared library raises, and every op raises on
+non-CUDA tensors.  torch is used only for device memory and streams.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+import numpy as np
+import torch
+
+_HERE = Path(__file__).resolve().parent
+LIB_PATH = _HERE / "libwaveflow_b200.so"
+
+WF_MAX_P = 32
+WF_HIDDEN = 64
+WF_WIN = 8
+KIND_I, KIND_M, KIND_B = 0, 1, 2
+KIND = {"I": KIND_I, "M": KIND_M, "B": KIND_B}
+
+
+class WaveflowB200Error(RuntimeError):
+    pass
+
+
+class LiveModelStruct(C.Structure):
+    """struct wf_live_model (include/waveflow_b200.h)."""
+    _fields_ = [("D", C.c_int32), ("n_layers", C.c_int32), ("T", C.c_int32), ("P_I", C.c_int32), ("k_I", C.c_int32),
+                ("prior_kind", C.c_int32), ("P_P", C.c_int32), ("k_P", C.c_int32), ("has_box", C.c_int32),
+                ("coord_mean", C.c_int32), ("bc_I", C.c_int32), ("bc_P", C.c_int32), ("box", C.c_float),
+                ("reg", C.c_float), ("tol", C.c_float), ("reserved", C.c_float)]
+
+
+def _load() -> C.CDLL:
+    if not LIB_PATH.exists():
+        if os.environ.get("WAVEFLOW_B200_NO_AUTOBUILD"):
+            raise WaveflowB200Error(f"{LIB_PATH} is missing: run `python -m waveflow_b200.build` (needs nvcc)")
+        from . import build as _build
+        _build.build()
+    return C.CDLL(str(LIB_PATH))
+
+
+lib = _load()
+
+_p = C.c_void_p
+_i = C.c_int
+_l = C.c_int64
+_f = C.c_float
+_SIGS = {
+    "wf_abi_version": (C.c_int, [C.POINTER(C.c_int)]),
+    "wf_status_string": (C.c_char_p, [_i]),
+    "wf_table_layout_host": (_i, [_p, _i, _i, _i, _p, _p, _p]),
+    "wf_spline_apply_dense": (_i, [_p, _i, _i, _p, _p, _l, _i, _i, C.POINTER(_p), _p, _p]),
+    "wf_spline_apply_local": (_i, [_p, _p, _p, _i, _i, _i, _p, _p, _l, _p, _p, _p, _p]),
+    "wf_bspline_apply": (_i, [_p, _p, _i, _i, _p, _p, _l, _i, _p, _p]),
+    "wf_remove_bias": (_i, [_i, _i, _i, _p, _l, _p, _p]),
+    "wf_enforce_bc": (_i, [_i, _i, _i, _p, _p, _p, _i, _p, _p, _p, _p, _l, _p, _p]),
+    "wf_spline_reverse": (_i, [_p, _i, _i, _p, _p, _l, _f, _p, _p, _p]),
+    "wf_rqs_apply": (_i, [_p, _p, _p, _p, _l, _i, _f, _i, _p, _p, _p, _p]),
+    "wf_live_net_floats": (_l, [_i]),
+    "wf_live_forward": (_i, [C.POINTER(LiveModelStruct), _p, _p, _p, _p, _p, _l, _p, _p, _p, _p, _p]),
+    "wf_local_energy": (_i, [C.POINTER(LiveModelStruct), _p, _p, _p, _p, _p, _i, _p, _l, _p, _p, _p, _p, _p, _p, _p]),
+}
+for _name, (_res, _args) in _SIGS.items():
+    _fn = getattr(lib, _name)
+    _fn.restype = _res
+    _fn.argtypes = _args
+
+if lib.wf_abi_version(None) != 1:
+    raise WaveflowB200Error("libwaveflow_b200.so ABI version mismatch: rebuild with `python -m waveflow_b200.build --force`")
+
+
+def check(status: int, what: str = ""):
+    if status != 0:
+        msg = lib.wf_status_string(status).decode()
+        raise WaveflowB200Error(f"{what or 'waveflow_b200'} failed: {msg} (status {status})")
+
+
+def ptr(t) -> C.c_void_p:
+    """Device pointer of a CUDA float32/int32/float64 tensor (None -> NULL)."""
+    if t is None:
+        return C.c_void_p(0)
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise WaveflowB200Error("waveflow_b200 ops take CUDA tensors only (there is no CPU path)")
+    if not t.is_contiguous():
+        raise WaveflowB200Error("tensor must be contiguous")
+    return C.c_void_p(t.data_ptr())
+
+
+def f32(t: torch.Tensor) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor):
+        raise WaveflowB200Error("expected a torch.Tensor on a CUDA device")
+    if not t.is_cuda:
+        raise WaveflowB200Error("waveflow_b200 ops take CUDA tensors only (there is no CPU path)")
+    return t.detach().to(torch.float32).contiguous()
+
+
+def stream_ptr() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def host_f32(a) -> np.ndarray:
+    return np.ascontiguousarray(np.asarray(a, dtype=np.float32))
+
+
+def np_ptr(a: np.ndarray | None) -> C.c_void_p:
+    return C.c_void_p(0) if a is None else C.c_void_p(a.ctypes.data)
+
+
+def table_layouts(tab: np.ndarray, kind: str):
+    """tab [4][P][T] (any float) -> (dense_t [T][4][PP] f32, rec [T][4][8] f32 | None, lo [T] i32 | None)  (host)."""
+    tab32 = host_f32(tab)
+    _, P, T = tab32.shape
+    PP = (P + 3) & ~3
+    dense = np.zeros((T, 4, PP), dtype=np.float32)
+    rec = np.zeros((T, 4, WF_WIN), dtype=np.float32)
+    lo = np.zeros(T, dtype=np.int32)
+    st = lib.wf_table_layout_host(np_ptr(tab32), KIND[kind], P, T, np_ptr(dense), np_ptr(rec), np_ptr(lo))
+    if st == -2:      # WF_ERR_UNSUPPORTED: no compact local-support form (e.g. orthonormalised B tables)
+        return dense, None, None
+    check(st, "wf_table_layout_host")
+    return dense, rec, lo

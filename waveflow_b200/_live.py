@@ -1,0 +1,188 @@
+"""Host-side driver of the fused live-path kernels (wf_live_forward / wf_local_energy).
+
+Turns a model description + the reference's parameter pytree into the packed device buffers the kernels read:
+MADE masks applied (model_factory.py:8-19,31-33), third layer re-ordered per dimension and zero-padded to 32
+coefficients (model_factory.py:59-60).  Everything here is torch-on-device plumbing; the arithmetic of the path is in
+csrc/live_device.cuh.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+
+import numpy as np
+import torch
+
+from . import _ffi
+from ._ffi import LiveModelStruct, check, lib, ptr, stream_ptr
+from .splines.tables import SplineTables
+
+HIDDEN = _ffi.WF_HIDDEN
+MAXP = _ffi.WF_MAX_P
+
+
+def made_masks(D: int, hidden: int = HIDDEN):
+    """model_factory.py:8-19 (num_hidden=1): [D,H], [H,H], [H,D] float32 masks."""
+    deg = [np.arange(D), np.arange(hidden) % (D - 1), np.arange(hidden) % (D - 1), np.arange(D) % D - 1]
+    return [(d1[:, None] >= d0[None, :]).T.astype(np.float32) for d0, d1 in zip(deg[:-1], deg[1:])]
+
+
+_MASK_CACHE: dict = {}
+
+
+def _masks_on(D: int, device):
+    key = (D, str(device))
+    if key not in _MASK_CACHE:
+        _MASK_CACHE[key] = [torch.from_numpy(m).to(device) for m in made_masks(D)]
+    return _MASK_CACHE[key]
+
+
+def net_arrays(net):
+    """(stax.serial params, zero_params) -> W1, b1, W2, b2, W3, b3  (reference pytree, model_factory.py:86-88)."""
+    nn = net[0]
+    (W1, b1), _, (W2, b2), _, (W3, b3) = nn
+    return W1, b1, W2, b2, W3, b3
+
+
+def pack_net(net, D: int, P: int, device) -> torch.Tensor:
+    """One conditioner -> flat float32 [wf_live_net_floats(D)] in the kernel's layout."""
+    W1, b1, W2, b2, W3, b3 = [torch.as_tensor(a, dtype=torch.float32, device=device) for a in net_arrays(net)]
+    if W1.shape != (D, HIDDEN) or W2.shape != (HIDDEN, HIDDEN) or W3.shape != (HIDDEN, D * P):
+        raise _ffi.WaveflowB200Error(f"unexpected conditioner shapes {tuple(W1.shape)}, {tuple(W2.shape)}, {tuple(W3.shape)} "
+                                     f"for D={D}, P={P} (hidden width is fixed at 64, model_factory.py:72)")
+    m1, m2, m3 = _masks_on(D, device)
+    W3m = (W3 * m3.repeat(1, P)).reshape(HIDDEN, P, D).permute(0, 2, 1)          # [64, D, P]
+    W3p = torch.zeros(HIDDEN, D, MAXP, dtype=torch.float32, device=device)
+    W3p[:, :, :P] = W3m
+    b3p = torch.zeros(D, MAXP, dtype=torch.float32, device=device)
+    b3p[:, :P] = b3.reshape(P, D).t()
+    return torch.cat([(W1 * m1).reshape(-1), b1.reshape(-1), (W2 * m2).reshape(-1), b2.reshape(-1), W3p.reshape(-1),
+                      b3p.reshape(-1)])
+
+
+def _bc_bits_I(left: dict, right: dict) -> int | None:
+    """Constraint sets the fused kernel supports for I-splines: {} or {0:0} on the left, {} or {0:1} on the right."""
+    bits = 0
+    if left:
+        if list(left.items()) != [(0, 0)] and list(left.items()) != [(0, 0.0)]:
+            return None
+        bits |= 1
+    if right:
+        if list(right.keys()) != [0] or float(list(right.values())[0]) != 1.0:
+            return None
+        bits |= 2
+    return bits
+
+
+def _bc_bits_P(left: dict, right: dict) -> int | None:
+    bits = 0
+    for i, d in enumerate((left, right)):
+        if d:
+            if list(d.keys()) != [0] or float(list(d.values())[0]) != 0.0:
+                return None
+            bits |= 1 << i
+    return bits
+
+
+@dataclass
+class LiveSpec:
+    """Everything static about a model assembled by model_factory (mirrors struct wf_live_model)."""
+    D: int
+    n_layers: int
+    tab_I: SplineTables
+    k_I: int
+    reg: float = 0.0
+    tol: float = 1e-6
+    bc_I_left: dict = field(default_factory=dict)
+    bc_I_right: dict = field(default_factory=dict)
+    prior: str | None = None            # 'B', 'M' or None (uniform prior)
+    tab_P: SplineTables | None = None
+    k_P: int = 0
+    bc_P_left: dict = field(default_factory=dict)
+    bc_P_right: dict = field(default_factory=dict)
+    box: float | None = None
+    coord: str = "mean"
+
+    def fusible(self) -> bool:
+        return (2 <= self.D <= 4 and self.tab_I.P <= MAXP and (self.tab_P is None or self.tab_P.P <= MAXP)
+                and _bc_bits_I(self.bc_I_left, self.bc_I_right) is not None
+                and _bc_bits_P(self.bc_P_left, self.bc_P_right) is not None)
+
+    def struct(self) -> LiveModelStruct:
+        s = LiveModelStruct()
+        s.D, s.n_layers, s.T = self.D, self.n_layers, self.tab_I.T
+        s.P_I, s.k_I = self.tab_I.P, self.k_I
+        s.prior_kind = {"B": _ffi.KIND_B, "M": _ffi.KIND_M, None: -1}[self.prior]
+        s.P_P = self.tab_P.P if self.tab_P is not None else 0
+        s.k_P = self.k_P
+        s.has_box = int(self.box is not None)
+        s.coord_mean = int(self.coord == "mean")
+        s.bc_I = _bc_bits_I(self.bc_I_left, self.bc_I_right)
+        s.bc_P = _bc_bits_P(self.bc_P_left, self.bc_P_right)
+        s.box = float(self.box or 0.0)
+        s.reg, s.tol = float(self.reg), float(self.tol)
+        return s
+
+
+def pack_params(spec: LiveSpec, transform_params, sp_params, device) -> torch.Tensor:
+    """Reference pytrees -> one flat device buffer: IMADE nets in order, then the prior net."""
+    nets = [p for p in transform_params if len(p)]
+    if len(nets) != spec.n_layers:
+        raise _ffi.WaveflowB200Error(f"expected {spec.n_layers} IMADE parameter blocks, got {len(nets)}")
+    parts = [pack_net(n, spec.D, spec.tab_I.P, device) for n in nets]
+    if spec.prior is not None:
+        parts.append(pack_net(sp_params, spec.D, spec.tab_P.P, device))
+    return torch.cat(parts).contiguous()
+
+
+def _tables(spec: LiveSpec, device):
+    tI = spec.tab_I.dev(device)["dense32"]
+    tP = ob = None
+    if spec.prior == "B":
+        tP = spec.tab_P.dev(device)["ob_dense32"]
+        ob = spec.tab_P.dev(device)["ob_to_b"]
+    elif spec.prior == "M":
+        tP = spec.tab_P.dev(device)["dense32"]
+    return tI, tP, ob
+
+
+def forward(spec: LiveSpec, weights: torch.Tensor, x: torch.Tensor, want=("u", "logdet")):
+    """wf_live_forward.  want: subset of {'u','logdet','logpdf','psi'} -> dict of tensors."""
+    x = _ffi.f32(x)
+    N = x.shape[0]
+    dev = x.device
+    tI, tP, ob = _tables(spec, dev)
+    out = {}
+    if "u" in want:
+        out["u"] = torch.empty(N, spec.D, dtype=torch.float32, device=dev)
+    for k in ("logdet", "logpdf", "psi"):
+        if k in want:
+            out[k] = torch.empty(N, dtype=torch.float32, device=dev)
+    st = lib.wf_live_forward(C.byref(spec.struct()), ptr(weights), ptr(tI), ptr(tP), ptr(ob), ptr(x), N,
+                             ptr(out.get("u")), ptr(out.get("logdet")), ptr(out.get("logpdf")), ptr(out.get("psi")),
+                             stream_ptr())
+    check(st, "wf_live_forward")
+    return out
+
+
+def local_energy(spec: LiveSpec, weights: torch.Tensor, x: torch.Tensor, protons, want=("psi", "hpsi", "eloc"),
+                 sums: torch.Tensor | None = None):
+    """wf_local_energy.  want: subset of {'psi','hpsi','eloc','grad','lap'}; sums: float64 [4] accumulator (zeroed by caller)."""
+    x = _ffi.f32(x)
+    N = x.shape[0]
+    dev = x.device
+    tI, tP, ob = _tables(spec, dev)
+    prot = _ffi.host_f32(np.asarray(protons, dtype=np.float32).reshape(-1))
+    out = {}
+    for k in ("psi", "hpsi", "eloc", "lap"):
+        if k in want:
+            out[k] = torch.empty(N, dtype=torch.float32, device=dev)
+    if "grad" in want:
+        out["grad"] = torch.empty(N, spec.D, dtype=torch.float32, device=dev)
+    if sums is not None and (sums.dtype != torch.float64 or sums.numel() != 4):
+        raise _ffi.WaveflowB200Error("sums must be a float64 tensor with 4 elements")
+    st = lib.wf_local_energy(C.byref(spec.struct()), ptr(weights), ptr(tI), ptr(tP), ptr(ob), _ffi.np_ptr(prot),
+                             int(prot.size), ptr(x), N, ptr(out.get("psi")), ptr(out.get("hpsi")), ptr(out.get("eloc")),
+                             ptr(out.get("grad")), ptr(out.get("lap")), ptr(sums), stream_ptr())
+    check(st, "wf_local_energy")
+    return out

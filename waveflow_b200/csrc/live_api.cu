@@ -1,0 +1,87 @@
+// C-ABI entry points of the fused live path (wf_live_forward, wf_local_energy).
+#include <string.h>
+#include "live_kernel.cuh"
+
+using namespace wf;
+
+extern "C" int64_t wf_live_net_floats(int D) { return (D >= 2 && D <= WF_MAX_D) ? (int64_t)net_floats(D) : -1; }
+
+namespace {
+
+// remove_bias applied to a vector of ones gives the per-coefficient scale (sequential, in place: isplines_jax.py:196-199,
+// msplines_jax.py:186-189); the {0: 0} / {0: 1} boundary constraints zero the end coefficients (isplines_jax.py:160-176).
+void coeff_weights(int kind, int k, int P, int bc_bits, bool with_bias, float* w) {
+  for (int q = 0; q < WF_MAX_P; ++q) w[q] = q < P ? 1.f : 0.f;
+  if (with_bias) {
+    for (int i = 0; i < k; ++i) {
+      const int a = kind == WF_KIND_I ? i + 1 : i;
+      const int b = kind == WF_KIND_I ? P - (i + 2) : P - (i + 1);
+      if (a >= 0 && a < P) w[a] = w[a] * (float)(i + 1) / (float)k;
+      if (b >= 0 && b < P) w[b] = w[b] * (float)(i + 1) / (float)k;
+    }
+  }
+  if (bc_bits & 1) w[0] = 0.f;
+  if (bc_bits & 2) w[P - 1] = 0.f;
+}
+
+int fill_params(const wf_live_model* m, const float* weights, const float* tab_I, const float* tab_P,
+                const float* ob_to_b, const float* x, int64_t N, LiveParams& P) {
+  if (!m || !weights || !tab_I || !x || N < 0) return WF_ERR_INVALID_ARG;
+  if (m->D < 2 || m->D > WF_MAX_D || m->n_layers < 0 || m->n_layers > WF_MAX_LAYERS || m->T < 2) return WF_ERR_INVALID_ARG;
+  if (m->P_I < 2 || m->P_I > WF_MAX_P || m->k_I < 0) return WF_ERR_INVALID_ARG;
+  if (m->D > 4) return WF_ERR_UNSUPPORTED;
+  const bool pnet = m->prior_kind == WF_KIND_B || m->prior_kind == WF_KIND_M;
+  if (m->prior_kind != -1 && !pnet) return WF_ERR_INVALID_ARG;
+  if (pnet && (!tab_P || m->P_P < 2 || m->P_P > WF_MAX_P)) return WF_ERR_INVALID_ARG;
+  if (m->prior_kind == WF_KIND_B && !ob_to_b) return WF_ERR_INVALID_ARG;
+  if (m->has_box && !(m->box > 0.f)) return WF_ERR_INVALID_ARG;
+  if ((reinterpret_cast<uintptr_t>(weights) & 15) || (reinterpret_cast<uintptr_t>(tab_I) & 15) ||
+      (tab_P && (reinterpret_cast<uintptr_t>(tab_P) & 15)))
+    return WF_ERR_INVALID_ARG;
+  memset(&P, 0, sizeof(P));
+  P.m = *m;
+  P.weights = weights; P.tab_I = tab_I; P.tab_P = tab_P; P.ob_to_b = ob_to_b; P.x = x; P.N = N;
+  P.n_nets = m->n_layers + (pnet ? 1 : 0);
+  coeff_weights(WF_KIND_I, m->k_I, m->P_I, m->bc_I, true, P.wq_I);
+  if (pnet) coeff_weights(m->prior_kind, m->k_P, m->P_P, m->bc_P, m->prior_kind == WF_KIND_M, P.wq_P);
+  return WF_OK;
+}
+
+int dispatch(LiveParams& P, bool lap, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  switch (P.m.D) {
+    case 2: return lap ? launch_live_d2_lap1(P, s) : launch_live_d2_lap0(P, s);
+    case 3: return lap ? launch_live_d3_lap1(P, s) : launch_live_d3_lap0(P, s);
+    case 4: return lap ? launch_live_d4_lap1(P, s) : launch_live_d4_lap0(P, s);
+    default: return WF_ERR_UNSUPPORTED;
+  }
+}
+
+}  // namespace
+
+extern "C" int wf_live_forward(const wf_live_model* model, const float* weights, const float* tab_I, const float* tab_P,
+                               const float* ob_to_b, const float* x, int64_t N, float* u, float* logdet, float* logpdf,
+                               float* psi, void* stream) {
+  LiveParams P;
+  const int st = fill_params(model, weights, tab_I, tab_P, ob_to_b, x, N, P);
+  if (st != WF_OK) return st;
+  if (psi && model->prior_kind != WF_KIND_B) return WF_ERR_INVALID_ARG;
+  if (N == 0) return WF_OK;
+  P.u = u; P.logdet = logdet; P.logpdf = logpdf; P.psi = psi;
+  return dispatch(P, false, stream);
+}
+
+extern "C" int wf_local_energy(const wf_live_model* model, const float* weights, const float* tab_I, const float* tab_P,
+                               const float* ob_to_b, const float* protons, int n_protons, const float* x, int64_t N,
+                               float* psi, float* hpsi, float* eloc, float* grad, float* lap, double* sums, void* stream) {
+  LiveParams P;
+  const int st = fill_params(model, weights, tab_I, tab_P, ob_to_b, x, N, P);
+  if (st != WF_OK) return st;
+  if (model->prior_kind != WF_KIND_B) return WF_ERR_INVALID_ARG;
+  if (n_protons < 0 || n_protons > WF_MAX_D || (n_protons > 0 && !protons)) return WF_ERR_INVALID_ARG;
+  if (N == 0) return WF_OK;
+  P.psi = psi; P.hpsi = hpsi; P.eloc = eloc; P.grad = grad; P.lap = lap; P.sums = sums;
+  P.n_protons = n_protons;
+  for (int i = 0; i < n_protons; ++i) P.protons[i] = protons[i];   // HOST array (a handful of floats)
+  return dispatch(P, true, stream);
+}

@@ -1,0 +1,5 @@
+// Instantiation of the fused live-path kernel for D = 2, forward-Laplacian (local energy) variant.
+#include "live_kernel.cuh"
+namespace wf {
+int launch_live_d2_lap1(LiveParams& P, cudaStream_t s) { return launch_live<2, true>(P, s); }
+}  // namespace wf

@@ -1,0 +1,251 @@
+// Persistent fused kernel for the live path (see live_device.cuh).  One CTA per SM; conditioner weights of all layers
+// stay resident in shared memory when they fit (136 KB at D=2, 205 KB at D=4, L=3), else they are re-staged per layer.
+#pragma once
+#include "live_device.cuh"
+
+namespace wf {
+
+template <int D>
+__device__ __forceinline__ float soft_coulomb(const float (&xs)[D], const float* protons, int n_protons) {
+  // utils/physics.py:66-71
+  float pe = 0.f;
+  for (int p = 0; p < n_protons; ++p)
+#pragma unroll
+    for (int e = 0; e < D; ++e) { const float d = protons[p] - xs[e]; pe += 1.f / sqrtf(1.f + d * d); }
+  float ee = 0.f;
+#pragma unroll
+  for (int i = 1; i < D; ++i)
+#pragma unroll
+    for (int j = 0; j < i; ++j) { const float d = xs[i] - xs[j]; ee += 1.f / sqrtf(1.f + d * d); }
+  return ee - pe;
+}
+
+template <int D, bool LAP>
+__global__ void __launch_bounds__(LIVE_THREADS, 1) live_kernel(const __grid_constant__ LiveParams P) {
+  using C = Ctx<D, LAP>;
+  extern __shared__ __align__(16) float smem[];
+  constexpr int NETF = net_floats(D);
+  const wf_live_model& M = P.m;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float* nets_s = smem;
+  float* ob_s = smem + (size_t)(P.nets_resident ? P.n_nets : 1) * NETF;     // [32][32], B prior only
+  double* red_s = reinterpret_cast<double*>(ob_s + WF_MAX_P * WF_MAX_P);    // [4][warps]
+
+  if (P.nets_resident) {
+    const int n4 = P.n_nets * NETF / 4;
+    for (int i = tid; i < n4; i += LIVE_THREADS)
+      reinterpret_cast<float4*>(nets_s)[i] = __ldg(reinterpret_cast<const float4*>(P.weights) + i);
+  }
+  if (M.prior_kind == WF_KIND_B) {
+    for (int i = tid; i < WF_MAX_P * WF_MAX_P; i += LIVE_THREADS) {
+      const int r = i / WF_MAX_P, c = i % WF_MAX_P;
+      ob_s[i] = (r < M.P_P && c < M.P_P) ? P.ob_to_b[r * M.P_P + c] : 0.f;
+    }
+  }
+  __syncthreads();
+
+  C cx;
+  cx.init(lane);
+  constexpr int WPB = (LIVE_THREADS / 32) * C::WPW;     // walkers per CTA batch
+  const int64_t n_batches = (P.N + WPB - 1) / WPB;
+  const bool has_prior_net = M.prior_kind == WF_KIND_B || M.prior_kind == WF_KIND_M;
+  double accE = 0.0, accE2 = 0.0, accN = 0.0, accP2 = 0.0;
+
+  auto stage_net = [&](int idx) -> const float* {
+    if (P.nets_resident) return nets_s + (size_t)idx * NETF;
+    __syncthreads();
+    for (int i = tid; i < NETF / 4; i += LIVE_THREADS)
+      reinterpret_cast<float4*>(nets_s)[i] = __ldg(reinterpret_cast<const float4*>(P.weights + (size_t)idx * NETF) + i);
+    __syncthreads();
+    return nets_s;
+  };
+
+  for (int64_t batch = blockIdx.x; batch < n_batches; batch += gridDim.x) {
+    const int64_t w_raw = batch * WPB + (int64_t)warp * C::WPW + cx.slot;
+    const bool lane_live = (!LAP || lane < C::WPW * C::G) && w_raw < P.N;
+    const int64_t w = w_raw < P.N ? w_raw : P.N - 1;
+
+    float xs[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) xs[d] = __ldg(P.x + w * D + d);
+
+    // ---------------------------------------------------------------- box transform (made.py:118-137,156-183)
+    float us[D];        // 1-register bundles of the current layer input
+    J ld = cx.constant(0.f);
+    {
+      J X[D];
+#pragma unroll
+      for (int d = 0; d < D; ++d) X[d] = J{cx.is_v ? xs[d] : (cx.comp == d + 1 ? 1.f : 0.f), 0.f, xs[d]};
+      if (M.has_box) {
+        const float L = M.box, tolr = 1e-7f;
+        J U[D];
+        if (M.coord_mean) {
+          J sum = X[0];
+#pragma unroll
+          for (int d = 1; d < D; ++d) sum = cx.add(sum, X[d]);
+          J mean = cx.scale(sum, 1.f / (float)D);
+          mean.v = sum.v / (float)D; if (cx.is_v) mean.m = mean.v;
+          const J l = cx.sub(mean, X[0]);
+          const J wd = cx.sub(X[D - 1], X[0]);
+          J space = cx.constant(2.f * L);
+#pragma unroll
+          for (int i = 0; i < D - 1; ++i) {
+            const J diff = cx.sub(X[i + 1], X[i]);
+            const J den = cx.addc(space, tolr);
+            U[i] = cx.div(diff, den);
+            ld = cx.sub(ld, cx.log(den));
+            space = cx.sub(space, diff);
+          }
+          const J den = cx.addc(cx.rsubc(2.f * L, wd), tolr);
+          U[D - 1] = cx.div(cx.sub(cx.addc(mean, L), l), den);
+          ld = cx.sub(ld, cx.log(den));
+        } else {
+          U[0] = cx.scale(cx.addc(X[0], L), 1.f / (2.f * L));
+          U[0].v = (xs[0] + L) / (2.f * L); if (cx.is_v) U[0].m = U[0].v;
+          ld = cx.addc(ld, -logf(2.f * L));
+#pragma unroll
+          for (int i = 1; i < D; ++i) {
+            const J den = cx.addc(cx.rsubc(L, X[i - 1]), tolr);
+            U[i] = cx.div(cx.sub(X[i], X[i - 1]), den);
+            ld = cx.sub(ld, cx.log(den));
+          }
+        }
+#pragma unroll
+        for (int d = 0; d < D; ++d) us[d] = cx.fold(U[d]);
+      } else {
+#pragma unroll
+        for (int d = 0; d < D; ++d) us[d] = X[d].m;
+      }
+    }
+
+    // ---------------------------------------------------------------- (IMADE, Reverse) x L   (made.py:66-81)
+    for (int layer = 0; layer < M.n_layers; ++layer) {
+      const float* net = stage_net(layer);
+      float h2[WF_HIDDEN];
+      mlp_hidden<D, LAP>(cx, net, us, h2);
+      float ys[D];
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        float o[WF_MAX_P];
+        mlp_out<D, LAP>(cx, net, d, h2, o);
+        const float xv = cx.bv(us[d]);
+        J y, dy;
+        sigmoid_spline<D, LAP, 2>(cx, o, M.P_I, P.wq_I, M.reg, P.tab_I, M.T, us[d], xv, y, dy);
+        ys[d] = cx.fold(y);
+        ld = cx.add(ld, cx.log(cx.addc(dy, LOG_TOL)));
+      }
+#pragma unroll
+      for (int d = 0; d < D; ++d) us[d] = ys[D - 1 - d];      // Reverse (bijections.py:336-345)
+    }
+
+    // ---------------------------------------------------------------- prior
+    float uv[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) uv[d] = cx.bv(us[d]);
+    J psi = cx.constant(1.f);
+    J lp = cx.constant(0.f);
+    if (has_prior_net) {
+      const float* net = stage_net(M.n_layers);
+      float h2[WF_HIDDEN];
+      mlp_hidden<D, LAP>(cx, net, us, h2);
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        float o[WF_MAX_P];
+        mlp_out<D, LAP>(cx, net, d, h2, o);
+        // constrained dimensions (model_factory.py:124-129): 'mean' -> 0..D-2, 'first' -> 1..D-1
+        const bool cons = M.coord_mean ? (d < D - 1) : (d >= 1);
+        if (M.prior_kind == WF_KIND_B) {
+          J phi = bprior_factor<D, LAP>(cx, o, M.P_P, P.wq_P, ob_s, P.tab_P, M.T, us[d], uv[d]);
+          if (!LAP) {
+            float pr = phi.v * phi.v;
+            if (cons) pr = pr / 2.f;
+            lp.v += logf(pr + LOG_TOL);
+          }
+          if (cons) phi = cx.scale(phi, 0.70710678118654752f);
+          psi = cx.mul(psi, phi);
+        } else {
+          const float xc = fminf(fmaxf(uv[d], 0.f), 1.f);
+          const float xd = (uv[d] > 0.f && uv[d] < 1.f) ? us[d] : 0.f;
+          J y, dy;
+          sigmoid_spline<D, LAP, 1>(cx, o, M.P_P, P.wq_P, 0.f, P.tab_P, M.T, xd, xc, y, dy);
+          lp.v += logf(y.v + LOG_TOL);
+        }
+      }
+    }
+    // psi = prod phi * exp(0.5 log_det)   (wavefunctions.py:67-71)
+    if (M.prior_kind == WF_KIND_B) psi = cx.mul(psi, cx.exp(cx.scale(ld, 0.5f)));
+    const float psi1 = cx.fold(psi);
+
+    // ---------------------------------------------------------------- outputs
+    if (lane_live && cx.is_v) {
+      if (P.u) {
+#pragma unroll
+        for (int d = 0; d < D; ++d) P.u[w * D + d] = uv[d];
+      }
+      if (P.logdet) P.logdet[w] = ld.v;
+      if (P.logpdf) P.logpdf[w] = lp.v + ld.v;
+      if (P.psi) P.psi[w] = psi.v;
+    }
+    if constexpr (LAP) {
+      const float lapv = __shfl_sync(FULL, psi1, cx.gbase + D + 1);
+      if (lane_live && cx.is_g && P.grad) P.grad[w * D + (cx.comp - 1)] = psi1;
+      if (lane_live && cx.is_v) {
+        const float V = soft_coulomb<D>(xs, P.protons, P.n_protons);
+        const float hp = fmaf(-0.5f, lapv, V * psi.v);           // physics.py:84
+        const float el = hp / (psi.v + 1e-8f);                  // vqmc.py:200
+        if (P.lap) P.lap[w] = lapv;
+        if (P.hpsi) P.hpsi[w] = hp;
+        if (P.eloc) P.eloc[w] = el;
+        accE += (double)el; accE2 += (double)el * (double)el; accN += 1.0; accP2 += (double)psi.v * (double)psi.v;
+      }
+    }
+  }
+
+  if constexpr (LAP) {
+    if (P.sums) {
+      double v[4] = {accE, accE2, accN, accP2};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v[k] += __shfl_xor_sync(FULL, v[k], off);
+        if (lane == 0) red_s[k * (LIVE_THREADS / 32) + warp] = v[k];
+      }
+      __syncthreads();
+      if (tid < 4) {
+        double s = 0.0;
+        for (int i = 0; i < LIVE_THREADS / 32; ++i) s += red_s[tid * (LIVE_THREADS / 32) + i];
+        atomicAdd(P.sums + tid, s);
+      }
+    }
+  }
+}
+
+inline size_t live_smem_bytes(int D, int n_nets, bool resident) {
+  return ((size_t)(resident ? n_nets : 1) * net_floats(D) + WF_MAX_P * WF_MAX_P) * sizeof(float) +
+         4 * (LIVE_THREADS / 32) * sizeof(double) + 16;
+}
+
+template <int D, bool LAP>
+int launch_live(LiveParams& P, cudaStream_t s) {
+  constexpr bool lap = LAP;
+  const size_t all = live_smem_bytes(D, P.n_nets, true);
+  P.nets_resident = all <= 227 * 1024 ? 1 : 0;
+  const size_t smem = live_smem_bytes(D, P.n_nets, P.nets_resident != 0);
+  if (smem > 227 * 1024) return WF_ERR_UNSUPPORTED;
+  const int wpw = lap ? 32 / (D + 2) : 32;
+  const int64_t wpb = (int64_t)(LIVE_THREADS / 32) * wpw;
+  const int64_t n_batches = (P.N + wpb - 1) / wpb;
+  const int blocks = (int)(n_batches < num_sms() ? n_batches : num_sms());
+  WF_CUDA(cudaFuncSetAttribute(live_kernel<D, LAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  live_kernel<D, LAP><<<blocks, LIVE_THREADS, smem, s>>>(P);
+  WF_LAUNCH_CHECK();
+  return WF_OK;
+}
+
+#define WF_DECL_LIVE(D) \
+  int launch_live_d##D##_lap0(LiveParams& P, cudaStream_t s); \
+  int launch_live_d##D##_lap1(LiveParams& P, cudaStream_t s);
+WF_DECL_LIVE(2) WF_DECL_LIVE(3) WF_DECL_LIVE(4)
+#undef WF_DECL_LIVE
+
+}  // namespace wf

@@ -1,0 +1,121 @@
+// Device-side rational-quadratic spline evaluation shared by the operator kernel (rqs.cu) and the fused coupling flow.
+// Follows flows/bijections/neural_splines.py:74-184 step by step.
+#pragma once
+#include "common.cuh"
+
+namespace wf {
+
+constexpr float RQS_MIN_BIN = 1e-3f;   // DEFAULT_MIN_BIN_WIDTH / HEIGHT (neural_splines.py:6-7)
+constexpr float RQS_MIN_DER = 1e-3f;   // DEFAULT_MIN_DERIVATIVE (neural_splines.py:8)
+constexpr float RQS_EPS = 1e-6f;       // searchsorted eps (neural_splines.py:11)
+
+__device__ __forceinline__ float softplus_f(float x) {
+  // jax.nn.softplus = logaddexp(x, 0)
+  return fmaxf(x, 0.f) + log1pf(expf(-fabsf(x)));
+}
+
+template <int KMAX, bool VEC>
+__device__ __forceinline__ void load_row(const float* __restrict__ row, int K, float (&a)[KMAX]) {
+  if (VEC) {
+#pragma unroll
+    for (int j = 0; j < KMAX; j += 4) {
+      if (j < K) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(row + j));
+        a[j] = v.x; a[j + 1] = v.y; a[j + 2] = v.z; a[j + 3] = v.w;
+      } else {
+        a[j] = a[j + 1] = a[j + 2] = a[j + 3] = -INFINITY;
+      }
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < KMAX; ++j) a[j] = j < K ? __ldg(row + j) : -INFINITY;
+  }
+}
+
+// In place: unnormalised -> right knots.  a[j] <- knot_{j+1} (neural_splines.py:98-107 / :111-120); knot_0 = lo.
+// Also returns count = #{j in 0..K : x >= knot_j (+eps on the last)} (neural_splines.py:11-13).
+template <int KMAX>
+__device__ __forceinline__ int knots_inplace(float (&a)[KMAX], int K, float lo, float hi, float x) {
+  float mx = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < KMAX; ++j)
+    if (j < K) mx = fmaxf(mx, a[j]);
+  float sum = 0.f;
+#pragma unroll
+  for (int j = 0; j < KMAX; ++j)
+    if (j < K) { a[j] = expf(a[j] - mx); sum += a[j]; }
+  const float scale = 1.f - RQS_MIN_BIN * (float)K;
+  const float span = hi - lo;
+  float c = 0.f;
+  int count = (x >= lo) ? 1 : 0;
+#pragma unroll
+  for (int j = 0; j < KMAX; ++j)
+    if (j < K) {
+      const float w = RQS_MIN_BIN + scale * (a[j] / sum);
+      c += w;
+      float kn = span * c + lo;
+      if (j == K - 1) kn = hi;
+      a[j] = kn;
+      const float cmp = (j == K - 1) ? kn + RQS_EPS : kn;
+      count += (x >= cmp) ? 1 : 0;
+    }
+  return count;
+}
+
+template <int KMAX>
+__device__ __forceinline__ void knot_pair(const float (&a)[KMAX], int K, float lo, int idx, float& kl, float& kr) {
+  kl = lo; kr = lo;
+#pragma unroll
+  for (int j = 0; j < KMAX; ++j)
+    if (j < K) {
+      if (j == idx - 1) kl = a[j];
+      if (j == idx) kr = a[j];
+    }
+}
+
+// a/b: unnormalised widths/heights (destroyed).  dget(j), j in [0, K-2]: unnormalised interior derivative j.
+template <int KMAX, class DGet>
+__device__ __forceinline__ void rqs_eval(float x, float (&a)[KMAX], float (&b)[KMAX], int K, float B, bool inverse,
+                                         DGet dget, float& out, float& lad, int& bin) {
+  const int cnt_w = knots_inplace<KMAX>(a, K, -B, B, x);
+  const int cnt_h = knots_inplace<KMAX>(b, K, -B, B, x);
+  int idx = (inverse ? cnt_h : cnt_w) - 1;
+  idx = min(max(idx, 0), K - 1);
+  bin = idx;
+  float cwl, cwr, chl, chr;
+  knot_pair<KMAX>(a, K, -B, idx, cwl, cwr);
+  knot_pair<KMAX>(b, K, -B, idx, chl, chr);
+  const float in_w = cwr - cwl, in_h = chr - chl;
+  const float delta = in_h / in_w;
+  // boundary derivatives are padded with log(exp(1 - min_derivative) - 1) (neural_splines.py:33-42)
+  const float cpad = logf(expf(1.f - RQS_MIN_DER) - 1.f);
+  const float ud0 = (idx == 0) ? cpad : dget(idx - 1);
+  const float ud1 = (idx == K - 1) ? cpad : dget(idx);
+  const float d0 = RQS_MIN_DER + softplus_f(ud0);
+  const float d1 = RQS_MIN_DER + softplus_f(ud1);
+  const float s = d0 + d1 - 2.f * delta;
+  float theta;
+  if (inverse) {
+    const float dy = x - chl;
+    const float qa = dy * s + in_h * (delta - d0);
+    const float qb = in_h * d0 - dy * s;
+    const float qc = -delta * dy;
+    const float disc = qb * qb - 4.f * qa * qc;
+    theta = (2.f * qc) / (-qb - sqrtf(disc));
+    out = theta * in_w + cwl;
+  } else {
+    theta = (x - cwl) / in_w;
+  }
+  const float t1mt = theta * (1.f - theta);
+  const float den = delta + s * t1mt;
+  if (!inverse) {
+    const float numer = in_h * (delta * theta * theta + d0 * t1mt);
+    out = chl + numer / den;
+  }
+  const float omt = 1.f - theta;
+  const float num = delta * delta * (d1 * theta * theta + 2.f * delta * t1mt + d0 * omt * omt);
+  const float l = logf(num) - 2.f * logf(den);
+  lad = inverse ? -l : l;
+}
+
+}  // namespace wf

@@ -1,0 +1,451 @@
+// Table-interpolated I-/M-/B-spline operators at the reference's operator boundary
+// (splines/isplines_jax.py, msplines_jax.py, bsplines_jax.py) for sm_100a.
+#include <math.h>
+#include <string.h>
+#include "common.cuh"
+
+using namespace wf;
+
+// ============================================================================================ host: table layouts
+extern "C" int wf_table_layout_host(const float* tab, int kind, int P, int T, float* dense_t, float* rec,
+                                    int32_t* lo) {
+  if (!tab || P <= 0 || T <= 1 || (kind != WF_KIND_I && kind != WF_KIND_M && kind != WF_KIND_B)) return WF_ERR_INVALID_ARG;
+  const int PP = (P + 3) & ~3;
+  if (dense_t) {
+    for (int m = 0; m < T; ++m)
+      for (int nd = 0; nd < 4; ++nd)
+        for (int q = 0; q < PP; ++q)
+          dense_t[((size_t)m * 4 + nd) * PP + q] = q < P ? tab[((size_t)nd * P + q) * T + m] : 0.0f;
+  }
+  if (!rec && !lo) return WF_OK;
+  if (!rec || !lo) return WF_ERR_INVALID_ARG;
+  // pass 1: windows
+  int32_t* lo_tmp = new int32_t[T];
+  int status = WF_OK;
+  for (int m = 0; m < T && status == WF_OK; ++m) {
+    int first = P, last = -1;
+    for (int q = 0; q < P; ++q) {
+      bool trivial_prefix = true, zero = true;
+      for (int nd = 0; nd < 4; ++nd) {
+        const float v = tab[((size_t)nd * P + q) * T + m];
+        const float pv = (nd == 0 && kind == WF_KIND_I) ? 1.0f : 0.0f;
+        if (v != pv) trivial_prefix = false;
+        if (v != 0.0f) zero = false;
+      }
+      if (!trivial_prefix && first == P) first = q;
+      if (!zero && !(q < first)) last = q;
+    }
+    if (first == P) first = (last >= 0) ? last : 0;  // node where everything is prefix/zero
+    // all bases beyond the window must be exactly zero, and bases before it exactly the prefix value
+    if (last - first + 1 > WF_WIN - 1) status = WF_ERR_UNSUPPORTED;
+    lo_tmp[m] = first;
+  }
+  for (int m = 0; m + 1 < T && status == WF_OK; ++m) {
+    const int s = lo_tmp[m + 1] - lo_tmp[m];
+    if (s < 0 || s > 1) status = WF_ERR_UNSUPPORTED;
+  }
+  if (status == WF_OK) {
+    for (int m = 0; m < T; ++m) {
+      lo[m] = lo_tmp[m];
+      for (int nd = 0; nd < 4; ++nd)
+        for (int j = 0; j < WF_WIN; ++j) {
+          const int q = lo_tmp[m] + j;
+          rec[((size_t)m * 4 + nd) * WF_WIN + j] = q < P ? tab[((size_t)nd * P + q) * T + m] : 0.0f;
+        }
+    }
+  }
+  delete[] lo_tmp;
+  return status;
+}
+
+// ============================================================================================ dense generic apply
+// One thread per element; coefficient rows and table rows read through L1/L2.  Reference semantics for any input.
+template <int NOUT>
+__global__ void __launch_bounds__(256) spline_dense_kernel(const float* __restrict__ dense_t, int T, int P, int PP,
+                                                           const float* __restrict__ c, const float* __restrict__ x,
+                                                           int64_t M, int nd0, float* o0, float* o1, float* o2,
+                                                           float* o3, float* out_logd) {
+  const float np_ = (float)(T - 1);
+  for (int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; m < M; m += (int64_t)gridDim.x * blockDim.x) {
+    const float xv = x[m];
+    const NodeIdx n = node_index(xv, T);
+    const float* cl = c + m * P;
+    float acc[NOUT];
+#pragma unroll
+    for (int k = 0; k < NOUT; ++k) acc[k] = 0.f;
+#pragma unroll
+    for (int k = 0; k < NOUT; ++k) {
+      const int nd = min(nd0 + k, 3);   // quirk Q5: derivative table index clamps at 3
+      const float* tl = dense_t + ((size_t)n.l * 4 + nd) * PP;
+      const float* tr = dense_t + ((size_t)n.r * 4 + nd) * PP;
+      float a = 0.f;
+      for (int q = 0; q < P; ++q) a = fmaf(cl[q], lerp_tab(__ldg(tl + q), __ldg(tr + q), np_, n.dx), a);
+      acc[k] = a;
+    }
+    float* outs[4] = {o0, o1, o2, o3};
+#pragma unroll
+    for (int k = 0; k < NOUT; ++k)
+      if (outs[k]) outs[k][m] = acc[k];
+    if (NOUT >= 2 && out_logd) out_logd[m] = logf(acc[1] + LOG_TOL);
+  }
+}
+
+extern "C" int wf_spline_apply_dense(const float* dense_t, int T, int P, const float* c, const float* x, int64_t M,
+                                     int nd0, int n_out, float* const* out_host, float* out_logd, void* stream) {
+  if (!dense_t || !c || !x || !out_host || T < 2 || P < 1 || P > 64 || M < 0 || n_out < 1 || n_out > 4 || nd0 < 0)
+    return WF_ERR_INVALID_ARG;
+  if (out_logd && n_out < 2) return WF_ERR_INVALID_ARG;
+  if (M == 0) return WF_OK;
+  float* o[4] = {nullptr, nullptr, nullptr, nullptr};
+  for (int k = 0; k < n_out; ++k) o[k] = out_host[k];
+  const int PP = (P + 3) & ~3;
+  const int threads = 256;
+  const int64_t want = (M + threads - 1) / threads;
+  const int blocks = (int)(want < (int64_t)num_sms() * 8 ? want : (int64_t)num_sms() * 8);
+  cudaStream_t s = (cudaStream_t)stream;
+  switch (n_out) {
+    case 1: spline_dense_kernel<1><<<blocks, threads, 0, s>>>(dense_t, T, P, PP, c, x, M, nd0, o[0], o[1], o[2], o[3], out_logd); break;
+    case 2: spline_dense_kernel<2><<<blocks, threads, 0, s>>>(dense_t, T, P, PP, c, x, M, nd0, o[0], o[1], o[2], o[3], out_logd); break;
+    case 3: spline_dense_kernel<3><<<blocks, threads, 0, s>>>(dense_t, T, P, PP, c, x, M, nd0, o[0], o[1], o[2], o[3], out_logd); break;
+    default: spline_dense_kernel<4><<<blocks, threads, 0, s>>>(dense_t, T, P, PP, c, x, M, nd0, o[0], o[1], o[2], o[3], out_logd); break;
+  }
+  WF_LAUNCH_CHECK();
+  return WF_OK;
+}
+
+// ============================================================================================ fused local apply (HBM-bound)
+// Persistent CTAs.  Shared memory:  node records (nd 0,1) [T][2][8] | lo [T] (u8) | 2 x coefficient tile [R][P] | mbarriers.
+// Coefficient tiles arrive through cp.async.bulk (TMA, SASS UBLKCP) double-buffered against the compute of the previous
+// tile; x is read and the outputs are written fully coalesced (thread r <-> row tile*R + r).
+constexpr int LOCAL_R = 256;
+
+struct LocalSmem {
+  static __host__ __device__ size_t rec_bytes(int T) { return (size_t)T * 16 * sizeof(float); }
+  static __host__ __device__ size_t lo_bytes(int T) { return ((size_t)T + 15) & ~(size_t)15; }
+  static __host__ __device__ size_t tile_bytes(int P) { return (size_t)LOCAL_R * P * sizeof(float); }
+  static __host__ __device__ size_t total(int T, int P) { return rec_bytes(T) + lo_bytes(T) + 2 * tile_bytes(P) + 64; }
+};
+
+template <bool PREFIX_ONE>
+__device__ __forceinline__ void local_eval(const float* __restrict__ crow, const float* __restrict__ rec_s,
+                                           const uint8_t* __restrict__ lo_s, const float* __restrict__ dense_t,
+                                           int T, int P, float xv, float& val, float& grad) {
+  const float np_ = (float)(T - 1);
+  const NodeIdx n = node_index(xv, T);
+  const int lo_l = lo_s[n.l], lo_r = lo_s[n.r];
+  const int s = lo_r - lo_l;
+  float a0 = 0.f, a1 = 0.f;
+  if (s < 0 || s > 1) {
+    // wrapped / far-apart nodes (only reachable for x outside [0,1]): reference-exact dense evaluation
+    const int PP = (P + 3) & ~3;
+    const float* tl0 = dense_t + ((size_t)n.l * 4 + 0) * PP;
+    const float* tr0 = dense_t + ((size_t)n.r * 4 + 0) * PP;
+    for (int q = 0; q < P; ++q) {
+      const float cq = crow[q];
+      a0 = fmaf(cq, lerp_tab(__ldg(tl0 + q), __ldg(tr0 + q), np_, n.dx), a0);
+      a1 = fmaf(cq, lerp_tab(__ldg(tl0 + PP + q), __ldg(tr0 + PP + q), np_, n.dx), a1);
+    }
+    val = a0; grad = a1;
+    return;
+  }
+  if (PREFIX_ONE) {
+    // bases below the window are identically 1 at both nodes: c_q * (1 + 0*dx) == c_q, added in index order
+    for (int q = 0; q < lo_l; ++q) a0 += crow[q];
+  }
+  const float* rl = rec_s + n.l * 16;
+  const float* rr = rec_s + n.r * 16 - s;     // shifted so that rr[t] is basis lo_l + t at the right node
+  const float pre0 = PREFIX_ONE ? 1.f : 0.f;
+#pragma unroll
+  for (int t = 0; t < WF_WIN; ++t) {
+    const int q = lo_l + t;
+    if (q < P) {
+      const float cq = crow[q];
+      const bool inr = (t - s) >= 0;
+      const float yl0 = rl[t], yl1 = rl[8 + t];
+      const float yr0 = inr ? rr[t] : pre0;
+      const float yr1 = inr ? rr[8 + t] : 0.f;
+      a0 = fmaf(cq, lerp_tab(yl0, yr0, np_, n.dx), a0);
+      a1 = fmaf(cq, lerp_tab(yl1, yr1, np_, n.dx), a1);
+    }
+  }
+  val = a0; grad = a1;
+}
+
+template <bool PREFIX_ONE>
+__global__ void __launch_bounds__(LOCAL_R, 1)
+spline_local_kernel(const float* __restrict__ rec, const int32_t* __restrict__ lo, const float* __restrict__ dense_t,
+                    int T, int P, const float* __restrict__ c, const float* __restrict__ x, int64_t M,
+                    float* __restrict__ out_val, float* __restrict__ out_grad, float* __restrict__ out_logd) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  float* rec_s = reinterpret_cast<float*>(smem);
+  uint8_t* lo_s = smem + LocalSmem::rec_bytes(T);
+  float* tile0 = reinterpret_cast<float*>(smem + LocalSmem::rec_bytes(T) + LocalSmem::lo_bytes(T));
+  float* tile1 = tile0 + (size_t)LOCAL_R * P;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + LocalSmem::rec_bytes(T) + LocalSmem::lo_bytes(T) + 2 * LocalSmem::tile_bytes(P));
+
+  const int tid = threadIdx.x;
+  const int64_t n_tiles = (M + LOCAL_R - 1) / LOCAL_R;
+  const uint32_t full_bytes = (uint32_t)LocalSmem::tile_bytes(P);
+
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    mbar_fence_init();
+  }
+  // node records: only derivative orders 0 and 1 (first 16 of the 32 floats of each node)
+  for (int i = tid; i < T * 4; i += LOCAL_R) {
+    const int m = i >> 2, part = i & 3;
+    reinterpret_cast<float4*>(rec_s)[i] = __ldg(reinterpret_cast<const float4*>(rec) + m * 8 + part);
+  }
+  for (int i = tid; i < T; i += LOCAL_R) lo_s[i] = (uint8_t)lo[i];
+  __syncthreads();
+
+  auto issue = [&](int64_t tile, int buf) {
+    // whole tiles go through the bulk-copy engine; the ragged last tile is copied by the threads (see below)
+    float* dst = buf ? tile1 : tile0;
+    mbar_expect_tx(&bars[buf], full_bytes);
+    bulk_g2s(dst, c + tile * (int64_t)LOCAL_R * P, full_bytes, &bars[buf]);
+  };
+  auto is_full = [&](int64_t tile) { return (tile + 1) * LOCAL_R <= M; };
+
+  int64_t tile = blockIdx.x;
+  uint32_t phase[2] = {0u, 0u};
+  int buf = 0;
+  if (tile < n_tiles && is_full(tile) && tid == 0) issue(tile, 0);
+
+  for (; tile < n_tiles; tile += gridDim.x, buf ^= 1) {
+    const int64_t next = tile + gridDim.x;
+    if (next < n_tiles && is_full(next) && tid == 0) issue(next, buf ^ 1);
+    const int64_t row = tile * LOCAL_R + tid;
+    const bool live = row < M;
+    const float xv = live ? ldg_stream(x + row) : 0.f;
+    float* ct = buf ? tile1 : tile0;
+    if (is_full(tile)) {
+      mbar_wait(&bars[buf], phase[buf]);
+      phase[buf] ^= 1u;
+    } else {
+      const int64_t base = tile * (int64_t)LOCAL_R * P;
+      const int64_t cnt = (M - tile * LOCAL_R) * P;
+      for (int64_t i = tid; i < cnt; i += LOCAL_R) ct[i] = c[base + i];
+      __syncthreads();
+    }
+    if (live) {
+      float v, g;
+      local_eval<PREFIX_ONE>(ct + (size_t)tid * P, rec_s, lo_s, dense_t, T, P, xv, v, g);
+      if (out_val) stg_stream(out_val + row, v);
+      if (out_grad) stg_stream(out_grad + row, g);
+      if (out_logd) stg_stream(out_logd + row, logf(g + LOG_TOL));
+    }
+    __syncthreads();   // everyone is done with `buf` before it is refilled two iterations from now
+  }
+}
+
+extern "C" int wf_spline_apply_local(const float* rec, const int32_t* lo, const float* dense_t, int kind, int T, int P,
+                                     const float* c, const float* x, int64_t M, float* out_val, float* out_grad,
+                                     float* out_logd, void* stream) {
+  if (!rec || !lo || !dense_t || !c || !x || T < 2 || P < 1 || P > 64 || M < 0) return WF_ERR_INVALID_ARG;
+  if (kind != WF_KIND_I && kind != WF_KIND_M && kind != WF_KIND_B) return WF_ERR_INVALID_ARG;
+  if ((reinterpret_cast<uintptr_t>(c) & 15) || (reinterpret_cast<uintptr_t>(rec) & 15)) return WF_ERR_INVALID_ARG;
+  if (M == 0) return WF_OK;
+  const size_t smem = LocalSmem::total(T, P);
+  if (smem > 227 * 1024) return WF_ERR_UNSUPPORTED;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int64_t n_tiles = (M + LOCAL_R - 1) / LOCAL_R;
+  const int blocks = (int)(n_tiles < num_sms() ? n_tiles : num_sms());
+  if (kind == WF_KIND_I) {
+    WF_CUDA(cudaFuncSetAttribute(spline_local_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    spline_local_kernel<true><<<blocks, LOCAL_R, smem, s>>>(rec, lo, dense_t, T, P, c, x, M, out_val, out_grad, out_logd);
+  } else {
+    WF_CUDA(cudaFuncSetAttribute(spline_local_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    spline_local_kernel<false><<<blocks, LOCAL_R, smem, s>>>(rec, lo, dense_t, T, P, c, x, M, out_val, out_grad, out_logd);
+  }
+  WF_LAUNCH_CHECK();
+  return WF_OK;
+}
+
+// ============================================================================================ B-spline apply (OB basis)
+// c = w @ ob_to_b; c /= ||c||;  out = sum_j c_j OB_j^{(nd)}(x).  One thread per element, ob_to_b in shared memory.
+__global__ void __launch_bounds__(128) bspline_apply_kernel(const float* __restrict__ ob_dense_t,
+                                                            const float* __restrict__ ob_to_b, int T, int P, int PP,
+                                                            const float* __restrict__ w, const float* __restrict__ x,
+                                                            int64_t M, int nd, float* __restrict__ out) {
+  extern __shared__ float mat_s[];   // [P][P]
+  for (int i = threadIdx.x; i < P * P; i += blockDim.x) mat_s[i] = ob_to_b[i];
+  __syncthreads();
+  const float np_ = (float)(T - 1);
+  for (int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; m < M; m += (int64_t)gridDim.x * blockDim.x) {
+    float cc[64];
+    const float* wr = w + m * P;
+#pragma unroll 1
+    for (int j = 0; j < P; ++j) cc[j] = 0.f;
+    for (int i = 0; i < P; ++i) {
+      const float wi = wr[i];
+      for (int j = 0; j < P; ++j) cc[j] = fmaf(wi, mat_s[i * P + j], cc[j]);
+    }
+    float ss = 0.f;
+    for (int j = 0; j < P; ++j) ss = fmaf(cc[j], cc[j], ss);
+    const float nrm = sqrtf(ss);
+    const NodeIdx n = node_index(x[m], T);
+    const int ndc = min(nd, 3);
+    const float* tl = ob_dense_t + ((size_t)n.l * 4 + ndc) * PP;
+    const float* tr = ob_dense_t + ((size_t)n.r * 4 + ndc) * PP;
+    float a = 0.f;
+    for (int j = 0; j < P; ++j) a = fmaf(cc[j] / nrm, lerp_tab(__ldg(tl + j), __ldg(tr + j), np_, n.dx), a);
+    out[m] = a;
+  }
+}
+
+extern "C" int wf_bspline_apply(const float* ob_dense_t, const float* ob_to_b, int T, int P, const float* w,
+                                const float* x, int64_t M, int nd, float* out, void* stream) {
+  if (!ob_dense_t || !ob_to_b || !w || !x || !out || T < 2 || P < 1 || P > 64 || M < 0 || nd < 0) return WF_ERR_INVALID_ARG;
+  if (M == 0) return WF_OK;
+  const int threads = 128;
+  const int64_t want = (M + threads - 1) / threads;
+  const int blocks = (int)(want < (int64_t)num_sms() * 8 ? want : (int64_t)num_sms() * 8);
+  bspline_apply_kernel<<<blocks, threads, (size_t)P * P * sizeof(float), (cudaStream_t)stream>>>(
+      ob_dense_t, ob_to_b, T, P, (P + 3) & ~3, w, x, M, nd, out);
+  WF_LAUNCH_CHECK();
+  return WF_OK;
+}
+
+// ============================================================================================ remove_bias
+__global__ void __launch_bounds__(256) remove_bias_kernel(int kind, int k, int P, const float* __restrict__ p,
+                                                          int64_t M, float* __restrict__ out) {
+  for (int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; m < M; m += (int64_t)gridDim.x * blockDim.x) {
+    float r[64];
+    const float* pr = p + m * P;
+    for (int q = 0; q < P; ++q) r[q] = pr[q];
+    const float fk = (float)k;
+    for (int i = 0; i < k; ++i) {
+      // params[i+1] * (i + 1) / k ; params[-(i+2)] * (i + 1) / k   (I);  params[i], params[-(i+1)] (M) -- sequential, in place
+      const int a = kind == WF_KIND_I ? i + 1 : i;
+      const int b = kind == WF_KIND_I ? P - (i + 2) : P - (i + 1);
+      if (a >= 0 && a < P) r[a] = r[a] * (float)(i + 1) / fk;
+      if (b >= 0 && b < P) r[b] = r[b] * (float)(i + 1) / fk;
+    }
+    float s = 0.f;
+    for (int q = 0; q < P; ++q) s += r[q];
+    float* orow = out + m * P;
+    for (int q = 0; q < P; ++q) orow[q] = r[q] / s;
+  }
+}
+
+extern "C" int wf_remove_bias(int kind, int k, int P, const float* p, int64_t M, float* out, void* stream) {
+  if (!p || !out || P < 1 || P > 64 || k < 0 || M < 0 || (kind != WF_KIND_I && kind != WF_KIND_M)) return WF_ERR_INVALID_ARG;
+  if (M == 0) return WF_OK;
+  const int64_t want = (M + 255) / 256;
+  const int blocks = (int)(want < (int64_t)num_sms() * 8 ? want : (int64_t)num_sms() * 8);
+  remove_bias_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(kind, k, P, p, M, out);
+  WF_LAUNCH_CHECK();
+  return WF_OK;
+}
+
+// ============================================================================================ boundary conditions
+struct BcSpec {
+  int n_left, n_right;
+  int nd_left[4], nd_right[4];
+  float val_left[4], val_right[4];
+  float bv_left[16], bv_right[16];
+};
+
+__global__ void __launch_bounds__(256) enforce_bc_kernel(int kind, int P, BcSpec bc, const float* __restrict__ w,
+                                                         int64_t M, float* __restrict__ out) {
+  for (int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; m < M; m += (int64_t)gridDim.x * blockDim.x) {
+    float r[64];
+    const float* wr = w + m * P;
+    for (int q = 0; q < P; ++q) r[q] = wr[q];
+    for (int i = 0; i < bc.n_left; ++i) {
+      const int nd = bc.nd_left[i];
+      float s = 0.f;
+      for (int j = 0; j < nd; ++j) s += bc.bv_left[i * 4 + j] * r[j];
+      r[nd] = (bc.val_left[i] - s) / bc.bv_left[i * 4 + nd];
+    }
+    for (int i = 0; i < bc.n_right; ++i) {
+      const int nd = bc.nd_right[i];
+      if (kind == WF_KIND_I && nd == 0) { r[P - 1] = 0.f; continue; }
+      float s = 0.f;
+      for (int j = 0; j < nd; ++j) s += bc.bv_right[i * 4 + j] * r[P - 1 - j];
+      r[P - 1 - nd] = (bc.val_right[i] - s) / bc.bv_right[i * 4 + nd];
+    }
+    float s = 0.f;
+    if (kind == WF_KIND_B) {
+      for (int q = 0; q < P; ++q) s = fmaf(r[q], r[q], s);
+      s = sqrtf(s);
+    } else {
+      for (int q = 0; q < P; ++q) s += r[q];
+    }
+    float* orow = out + m * P;
+    for (int q = 0; q < P; ++q) orow[q] = r[q] / s;
+  }
+}
+
+extern "C" int wf_enforce_bc(int kind, int P, int n_left, const int* nd_left, const float* val_left,
+                             const float* bv_left, int n_right, const int* nd_right, const float* val_right,
+                             const float* bv_right, const float* w, int64_t M, float* out, void* stream) {
+  if (!w || !out || P < 1 || P > 64 || M < 0 || n_left < 0 || n_left > 4 || n_right < 0 || n_right > 4) return WF_ERR_INVALID_ARG;
+  if (kind != WF_KIND_I && kind != WF_KIND_M && kind != WF_KIND_B) return WF_ERR_INVALID_ARG;
+  BcSpec bc;
+  memset(&bc, 0, sizeof(bc));
+  bc.n_left = n_left; bc.n_right = n_right;
+  for (int i = 0; i < n_left; ++i) {
+    if (nd_left[i] < 0 || nd_left[i] > 3 || nd_left[i] >= P) return WF_ERR_INVALID_ARG;
+    bc.nd_left[i] = nd_left[i]; bc.val_left[i] = val_left[i];
+    for (int j = 0; j < 4; ++j) bc.bv_left[i * 4 + j] = bv_left[i * 4 + j];
+  }
+  for (int i = 0; i < n_right; ++i) {
+    if (nd_right[i] < 0 || nd_right[i] > 3 || nd_right[i] >= P) return WF_ERR_INVALID_ARG;
+    if (kind == WF_KIND_I && nd_right[i] == 0 && val_right[i] != 1.0f) return WF_ERR_UNSUPPORTED;  // isplines_jax.py:177-179
+    bc.nd_right[i] = nd_right[i]; bc.val_right[i] = val_right[i];
+    for (int j = 0; j < 4; ++j) bc.bv_right[i * 4 + j] = bv_right[i * 4 + j];
+  }
+  if (M == 0) return WF_OK;
+  const int64_t want = (M + 255) / 256;
+  const int blocks = (int)(want < (int64_t)num_sms() * 8 ? want : (int64_t)num_sms() * 8);
+  enforce_bc_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(kind, P, bc, w, M, out);
+  WF_LAUNCH_CHECK();
+  return WF_OK;
+}
+
+// ============================================================================================ bisection inverse
+// helpers.py:150-166: while (lo + tol/2 < mid) & (mid < hi - tol/2): if f(mid) > 0: hi = mid else lo = mid; return lo.
+__global__ void __launch_bounds__(128) spline_reverse_kernel(const float* __restrict__ dense_t, int T, int P, int PP,
+                                                             const float* __restrict__ c, const float* __restrict__ y,
+                                                             int64_t M, float tol, float* __restrict__ out,
+                                                             int32_t* __restrict__ n_iter) {
+  const float np_ = (float)(T - 1);
+  const float half_tol = tol / 2.f;
+  for (int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; m < M; m += (int64_t)gridDim.x * blockDim.x) {
+    float cr[64];
+    const float* cl = c + m * P;
+    for (int q = 0; q < P; ++q) cr[q] = cl[q];
+    const float yv = y[m];
+    float lo = 0.f, hi = 1.f;
+    int it = 0;
+    while (true) {
+      const float mid = 0.5f * (lo + hi);
+      if (!((lo + half_tol < mid) && (mid < hi - half_tol))) break;
+      const NodeIdx n = node_index(mid, T);
+      const float* tl = dense_t + (size_t)n.l * 4 * PP;
+      const float* tr = dense_t + (size_t)n.r * 4 * PP;
+      float a = 0.f;
+      for (int q = 0; q < P; ++q) a = fmaf(cr[q], lerp_tab(__ldg(tl + q), __ldg(tr + q), np_, n.dx), a);
+      const bool upper = (a - yv) > 0.f;
+      lo = upper ? lo : mid;
+      hi = upper ? mid : hi;
+      ++it;
+    }
+    out[m] = lo;
+    if (n_iter) n_iter[m] = it;
+  }
+}
+
+extern "C" int wf_spline_reverse(const float* dense_t, int T, int P, const float* c, const float* y, int64_t M,
+                                 float tol, float* out, int32_t* n_iter, void* stream) {
+  if (!dense_t || !c || !y || !out || T < 2 || P < 1 || P > 64 || M < 0 || !(tol > 0.f)) return WF_ERR_INVALID_ARG;
+  if (M == 0) return WF_OK;
+  const int64_t want = (M + 127) / 128;
+  const int blocks = (int)(want < (int64_t)num_sms() * 16 ? want : (int64_t)num_sms() * 16);
+  spline_reverse_kernel<<<blocks, 128, 0, (cudaStream_t)stream>>>(dense_t, T, P, (P + 3) & ~3, c, y, M, tol, out, n_iter);
+  WF_LAUNCH_CHECK();
+  return WF_OK;
+}
