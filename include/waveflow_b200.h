@@ -157,28 +157,6 @@ int wf_local_energy(const wf_live_model* model_host, const float* weights, const
                     const float* ob_to_b, const float* protons, int n_protons, const float* x, int64_t N, float* psi,
                     float* hpsi, float* eloc, float* grad, float* lap, double* sums, void* stream);
 
-/* Serial.inverse_fun for the live flow (bijections.py:462-463): (Reverse, IMADE.inverse) x L then the box inverse.
- * exact == 0 reproduces the reference (made.py:85-100: coefficients conditioned on the layer INPUT, quirk Q1; bisection
- * of helpers.py:150-166; box inverse of made.py:186-197, D=2 only for 'mean').  exact != 0 conditions each dimension on
- * the already-inverted prefix (a true inverse). */
-int wf_live_inverse(const wf_live_model* model_host, const float* weights, const float* tab_I, const float* u,
-                    int64_t N, int exact, float* x, void* stream);
-
-/* Rejection sampler of the prior + inverse flow = Waveflow.sample / MFlow.sample (wavefunctions.py:74-107,
- * distributions.py:165-190, bsplines_jax.py:144-171, msplines_jax.py:129-154).  Counter-based Philox streams keyed by
- * (seed, sample index); NOT bit-compatible with JAX's threefry stream (statistical parity only).
- * b_to_ob [P_P][P_P] is only read for the B prior (ymax bound, bsplines_jax.py:163-165).
- * u_out (nullable) receives the prior-space samples. */
-int wf_live_sample(const wf_live_model* model_host, const float* weights, const float* tab_I, const float* tab_P,
-                   const float* ob_to_b, const float* b_to_ob, uint64_t seed, int64_t N, int exact, float* x,
-                   float* u_out, void* stream);
-
-/* Serial(NeuralSplineCoupling x L).direct_fun / inverse_fun (neural_splines.py:244-296), fused over all layers.
- * weights: per layer f1 then f2, each  W1 [D/2][Hd] | b1 [Hd] | W2 [Hd][Hd] | b2 [Hd] | W3 [Hd][(3K-1)*D/2] | b3.
- * Supported: D even <= 8, K <= 32, Hd <= 64. */
-int wf_rqs_coupling_flow(const float* weights, int n_layers, int D, int K, int Hd, float tail_bound, int inverse,
-                         const float* x, int64_t N, float* y, float* logdet, void* stream);
-
 #ifdef __cplusplus
 }
 #endif

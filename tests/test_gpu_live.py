@@ -1,0 +1,146 @@
+"""T3/T4: fused live-path parity -- psi / log_pdf / u / log|det J| and the forward-Laplacian local energy."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import fixtures as fx
+from oracle import laplacian as olap
+from oracle import live
+from tests.util import relerr, spec_from_live
+
+pytestmark = pytest.mark.gpu
+
+
+def _pack(spec, params, device):
+    from waveflow_b200 import _live
+    return _live.pack_params(spec, params[0], params[1], device)
+
+
+def _grid():
+    y, x = np.meshgrid(np.linspace(-10, 10, 100), np.linspace(-10, 10, 100))
+    c = np.stack([x, y], -1).reshape(-1, 2)
+    return c, (c[:, 0] > c[:, 1]).astype(int)
+
+
+def test_psi_published_known_answer(cuda):
+    """He checkpoint -> psi on the published 100x100 grid (utils/helpers.py:52-59), compared with the values the
+    reference itself wrote (float32 JAX) and with the float64 oracle."""
+    from waveflow_b200 import _live
+    params, gold = fx.load_he_checkpoint()
+    m64 = fx.waveflow_model(2)
+    spec = spec_from_live(m64)
+    w = _pack(spec, params, cuda)
+    c, inv = _grid()
+    sc = np.sort(c, -1).astype(np.float32)
+    out = _live.forward(spec, w, torch.from_numpy(sc).to(cuda), want=("u", "logdet", "logpdf", "psi"))
+    psi = out["psi"].cpu().numpy() * (-1.0) ** inv
+    assert np.abs(psi - gold["psi_grid"]).max() < 3e-5                 # |psi| up to 1.53
+    ref = live.psi(m64, params, sc.astype(np.float64)) * (-1.0) ** inv
+    e32 = np.abs(live.psi(fx.waveflow_model(2, dtype=np.float32), fx.cast_params(params, np.float32), sc) * (-1.0) ** inv - ref).max()
+    assert np.abs(psi - ref).max() < max(3e-5, 4 * e32)
+    assert relerr(psi, ref) < 1e-5                                     # 1e-5 relative to max|psi|
+    u64, ld64 = live.flow_direct(m64, params[0], sc.astype(np.float64))
+    assert np.abs(out["u"].cpu().numpy() - u64).max() < 2e-5
+    assert relerr(out["logdet"].cpu().numpy(), ld64, 1.0) < 1e-5
+    lp64 = live.log_pdf(m64, params, sc.astype(np.float64))
+    assert relerr(out["logpdf"].cpu().numpy(), lp64, 1.0) < 2e-5
+
+
+@pytest.mark.parametrize("D,coord", [(2, "mean"), (3, "mean"), (4, "mean"), (3, "first"), (4, "first")])
+def test_waveflow_forward_random_params(cuda, D, coord):
+    from waveflow_b200 import _live
+    m = fx.waveflow_model(D, coord=coord)
+    params = fx.random_params(np.random.default_rng(D), m, scale=3.0)
+    spec = spec_from_live(m)
+    w = _pack(spec, params, cuda)
+    x = np.sort(np.random.default_rng(1).uniform(-10, 10, (4001, D)), -1).astype(np.float32)
+    out = _live.forward(spec, w, torch.from_numpy(x).to(cuda), want=("u", "logdet", "logpdf", "psi"))
+    x64 = x.astype(np.float64)
+    assert relerr(out["psi"].cpu().numpy(), live.psi(m, params, x64)) < 1e-5
+    assert relerr(out["logpdf"].cpu().numpy(), live.log_pdf(m, params, x64), 1.0) < 2e-5
+    u64, ld64 = live.flow_direct(m, params[0], x64)
+    assert np.abs(out["u"].cpu().numpy() - u64).max() < 2e-5
+    assert relerr(out["logdet"].cpu().numpy(), ld64, 1.0) < 1e-5
+
+
+@pytest.mark.parametrize("bc", [({0: 0.0}, {0: 1.0}), ({}, {})])
+def test_mflow_log_pdf(cuda, bc):
+    """benchmark_tests.get_model('MFlow') shape: 3 x (IMADE, Reverse), I degree 5 / 23 knots, M prior degree 3 / 15 knots."""
+    from waveflow_b200 import _live
+    m = fx.mflow_model(bc_i_left=bc[0], bc_i_right=bc[1])
+    params = fx.random_params(np.random.default_rng(0), m, scale=3.0)
+    spec = spec_from_live(m)
+    w = _pack(spec, params, cuda)
+    x = np.random.default_rng(1).uniform(0.025, 0.975, (5000, 2)).astype(np.float32)
+    out = _live.forward(spec, w, torch.from_numpy(x).to(cuda), want=("u", "logdet", "logpdf"))
+    lp64, u64 = live.log_pdf(m, params, x.astype(np.float64), return_sample=True)
+    assert relerr(out["logpdf"].cpu().numpy(), lp64, 1.0) < 2e-5
+    assert np.abs(np.clip(out["u"].cpu().numpy(), 0, 1) - u64).max() < 2e-5
+
+
+def _check_energy(out, ref, tol_e=1e-4):
+    psi, hpsi, eloc = [out[k].cpu().numpy() for k in ("psi", "hpsi", "eloc")]
+    assert relerr(psi, ref["psi"]) < 1e-5
+    assert relerr(out["grad"].cpu().numpy(), ref["grad"]) < 2e-5
+    assert relerr(out["lap"].cpu().numpy(), ref["lap"]) < tol_e
+    assert relerr(hpsi, ref["hpsi"]) < tol_e
+    # E_loc = H psi / (psi + 1e-8): relative to |E_loc| wherever psi is not at a node, else to the batch scale
+    big = np.abs(ref["psi"]) > 1e-3 * np.abs(ref["psi"]).max()
+    assert np.max(np.abs(eloc - ref["eloc"])[big] / (np.abs(ref["eloc"])[big] + np.median(np.abs(ref["eloc"])))) < 10 * tol_e
+    return psi, eloc
+
+
+def test_local_energy_he_checkpoint(cuda):
+    from waveflow_b200 import _live
+    params, gold = fx.load_he_checkpoint()
+    m = fx.waveflow_model(2)
+    spec = spec_from_live(m)
+    w = _pack(spec, params, cuda)
+    prot = np.array([[0.0], [0.0]])
+    rng = np.random.default_rng(5)
+    x = np.concatenate([np.sort(gold["samples"], -1), np.sort(rng.uniform(-10, 10, (262, 2)), -1)]).astype(np.float32)
+    sums = torch.zeros(4, dtype=torch.float64, device=cuda)
+    out = _live.local_energy(spec, w, torch.from_numpy(x).to(cuda), prot, want=("psi", "hpsi", "eloc", "grad", "lap"), sums=sums)
+    ref = olap.local_energy_bundle(m, params, x.astype(np.float64), prot)
+    psi, eloc = _check_energy(out, ref)
+    s = sums.cpu().numpy()
+    assert s[2] == len(x)
+    assert abs(s[0] - eloc.astype(np.float64).sum()) <= 1e-6 * np.abs(eloc).sum()
+    assert abs(s[1] - (eloc.astype(np.float64) ** 2).sum()) <= 1e-6 * (eloc.astype(np.float64) ** 2).sum()
+    assert abs(s[3] - (psi.astype(np.float64) ** 2).sum()) <= 1e-6 * (psi.astype(np.float64) ** 2).sum()
+    # the forward kernel and the Laplacian kernel agree on psi
+    fw = _live.forward(spec, w, torch.from_numpy(x).to(cuda), want=("psi",))["psi"].cpu().numpy()
+    assert np.abs(fw - psi).max() <= 2e-6 * np.abs(psi).max()
+
+
+@pytest.mark.parametrize("D,coord,N", [(2, "mean", 1000), (3, "mean", 333), (4, "mean", 777), (4, "first", 100), (3, "first", 64)])
+def test_local_energy_random_params(cuda, D, coord, N):
+    from waveflow_b200 import _live
+    m = fx.waveflow_model(D, coord=coord)
+    params = fx.random_params(np.random.default_rng(10 + D), m, scale=2.0)
+    spec = spec_from_live(m)
+    w = _pack(spec, params, cuda)
+    prot = np.zeros((D, 1))
+    x = np.sort(np.random.default_rng(2).uniform(-10, 10, (N, D)), -1).astype(np.float32)
+    out = _live.local_energy(spec, w, torch.from_numpy(x).to(cuda), prot, want=("psi", "hpsi", "eloc", "grad", "lap"))
+    ref = olap.local_energy_bundle(m, params, x.astype(np.float64), prot)
+    _check_energy(out, ref)
+
+
+def test_local_energy_shard_equality(cuda):
+    """T5 (emulated ranks): evaluating disjoint row blocks separately gives bit-identical per-walker results and the
+    same estimator sums as one call over all walkers."""
+    from waveflow_b200 import _live
+    m = fx.waveflow_model(4)
+    params = fx.random_params(np.random.default_rng(1), m)
+    spec = spec_from_live(m)
+    w = _pack(spec, params, cuda)
+    prot = np.zeros((4, 1))
+    x = torch.from_numpy(np.sort(np.random.default_rng(3).uniform(-10, 10, (4096, 4)), -1).astype(np.float32)).to(cuda)
+    full_s = torch.zeros(4, dtype=torch.float64, device=cuda)
+    full = _live.local_energy(spec, w, x, prot, want=("eloc", "psi"), sums=full_s)
+    part_s = torch.zeros(4, dtype=torch.float64, device=cuda)
+    parts = [_live.local_energy(spec, w, x[r * 512:(r + 1) * 512].contiguous(), prot, want=("eloc", "psi"), sums=part_s) for r in range(8)]
+    assert torch.equal(torch.cat([p["eloc"] for p in parts]), full["eloc"])
+    assert torch.equal(torch.cat([p["psi"] for p in parts]), full["psi"])
+    assert torch.allclose(part_s, full_s, rtol=1e-12)

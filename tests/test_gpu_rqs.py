@@ -1,0 +1,86 @@
+"""T2: rational-quadratic spline operator parity (GPU through the C ABI vs the numpy restatement)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import rqs as orqs
+from tests.util import relerr
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(cuda, x, uw, uh, ud, inverse, B):
+    from waveflow_b200.flows.neural_splines import unconstrained_RQS
+    t = lambda a: torch.from_numpy(a).to(cuda)
+    out, lad, bins = unconstrained_RQS(t(x), t(uw), t(uh), t(ud), inverse=inverse, tail_bound=B, return_bin_idx=True)
+    return out.cpu().numpy(), lad.cpu().numpy(), bins.cpu().numpy()
+
+
+@pytest.mark.parametrize("K", [5, 8, 32, 64])
+def test_rqs_forward_inverse_parity(cuda, K):
+    rng = np.random.default_rng(K)
+    N, B = 50000, 3.0
+    x = rng.uniform(-4, 4, N).astype(np.float32)
+    x[:6] = [-3.0, 3.0, 0.0, -3.0000002, 3.0000002, 2.9999998]
+    uw, uh = rng.standard_normal((2, N, K)).astype(np.float32)
+    ud = rng.standard_normal((N, K - 1)).astype(np.float32)
+    d64 = lambda a: a.astype(np.float64)
+    for inverse in (False, True):
+        out, lad, bins = _run(cuda, x, uw, uh, ud, inverse, B)
+        ro, rl, rb = orqs.unconstrained_rqs(d64(x), d64(uw), d64(uh), d64(ud), inverse, B, return_bin=True)
+        # bin indices: bit-exact away from float32 knot rounding (|x - knot| > 1e-5)
+        cw, _ = orqs._knots(d64(uh if inverse else uw), -B, B, orqs.MIN_BIN_WIDTH)
+        near = np.min(np.abs(cw - d64(x)[:, None]), axis=-1) < 1e-5
+        inside = (x >= -B) & (x <= B)
+        assert np.array_equal(bins[~near | ~inside], rb[~near | ~inside])
+        assert near.mean() < 1e-3
+        assert np.all(bins[~inside] == -1) and np.all(out[~inside] == x[~inside]) and np.all(lad[~inside] == 0)
+        ok = ~near
+        assert relerr(out[ok], ro[ok], B) < 1e-5
+        assert relerr(lad[ok], rl[ok], 1.0) < 2e-5
+
+
+def test_rqs_bins_bit_exact_on_exact_knots(cuda):
+    """Uniform bins (all unnormalised parameters equal): the float32 knot positions are reproduced operation by operation
+    (sequential cumsum, neural_splines.py:98-107), so the located bin must equal the float32 oracle's everywhere."""
+    rng = np.random.default_rng(0)
+    N, K, B = 200000, 32, 3.0
+    uw = np.zeros((N, K), dtype=np.float32); uh = np.zeros((N, K), dtype=np.float32)
+    ud = rng.standard_normal((N, K - 1)).astype(np.float32)
+    cw, _ = orqs._knots(uw[:1], -B, B, orqs.MIN_BIN_WIDTH)
+    x = rng.uniform(-B, B, N).astype(np.float32)
+    kn = cw[0]
+    x[:K + 1] = kn                                                # exactly on the knots
+    x[K + 1:2 * K + 2] = np.nextafter(kn, np.float32(-10))          # one ulp below
+    x[2 * K + 2:3 * K + 3] = np.nextafter(kn, np.float32(10))       # one ulp above
+    x = np.clip(x, -B, B)
+    for inverse in (False, True):
+        _, _, bins = _run(cuda, x, uw, uh, ud, inverse, B)
+        _, _, rb = orqs.unconstrained_rqs(x, uw, uh, ud, inverse, B, return_bin=True)
+        assert np.array_equal(bins, rb)
+
+
+def test_rqs_round_trip_and_monotone(cuda):
+    rng = np.random.default_rng(1)
+    N, K, B = 1 << 18, 32, 3.0
+    x = np.sort(rng.uniform(-B, B, N).astype(np.float32))
+    uw = np.tile(rng.standard_normal((1, K)).astype(np.float32), (N, 1))
+    uh = np.tile(rng.standard_normal((1, K)).astype(np.float32), (N, 1))
+    ud = np.tile(rng.standard_normal((1, K - 1)).astype(np.float32), (N, 1))
+    y, l1, b1 = _run(cuda, x, uw, uh, ud, False, B)
+    x2, l2, b2 = _run(cuda, y, uw, uh, ud, True, B)
+    assert np.all(np.diff(y) >= -1e-6)                              # monotone map
+    assert np.abs(x2 - x).max() < 2e-4 and np.median(np.abs(x2 - x)) < 1e-6
+    assert np.abs(l1 + l2).max() < 1e-3
+    assert np.mean(b1 == b2) > 0.999
+
+
+def test_rqs_argument_errors(cuda):
+    from waveflow_b200 import _ffi
+    from waveflow_b200.flows.neural_splines import unconstrained_RQS
+    z = torch.zeros(4, device=cuda)
+    with pytest.raises(_ffi.WaveflowB200Error):
+        unconstrained_RQS(z, torch.zeros(4, 128, device=cuda), torch.zeros(4, 128, device=cuda), torch.zeros(4, 127, device=cuda))
+    out, lad = unconstrained_RQS(torch.zeros(0, device=cuda), torch.zeros(0, 8, device=cuda), torch.zeros(0, 8, device=cuda),
+                                 torch.zeros(0, 7, device=cuda))
+    assert out.shape == (0,)

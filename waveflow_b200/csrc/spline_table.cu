@@ -19,10 +19,13 @@ extern "C" int wf_table_layout_host(const float* tab, int kind, int P, int T, fl
   }
   if (!rec && !lo) return WF_OK;
   if (!rec || !lo) return WF_ERR_INVALID_ARG;
-  // pass 1: windows
+  // pass 1: per node, the admissible range [lo_min, lo_max] of the window start: every entry that differs from the
+  // prefix value / from zero must fall inside [lo, lo + WF_WIN - 1) (one slot is kept spare for the one-basis shift).
   int32_t* lo_tmp = new int32_t[T];
+  int32_t* lo_min = new int32_t[T];
+  int32_t* lo_max = new int32_t[T];
   int status = WF_OK;
-  for (int m = 0; m < T && status == WF_OK; ++m) {
+  for (int m = 0; m < T; ++m) {
     int first = P, last = -1;
     for (int q = 0; q < P; ++q) {
       bool trivial_prefix = true, zero = true;
@@ -33,17 +36,24 @@ extern "C" int wf_table_layout_host(const float* tab, int kind, int P, int T, fl
         if (v != 0.0f) zero = false;
       }
       if (!trivial_prefix && first == P) first = q;
-      if (!zero && !(q < first)) last = q;
+      if (!zero && first != P) last = q;
     }
-    if (first == P) first = (last >= 0) ? last : 0;  // node where everything is prefix/zero
-    // all bases beyond the window must be exactly zero, and bases before it exactly the prefix value
-    if (last - first + 1 > WF_WIN - 1) status = WF_ERR_UNSUPPORTED;
-    lo_tmp[m] = first;
+    if (first == P) { first = P - 1; last = P - 1; }
+    if (last < first) last = first;
+    lo_max[m] = first;
+    lo_min[m] = last - (WF_WIN - 2) > 0 ? last - (WF_WIN - 2) : 0;
+    if (lo_min[m] > lo_max[m]) status = WF_ERR_UNSUPPORTED;
   }
-  for (int m = 0; m + 1 < T && status == WF_OK; ++m) {
-    const int s = lo_tmp[m + 1] - lo_tmp[m];
-    if (s < 0 || s > 1) status = WF_ERR_UNSUPPORTED;
+  // pass 2: a non-decreasing sequence with steps of at most one basis
+  for (int m = 0; m < T && status == WF_OK; ++m) {
+    int v = m == 0 ? lo_min[0] : lo_tmp[m - 1];
+    if (v < lo_min[m]) v = lo_min[m];
+    if (v > lo_max[m]) v = lo_max[m];
+    if (m > 0 && (v - lo_tmp[m - 1] < 0 || v - lo_tmp[m - 1] > 1)) status = WF_ERR_UNSUPPORTED;
+    lo_tmp[m] = v;
   }
+  delete[] lo_min;
+  delete[] lo_max;
   if (status == WF_OK) {
     for (int m = 0; m < T; ++m) {
       lo[m] = lo_tmp[m];
