@@ -4,7 +4,7 @@ import pytest
 import torch
 
 from oracle import rqs as orqs
-from tests.util import relerr
+from tests.util import assert_fp32_grade, relerr
 
 pytestmark = pytest.mark.gpu
 
@@ -35,9 +35,10 @@ def test_rqs_forward_inverse_parity(cuda, K):
         assert np.array_equal(bins[~near | ~inside], rb[~near | ~inside])
         assert near.mean() < 1e-3
         assert np.all(bins[~inside] == -1) and np.all(out[~inside] == x[~inside]) and np.all(lad[~inside] == 0)
-        ok = ~near
-        assert relerr(out[ok], ro[ok], B) < 1e-5
-        assert relerr(lad[ok], rl[ok], 1.0) < 2e-5
+        o32, l32, b32 = orqs.unconstrained_rqs(x, uw, uh, ud, inverse, B, return_bin=True)
+        ok = ~near & (b32 == rb)
+        assert_fp32_grade(out[ok], ro[ok], o32[ok], 1e-5, B, "outputs")
+        assert_fp32_grade(lad[ok], rl[ok], l32[ok], 1e-5, 1.0, "logabsdet")
 
 
 def test_rqs_bins_bit_exact_on_exact_knots(cuda):

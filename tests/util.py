@@ -34,3 +34,18 @@ def spec_from_live(m):
     return LiveSpec(D=m.D, n_layers=m.n_layers, tab_I=tI, k_I=m.k_i, reg=m.reg, tol=m.tol, bc_I_left=m.bc_i_left,
                     bc_I_right=m.bc_i_right, prior=prior, tab_P=tP, k_P=m.k_p, bc_P_left=m.bc_p_left,
                     bc_P_right=m.bc_p_right, box=m.box, coord=m.coord)
+
+
+def assert_fp32_grade(got, ref64, ref32, rtol, scale=None, name=""):
+    """The GPU result must agree with the float64 oracle to `rtol` (relative to |ref| + scale) -- or, where float32
+    arithmetic itself cannot (ill-conditioned points: log(p + 1e-7) next to a node of psi, log-dets of tiny bins), be as
+    accurate as the reference's own float32 arithmetic, i.e. the numpy restatement run in float32 (`ref32`):
+    median, 99th percentile and maximum error at most 2x / 2x / 4x those of the float32 restatement."""
+    got, ref64, ref32 = [np.asarray(a, dtype=np.float64) for a in (got, ref64, ref32)]
+    s = np.abs(ref64).max() if scale is None else scale
+    eg = np.abs(got - ref64) / (np.abs(ref64) + s)
+    eo = np.abs(ref32 - ref64) / (np.abs(ref64) + s)
+    assert np.all(np.isfinite(got)), name
+    assert np.median(eg) <= max(rtol / 10, 2 * np.median(eo)), (name, "median", np.median(eg), np.median(eo))
+    assert np.quantile(eg, 0.99) <= max(rtol, 2 * np.quantile(eo, 0.99)), (name, "p99", np.quantile(eg, 0.99), np.quantile(eo, 0.99))
+    assert eg.max() <= max(rtol, 4 * eo.max()), (name, "max", eg.max(), eo.max())

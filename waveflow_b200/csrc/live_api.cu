@@ -62,6 +62,7 @@ int dispatch(LiveParams& P, bool lap, void* stream) {
 extern "C" int wf_live_forward(const wf_live_model* model, const float* weights, const float* tab_I, const float* tab_P,
                                const float* ob_to_b, const float* x, int64_t N, float* u, float* logdet, float* logpdf,
                                float* psi, void* stream) {
+  if (N == 0) return WF_OK;   // empty batch: nothing to do (pointers of empty buffers may be NULL)
   LiveParams P;
   const int st = fill_params(model, weights, tab_I, tab_P, ob_to_b, x, N, P);
   if (st != WF_OK) return st;
@@ -74,6 +75,7 @@ extern "C" int wf_live_forward(const wf_live_model* model, const float* weights,
 extern "C" int wf_local_energy(const wf_live_model* model, const float* weights, const float* tab_I, const float* tab_P,
                                const float* ob_to_b, const float* protons, int n_protons, const float* x, int64_t N,
                                float* psi, float* hpsi, float* eloc, float* grad, float* lap, double* sums, void* stream) {
+  if (N == 0) return WF_OK;   // empty batch: nothing to do (pointers of empty buffers may be NULL)
   LiveParams P;
   const int st = fill_params(model, weights, tab_I, tab_P, ob_to_b, x, N, P);
   if (st != WF_OK) return st;

@@ -50,6 +50,7 @@ static int launch_rqs(const float* inputs, const float* uw, const float* uh, con
 extern "C" int wf_rqs_apply(const float* inputs, const float* uw, const float* uh, const float* ud, int64_t M, int K,
                             float tail_bound, int inverse, float* outputs, float* logabsdet, int32_t* bin_idx,
                             void* stream) {
+  if (M == 0) return WF_OK;   // empty batch: nothing to do (pointers of empty buffers may be NULL)
   if (!inputs || !uw || !uh || !ud || !outputs || !logabsdet || M < 0 || K < 2 || !(tail_bound > 0.f)) return WF_ERR_INVALID_ARG;
   if (K > 64) return WF_ERR_UNSUPPORTED;
   // neural_splines.py:93-96

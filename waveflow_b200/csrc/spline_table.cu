@@ -102,6 +102,7 @@ __global__ void __launch_bounds__(256) spline_dense_kernel(const float* __restri
 
 extern "C" int wf_spline_apply_dense(const float* dense_t, int T, int P, const float* c, const float* x, int64_t M,
                                      int nd0, int n_out, float* const* out_host, float* out_logd, void* stream) {
+  if (M == 0) return WF_OK;   // empty batch: nothing to do (pointers of empty buffers may be NULL)
   if (!dense_t || !c || !x || !out_host || T < 2 || P < 1 || P > 64 || M < 0 || n_out < 1 || n_out > 4 || nd0 < 0)
     return WF_ERR_INVALID_ARG;
   if (out_logd && n_out < 2) return WF_ERR_INVALID_ARG;
@@ -253,6 +254,7 @@ spline_local_kernel(const float* __restrict__ rec, const int32_t* __restrict__ l
 extern "C" int wf_spline_apply_local(const float* rec, const int32_t* lo, const float* dense_t, int kind, int T, int P,
                                      const float* c, const float* x, int64_t M, float* out_val, float* out_grad,
                                      float* out_logd, void* stream) {
+  if (M == 0) return WF_OK;   // empty batch: nothing to do (pointers of empty buffers may be NULL)
   if (!rec || !lo || !dense_t || !c || !x || T < 2 || P < 1 || P > 64 || M < 0) return WF_ERR_INVALID_ARG;
   if (kind != WF_KIND_I && kind != WF_KIND_M && kind != WF_KIND_B) return WF_ERR_INVALID_ARG;
   if ((reinterpret_cast<uintptr_t>(c) & 15) || (reinterpret_cast<uintptr_t>(rec) & 15)) return WF_ERR_INVALID_ARG;
@@ -307,6 +309,7 @@ __global__ void __launch_bounds__(128) bspline_apply_kernel(const float* __restr
 
 extern "C" int wf_bspline_apply(const float* ob_dense_t, const float* ob_to_b, int T, int P, const float* w,
                                 const float* x, int64_t M, int nd, float* out, void* stream) {
+  if (M == 0) return WF_OK;   // empty batch: nothing to do (pointers of empty buffers may be NULL)
   if (!ob_dense_t || !ob_to_b || !w || !x || !out || T < 2 || P < 1 || P > 64 || M < 0 || nd < 0) return WF_ERR_INVALID_ARG;
   if (M == 0) return WF_OK;
   const int threads = 128;
@@ -341,6 +344,7 @@ __global__ void __launch_bounds__(256) remove_bias_kernel(int kind, int k, int P
 }
 
 extern "C" int wf_remove_bias(int kind, int k, int P, const float* p, int64_t M, float* out, void* stream) {
+  if (M == 0) return WF_OK;   // empty batch: nothing to do (pointers of empty buffers may be NULL)
   if (!p || !out || P < 1 || P > 64 || k < 0 || M < 0 || (kind != WF_KIND_I && kind != WF_KIND_M)) return WF_ERR_INVALID_ARG;
   if (M == 0) return WF_OK;
   const int64_t want = (M + 255) / 256;
@@ -392,6 +396,7 @@ __global__ void __launch_bounds__(256) enforce_bc_kernel(int kind, int P, BcSpec
 extern "C" int wf_enforce_bc(int kind, int P, int n_left, const int* nd_left, const float* val_left,
                              const float* bv_left, int n_right, const int* nd_right, const float* val_right,
                              const float* bv_right, const float* w, int64_t M, float* out, void* stream) {
+  if (M == 0) return WF_OK;   // empty batch: nothing to do (pointers of empty buffers may be NULL)
   if (!w || !out || P < 1 || P > 64 || M < 0 || n_left < 0 || n_left > 4 || n_right < 0 || n_right > 4) return WF_ERR_INVALID_ARG;
   if (kind != WF_KIND_I && kind != WF_KIND_M && kind != WF_KIND_B) return WF_ERR_INVALID_ARG;
   BcSpec bc;
@@ -451,6 +456,7 @@ __global__ void __launch_bounds__(128) spline_reverse_kernel(const float* __rest
 
 extern "C" int wf_spline_reverse(const float* dense_t, int T, int P, const float* c, const float* y, int64_t M,
                                  float tol, float* out, int32_t* n_iter, void* stream) {
+  if (M == 0) return WF_OK;   // empty batch: nothing to do (pointers of empty buffers may be NULL)
   if (!dense_t || !c || !y || !out || T < 2 || P < 1 || P > 64 || M < 0 || !(tol > 0.f)) return WF_ERR_INVALID_ARG;
   if (M == 0) return WF_OK;
   const int64_t want = (M + 127) / 128;
