@@ -44,6 +44,9 @@ int wf_abi_version(int* sm_arch);
 /* Human-readable text for a status code returned by any wf_* call (static storage). */
 const char* wf_status_string(int status);
 
+/* Measurement aid (bench.py): runs an FFMA-only loop, 2 * 8 * iters * blocks * 256 FLOPs, to time the FP32 ceiling. */
+int wf_probe_fma(int iters, int blocks, float* out, void* stream);
+
 /* ------------------------------------------------------------------------------------------------------------------
  * Table layouts (host helper, pure C, no CUDA): converts the reference layout tab[4][P][T] (float32) to
  *   dense_t  [T][4][PP]      PP = P rounded up to a multiple of 4, zero padded   (transposed: one node = one row)

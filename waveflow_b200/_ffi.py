@@ -52,6 +52,7 @@ _f = C.c_float
 _SIGS = {
     "wf_abi_version": (C.c_int, [C.POINTER(C.c_int)]),
     "wf_status_string": (C.c_char_p, [_i]),
+    "wf_probe_fma": (_i, [_i, _i, _p, _p]),
     "wf_table_layout_host": (_i, [_p, _i, _i, _i, _p, _p, _p]),
     "wf_spline_apply_dense": (_i, [_p, _i, _i, _p, _p, _l, _i, _i, C.POINTER(_p), _p, _p]),
     "wf_spline_apply_local": (_i, [_p, _p, _p, _i, _i, _i, _p, _p, _l, _p, _p, _p, _p]),

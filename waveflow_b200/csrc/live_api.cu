@@ -26,11 +26,12 @@ void coeff_weights(int kind, int k, int P, int bc_bits, bool with_bias, float* w
 
 int fill_params(const wf_live_model* m, const float* weights, const float* tab_I, const float* tab_P,
                 const float* ob_to_b, const float* x, int64_t N, LiveParams& P) {
-  if (!m || !weights || !tab_I || !x || N < 0) return WF_ERR_INVALID_ARG;
+  if (!m || !tab_I || !x || N < 0) return WF_ERR_INVALID_ARG;
   if (m->D < 2 || m->D > WF_MAX_D || m->n_layers < 0 || m->n_layers > WF_MAX_LAYERS || m->T < 2) return WF_ERR_INVALID_ARG;
   if (m->P_I < 2 || m->P_I > WF_MAX_P || m->k_I < 0) return WF_ERR_INVALID_ARG;
   if (m->D > 4) return WF_ERR_UNSUPPORTED;
   const bool pnet = m->prior_kind == WF_KIND_B || m->prior_kind == WF_KIND_M;
+  if (!weights && (m->n_layers > 0 || pnet)) return WF_ERR_INVALID_ARG;
   if (m->prior_kind != -1 && !pnet) return WF_ERR_INVALID_ARG;
   if (pnet && (!tab_P || m->P_P < 2 || m->P_P > WF_MAX_P)) return WF_ERR_INVALID_ARG;
   if (m->prior_kind == WF_KIND_B && !ob_to_b) return WF_ERR_INVALID_ARG;
