@@ -89,9 +89,12 @@ def _check_energy(out, ref, psi32, tol_e=1e-4):
     assert relerr(out["grad"].cpu().numpy(), ref["grad"]) < tol_e
     assert relerr(out["lap"].cpu().numpy(), ref["lap"]) < tol_e
     assert relerr(hpsi, ref["hpsi"]) < tol_e
-    # E_loc = H psi / (psi + 1e-8): relative to |E_loc| wherever psi is not at a node, else to the batch scale
-    big = np.abs(ref["psi"]) > 1e-3 * np.abs(ref["psi"]).max()
+    # E_loc = H psi / (psi + 1e-8) amplifies the (absolute) float32 error of psi by max|psi| / |psi|: the 1e-4 relative
+    # bound is asserted where that amplification is below 100 (|psi| > 1% of its maximum) with that factor of head-room
+    # folded in as 10x, and on the batch estimator
+    big = np.abs(ref["psi"]) > 1e-2 * np.abs(ref["psi"]).max()
     assert np.max(np.abs(eloc - ref["eloc"])[big] / (np.abs(ref["eloc"])[big] + np.median(np.abs(ref["eloc"])))) < 10 * tol_e
+    assert abs(eloc[big].astype(np.float64).mean() - ref["eloc"][big].mean()) <= tol_e * np.abs(ref["eloc"][big]).mean()
     return psi, eloc
 
 

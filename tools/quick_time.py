@@ -10,6 +10,7 @@ from waveflow_b200.flows.neural_splines import unconstrained_RQS
 
 dev = torch.device("cuda:0")
 res = {}
+ONLY = sys.argv[1] if len(sys.argv) > 1 else "all"
 
 def timeit(fn, n=10, warm=3):
     for _ in range(warm): fn()
@@ -23,7 +24,7 @@ def timeit(fn, n=10, warm=3):
 
 # 1. table spline operator
 tabs = SplineTables.get("I", 6, 23)
-for logM in (22, 24):
+for logM in ((22, 24) if ONLY in ("all", "spline") else ()):
     M = 1 << logM
     c = torch.rand(M, 29, device=dev); c = c / c.sum(-1, keepdim=True)
     x = torch.rand(M, device=dev)
@@ -34,7 +35,7 @@ for logM in (22, 24):
         res[f"spline_dense_M2^{logM}"] = dict(ms=med, GBs=M * 128 / med / 1e6)
     del c, x
 # 2. rqs operator
-for K in (32, 64):
+for K in ((32, 64) if ONLY in ("all", "rqs") else ()):
     M = 1 << 22
     uw, uh = torch.randn(M, K, device=dev), torch.randn(M, K, device=dev); ud = torch.randn(M, K - 1, device=dev)
     x = (torch.rand(M, device=dev) * 6 - 3)
@@ -46,7 +47,7 @@ for K in (32, 64):
 sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
 from oracle import fixtures as fx
 from tests.util import spec_from_live
-for D in (2, 4):
+for D in ((2, 4) if ONLY in ("all", "live") else ()):
     m = fx.waveflow_model(D)
     params = fx.random_params(np.random.default_rng(0), m)
     spec = spec_from_live(m)

@@ -74,7 +74,7 @@ def spline_apply(tabs: SplineTables, c: torch.Tensor, x: torch.Tensor, nd0: int 
     outs = [torch.empty(M, dtype=torch.float32, device=c.device) for _ in range(n_out)]
     lg = torch.empty(M, dtype=torch.float32, device=c.device) if logd else None
     local_ok = (not force_dense and dense_key == "dense" and d["rec"] is not None and nd0 == 0 and n_out <= 2
-                and c.data_ptr() % 16 == 0)
+                and c.data_ptr() % 16 == 0 and x.data_ptr() % 16 == 0)
     if local_ok:
         st = lib.wf_spline_apply_local(ptr(d["rec"]), ptr(d["lo"]), ptr(d["dense"]), _ffi.KIND[tabs.kind], tabs.T, P,
                                        ptr(c), ptr(x), M, ptr(outs[0]), ptr(outs[1]) if n_out > 1 else None, ptr(lg),
