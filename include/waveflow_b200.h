@@ -131,34 +131,46 @@ typedef struct wf_live_model {
   float reserved;
 } wf_live_model;
 
+/* Device-resident basis tables of a model (a HOST struct of DEVICE pointers), all produced by wf_table_layout_host:
+ *   dense_* [T][4][32]  transposed tables zero-padded to WF_MAX_P bases; rec_* [T][4][8] / lo_* [T] the compact
+ *   local-support records.  *_I: I-spline tables of the flow layers.  *_P: prior tables -- for the B prior dense_P holds
+ *   the ORTHONORMALISED tables (bsplines_jax.py:98-106) and rec_P/lo_P are unused (NULL); for the M prior all three are
+ *   the M-spline tables.  ob_to_b [P_P][P_P] row-major (B prior only). */
+typedef struct wf_live_tables {
+  const float* dense_I;
+  const float* rec_I;
+  const int32_t* lo_I;
+  const float* dense_P;
+  const float* rec_P;
+  const int32_t* lo_P;
+  const float* ob_to_b;
+} wf_live_tables;
+
 /* Packed weights (device, float32), one block per conditioner, IMADE nets first then the prior net; per net
  *   W1m [D][64] | b1 [64] | W2m [64][64] | b2 [64] | W3p [64][D][32] | b3p [D][32]
  * W*m have the MADE masks already applied (model_factory.py:8-19,31-33); W3p/b3p are the third layer re-ordered so
  * that the P coefficients of dimension d are contiguous (p[n,d,q] = o[n, q*D + d], model_factory.py:59-60) and padded
- * with zeros to 32.  Size per net: wf_live_net_floats(D). */
+ * with zeros to 32.  Size per net: wf_live_net_floats(D).  The buffer must be 16-byte aligned. */
 int64_t wf_live_net_floats(int D);
 
-/* Outputs selector bits of wf_live_forward */
-#define WF_OUT_U 1        /* u [N][D]: flow output in the unit cube (Serial.direct_fun)                            */
-#define WF_OUT_LOGDET 2   /* log|det J| [N]                                                                         */
-#define WF_OUT_LOGPDF 4   /* MFlow.log_pdf / Waveflow.log_pdf [N] (distributions.py:139-163, wavefunctions.py:33-52) */
-#define WF_OUT_PSI 8      /* Waveflow.psi [N] (wavefunctions.py:54-71)                                              */
-
-/* Fused forward pass: BoxTransformLayer -> (IMADE, Reverse) x L -> prior, one thread per sample, no intermediate leaves
- * the SM.  tab_I / tab_P are [T][4][32] dense_t layouts (WF_MAX_P padded); for the B prior tab_P is the OB table and
- * ob_to_b [P_P][P_P].  Any of the outputs may be NULL. */
-int wf_live_forward(const wf_live_model* model_host, const float* weights, const float* tab_I, const float* tab_P,
-                    const float* ob_to_b, const float* x, int64_t N, float* u, float* logdet, float* logpdf,
-                    float* psi, void* stream);
+/* Outputs selector: any of the output pointers of wf_live_forward may be NULL.
+ *   u [N][D]     flow output in the unit cube (Serial.direct_fun, bijections.py:452-460)
+ *   logdet [N]   log|det J|
+ *   logpdf [N]   MFlow.log_pdf / Waveflow.log_pdf (distributions.py:139-163, wavefunctions.py:33-52)
+ *   psi [N]      Waveflow.psi (wavefunctions.py:54-71), B prior only
+ * Fused forward pass: BoxTransformLayer -> (IMADE, Reverse) x L -> prior, one thread per sample, no intermediate leaves
+ * the SM; conditioner weights stream through shared memory with cp.async.bulk (TMA). */
+int wf_live_forward(const wf_live_model* model_host, const wf_live_tables* tables_host, const float* weights,
+                    const float* x, int64_t N, float* u, float* logdet, float* logpdf, float* psi, void* stream);
 
 /* Local energy with a fused forward-mode Laplacian (replaces jax.hessian in utils/physics.py:50-52,79-93 and the
  * E_loc of vqmc.py:198-200):  psi, H psi = -1/2 lap psi + V psi, E_loc = H psi / (psi + 1e-8), with V the soft-Coulomb
- * potential of physics.py:60-76 for `n_protons` protons at positions protons[n_protons] (1 space dimension).
+ * potential of physics.py:60-76 for `n_protons` protons at positions protons_host[n_protons] (1 space dimension).
  * Optional outputs (nullable): psi[N], hpsi[N], eloc[N], grad[N][D] (d psi / dx), lap[N].
  * sums (nullable, double[4], must be zeroed by the caller): += {sum E_loc, sum E_loc^2, count, sum psi^2}. */
-int wf_local_energy(const wf_live_model* model_host, const float* weights, const float* tab_I, const float* tab_P,
-                    const float* ob_to_b, const float* protons, int n_protons, const float* x, int64_t N, float* psi,
-                    float* hpsi, float* eloc, float* grad, float* lap, double* sums, void* stream);
+int wf_local_energy(const wf_live_model* model_host, const wf_live_tables* tables_host, const float* weights,
+                    const float* protons_host, int n_protons, const float* x, int64_t N, float* psi, float* hpsi,
+                    float* eloc, float* grad, float* lap, double* sums, void* stream);
 
 #ifdef __cplusplus
 }

@@ -34,6 +34,11 @@ class LiveModelStruct(C.Structure):
                 ("reg", C.c_float), ("tol", C.c_float), ("reserved", C.c_float)]
 
 
+class LiveTablesStruct(C.Structure):
+    """struct wf_live_tables (include/waveflow_b200.h): device pointers."""
+    _fields_ = [(n, C.c_void_p) for n in ("dense_I", "rec_I", "lo_I", "dense_P", "rec_P", "lo_P", "ob_to_b")]
+
+
 def _load() -> C.CDLL:
     if not LIB_PATH.exists():
         if os.environ.get("WAVEFLOW_B200_NO_AUTOBUILD"):
@@ -62,8 +67,9 @@ _SIGS = {
     "wf_spline_reverse": (_i, [_p, _i, _i, _p, _p, _l, _f, _p, _p, _p]),
     "wf_rqs_apply": (_i, [_p, _p, _p, _p, _l, _i, _f, _i, _p, _p, _p, _p]),
     "wf_live_net_floats": (_l, [_i]),
-    "wf_live_forward": (_i, [C.POINTER(LiveModelStruct), _p, _p, _p, _p, _p, _l, _p, _p, _p, _p, _p]),
-    "wf_local_energy": (_i, [C.POINTER(LiveModelStruct), _p, _p, _p, _p, _p, _i, _p, _l, _p, _p, _p, _p, _p, _p, _p]),
+    "wf_live_forward": (_i, [C.POINTER(LiveModelStruct), C.POINTER(LiveTablesStruct), _p, _p, _l, _p, _p, _p, _p, _p]),
+    "wf_local_energy": (_i, [C.POINTER(LiveModelStruct), C.POINTER(LiveTablesStruct), _p, _p, _i, _p, _l, _p, _p, _p, _p, _p,
+                             _p, _p]),
 }
 for _name, (_res, _args) in _SIGS.items():
     _fn = getattr(lib, _name)

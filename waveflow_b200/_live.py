@@ -135,15 +135,19 @@ def pack_params(spec: LiveSpec, transform_params, sp_params, device) -> torch.Te
     return torch.cat(parts).contiguous()
 
 
-def _tables(spec: LiveSpec, device):
-    tI = spec.tab_I.dev(device)["dense32"]
-    tP = ob = None
+def _tables(spec: LiveSpec, device) -> _ffi.LiveTablesStruct:
+    """struct wf_live_tables for this model on `device` (the tensors are cached in SplineTables.dev)."""
+    t = _ffi.LiveTablesStruct()
+    dI = spec.tab_I.dev(device)
+    p = lambda x: None if x is None else x.data_ptr()
+    t.dense_I, t.rec_I, t.lo_I = p(dI["dense32"]), p(dI["rec"]), p(dI["lo"])
     if spec.prior == "B":
-        tP = spec.tab_P.dev(device)["ob_dense32"]
-        ob = spec.tab_P.dev(device)["ob_to_b"]
+        dP = spec.tab_P.dev(device)
+        t.dense_P, t.ob_to_b = p(dP["ob_dense32"]), p(dP["ob_to_b"])
     elif spec.prior == "M":
-        tP = spec.tab_P.dev(device)["dense32"]
-    return tI, tP, ob
+        dP = spec.tab_P.dev(device)
+        t.dense_P, t.rec_P, t.lo_P = p(dP["dense32"]), p(dP["rec"]), p(dP["lo"])
+    return t
 
 
 def forward(spec: LiveSpec, weights: torch.Tensor, x: torch.Tensor, want=("u", "logdet")):
@@ -151,16 +155,15 @@ def forward(spec: LiveSpec, weights: torch.Tensor, x: torch.Tensor, want=("u", "
     x = _ffi.f32(x)
     N = x.shape[0]
     dev = x.device
-    tI, tP, ob = _tables(spec, dev)
+    tabs = _tables(spec, dev)
     out = {}
     if "u" in want:
         out["u"] = torch.empty(N, spec.D, dtype=torch.float32, device=dev)
     for k in ("logdet", "logpdf", "psi"):
         if k in want:
             out[k] = torch.empty(N, dtype=torch.float32, device=dev)
-    st = lib.wf_live_forward(C.byref(spec.struct()), ptr(weights), ptr(tI), ptr(tP), ptr(ob), ptr(x), N,
-                             ptr(out.get("u")), ptr(out.get("logdet")), ptr(out.get("logpdf")), ptr(out.get("psi")),
-                             stream_ptr())
+    st = lib.wf_live_forward(C.byref(spec.struct()), C.byref(tabs), ptr(weights), ptr(x), N, ptr(out.get("u")),
+                             ptr(out.get("logdet")), ptr(out.get("logpdf")), ptr(out.get("psi")), stream_ptr())
     check(st, "wf_live_forward")
     return out
 
@@ -171,7 +174,7 @@ def local_energy(spec: LiveSpec, weights: torch.Tensor, x: torch.Tensor, protons
     x = _ffi.f32(x)
     N = x.shape[0]
     dev = x.device
-    tI, tP, ob = _tables(spec, dev)
+    tabs = _tables(spec, dev)
     prot = _ffi.host_f32(np.asarray(protons, dtype=np.float32).reshape(-1))
     out = {}
     for k in ("psi", "hpsi", "eloc", "lap"):
@@ -181,8 +184,8 @@ def local_energy(spec: LiveSpec, weights: torch.Tensor, x: torch.Tensor, protons
         out["grad"] = torch.empty(N, spec.D, dtype=torch.float32, device=dev)
     if sums is not None and (sums.dtype != torch.float64 or sums.numel() != 4):
         raise _ffi.WaveflowB200Error("sums must be a float64 tensor with 4 elements")
-    st = lib.wf_local_energy(C.byref(spec.struct()), ptr(weights), ptr(tI), ptr(tP), ptr(ob), _ffi.np_ptr(prot),
-                             int(prot.size), ptr(x), N, ptr(out.get("psi")), ptr(out.get("hpsi")), ptr(out.get("eloc")),
-                             ptr(out.get("grad")), ptr(out.get("lap")), ptr(sums), stream_ptr())
+    st = lib.wf_local_energy(C.byref(spec.struct()), C.byref(tabs), ptr(weights), _ffi.np_ptr(prot), int(prot.size), ptr(x),
+                             N, ptr(out.get("psi")), ptr(out.get("hpsi")), ptr(out.get("eloc")), ptr(out.get("grad")),
+                             ptr(out.get("lap")), ptr(sums), stream_ptr())
     check(st, "wf_local_energy")
     return out

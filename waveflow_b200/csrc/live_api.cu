@@ -24,24 +24,28 @@ void coeff_weights(int kind, int k, int P, int bc_bits, bool with_bias, float* w
   if (bc_bits & 2) w[P - 1] = 0.f;
 }
 
-int fill_params(const wf_live_model* m, const float* weights, const float* tab_I, const float* tab_P,
-                const float* ob_to_b, const float* x, int64_t N, LiveParams& P) {
-  if (!m || !tab_I || !x || N < 0) return WF_ERR_INVALID_ARG;
+int fill_params(const wf_live_model* m, const wf_live_tables* t, const float* weights, const float* x, int64_t N,
+                LiveParams& P) {
+  if (!m || !t || !t->dense_I || !x || N < 0) return WF_ERR_INVALID_ARG;
   if (m->D < 2 || m->D > WF_MAX_D || m->n_layers < 0 || m->n_layers > WF_MAX_LAYERS || m->T < 2) return WF_ERR_INVALID_ARG;
   if (m->P_I < 2 || m->P_I > WF_MAX_P || m->k_I < 0) return WF_ERR_INVALID_ARG;
   if (m->D > 4) return WF_ERR_UNSUPPORTED;
   const bool pnet = m->prior_kind == WF_KIND_B || m->prior_kind == WF_KIND_M;
   if (!weights && (m->n_layers > 0 || pnet)) return WF_ERR_INVALID_ARG;
+  if (m->n_layers > 0 && (!t->rec_I || !t->lo_I)) return WF_ERR_INVALID_ARG;
   if (m->prior_kind != -1 && !pnet) return WF_ERR_INVALID_ARG;
-  if (pnet && (!tab_P || m->P_P < 2 || m->P_P > WF_MAX_P)) return WF_ERR_INVALID_ARG;
-  if (m->prior_kind == WF_KIND_B && !ob_to_b) return WF_ERR_INVALID_ARG;
+  if (pnet && (!t->dense_P || m->P_P < 2 || m->P_P > WF_MAX_P)) return WF_ERR_INVALID_ARG;
+  if (m->prior_kind == WF_KIND_B && !t->ob_to_b) return WF_ERR_INVALID_ARG;
+  if (m->prior_kind == WF_KIND_M && (!t->rec_P || !t->lo_P)) return WF_ERR_INVALID_ARG;
   if (m->has_box && !(m->box > 0.f)) return WF_ERR_INVALID_ARG;
-  if ((reinterpret_cast<uintptr_t>(weights) & 15) || (reinterpret_cast<uintptr_t>(tab_I) & 15) ||
-      (tab_P && (reinterpret_cast<uintptr_t>(tab_P) & 15)))
+  if ((reinterpret_cast<uintptr_t>(weights) & 15) || (reinterpret_cast<uintptr_t>(t->dense_I) & 15) ||
+      (t->dense_P && (reinterpret_cast<uintptr_t>(t->dense_P) & 15)))
     return WF_ERR_INVALID_ARG;
   memset(&P, 0, sizeof(P));
   P.m = *m;
-  P.weights = weights; P.tab_I = tab_I; P.tab_P = tab_P; P.ob_to_b = ob_to_b; P.x = x; P.N = N;
+  P.weights = weights; P.x = x; P.N = N;
+  P.tab_I = t->dense_I; P.rec_I = t->rec_I; P.lo_I = t->lo_I;
+  P.tab_P = t->dense_P; P.rec_P = t->rec_P; P.lo_P = t->lo_P; P.ob_to_b = t->ob_to_b;
   P.n_nets = m->n_layers + (pnet ? 1 : 0);
   coeff_weights(WF_KIND_I, m->k_I, m->P_I, m->bc_I, true, P.wq_I);
   if (pnet) coeff_weights(m->prior_kind, m->k_P, m->P_P, m->bc_P, m->prior_kind == WF_KIND_M, P.wq_P);
@@ -60,12 +64,12 @@ int dispatch(LiveParams& P, bool lap, void* stream) {
 
 }  // namespace
 
-extern "C" int wf_live_forward(const wf_live_model* model, const float* weights, const float* tab_I, const float* tab_P,
-                               const float* ob_to_b, const float* x, int64_t N, float* u, float* logdet, float* logpdf,
-                               float* psi, void* stream) {
+extern "C" int wf_live_forward(const wf_live_model* model, const wf_live_tables* tables, const float* weights,
+                               const float* x, int64_t N, float* u, float* logdet, float* logpdf, float* psi,
+                               void* stream) {
   if (N == 0) return WF_OK;   // empty batch: nothing to do (pointers of empty buffers may be NULL)
   LiveParams P;
-  const int st = fill_params(model, weights, tab_I, tab_P, ob_to_b, x, N, P);
+  const int st = fill_params(model, tables, weights, x, N, P);
   if (st != WF_OK) return st;
   if (psi && model->prior_kind != WF_KIND_B) return WF_ERR_INVALID_ARG;
   if (N == 0) return WF_OK;
@@ -73,12 +77,12 @@ extern "C" int wf_live_forward(const wf_live_model* model, const float* weights,
   return dispatch(P, false, stream);
 }
 
-extern "C" int wf_local_energy(const wf_live_model* model, const float* weights, const float* tab_I, const float* tab_P,
-                               const float* ob_to_b, const float* protons, int n_protons, const float* x, int64_t N,
-                               float* psi, float* hpsi, float* eloc, float* grad, float* lap, double* sums, void* stream) {
+extern "C" int wf_local_energy(const wf_live_model* model, const wf_live_tables* tables, const float* weights,
+                               const float* protons, int n_protons, const float* x, int64_t N, float* psi, float* hpsi,
+                               float* eloc, float* grad, float* lap, double* sums, void* stream) {
   if (N == 0) return WF_OK;   // empty batch: nothing to do (pointers of empty buffers may be NULL)
   LiveParams P;
-  const int st = fill_params(model, weights, tab_I, tab_P, ob_to_b, x, N, P);
+  const int st = fill_params(model, tables, weights, x, N, P);
   if (st != WF_OK) return st;
   if (model->prior_kind != WF_KIND_B) return WF_ERR_INVALID_ARG;
   if (n_protons < 0 || n_protons > WF_MAX_D || (n_protons > 0 && !protons)) return WF_ERR_INVALID_ARG;

@@ -13,6 +13,12 @@
 // coefficient; it is folded into the Laplacian lane once per dimension.
 // Without LAP, G = 1 and every helper collapses to scalar code: one thread per sample.
 //
+// Code shape: the instruction cache, not the FMA pipe, limited the first (fully unrolled, ~0.5 MB of SASS) version of
+// this kernel (ncu: 3.6 stall cycles per issue on "no instruction").  Hence: input activations of a layer live in
+// registers (statically indexed, the reduction loop is unrolled), output blocks are produced by ROLLED loops and parked
+// in a thread-private shared-memory scratch column, and all conditioner nets (flow layers and prior) run through the
+// same rolled loop body.
+//
 // Reference: flows/bijections/made.py:66-81,108-183, model_factory.py:8-93, splines/isplines_jax.py:45-79,158-202,
 // splines/bsplines_jax.py:127-137,173-198, wavefunctions.py:33-71, flows/distributions.py:139-163,
 // utils/physics.py:50-93, vqmc.py:198-200.
@@ -22,7 +28,8 @@
 
 namespace wf {
 
-constexpr int LIVE_THREADS = 256;
+constexpr int LIVE_THREADS = 384;          // 12 warps per SM (170 registers per thread)
+constexpr int LIVE_SCRATCH = 64;            // floats of thread-private scratch (one column per thread)
 constexpr unsigned FULL = 0xffffffffu;
 
 __host__ __device__ constexpr int net_floats(int D) {
@@ -31,9 +38,13 @@ __host__ __device__ constexpr int net_floats(int D) {
 
 struct LiveParams {
   wf_live_model m;
-  const float* weights;   // (n_layers + has_prior_net) nets, packed (see wf_live_net_floats)
-  const float* tab_I;     // [T][4][32]
-  const float* tab_P;     // [T][4][32]  (OB tables for the B prior, M tables for the M prior)
+  const float* weights;   // n_nets conditioners, packed (see wf_live_net_floats)
+  const float* tab_I;     // dense [T][4][32] I tables (fallback for arguments outside [0, 1])
+  const float* rec_I;     // compact node records [T][4][8]
+  const int32_t* lo_I;    // [T]
+  const float* tab_P;     // dense [T][4][32]: OB tables (B prior) / M tables (M prior)
+  const float* rec_P;     // compact records of the M tables (M prior)
+  const int32_t* lo_P;
   const float* ob_to_b;   // [P_P][P_P]  (B prior)
   const float* x;         // [N][D]
   int64_t N;
@@ -44,7 +55,6 @@ struct LiveParams {
   float wq_P[WF_MAX_P];   // same for the prior coefficients (M: remove_bias x mask, B: mask)
   float protons[WF_MAX_D];
   int n_protons;
-  int nets_resident;      // all conditioner nets fit in shared memory at once
   int n_nets;
 };
 
@@ -84,7 +94,6 @@ struct Ctx {
   __device__ __forceinline__ float fold(const J& a) const {  // -> 1-register bundle
     if constexpr (LAP) { const float s = gsum(a.p); return is_l ? a.m + s : a.m; } else return a.m;
   }
-  __device__ __forceinline__ J from1(float a) const { return J{a, 0.f, bv(a)}; }
   __device__ __forceinline__ J constant(float c) const { return J{is_v ? c : 0.f, 0.f, c}; }
   // f(a) given f, f', f'' evaluated at a.v
   __device__ __forceinline__ J unary(const J& a, float f0, float f1, float f2) const {
@@ -100,6 +109,9 @@ struct Ctx {
   __device__ __forceinline__ J add(const J& a, const J& b) const { return J{a.m + b.m, LAP ? a.p + b.p : 0.f, a.v + b.v}; }
   __device__ __forceinline__ J sub(const J& a, const J& b) const { return J{a.m - b.m, LAP ? a.p - b.p : 0.f, a.v - b.v}; }
   __device__ __forceinline__ J scale(const J& a, float s) const { return J{a.m * s, LAP ? a.p * s : 0.f, a.v * s}; }
+  __device__ __forceinline__ J axpy(float s, const J& a, const J& y) const {    // s * a + y
+    return J{fmaf(s, a.m, y.m), LAP ? fmaf(s, a.p, y.p) : 0.f, fmaf(s, a.v, y.v)};
+  }
   __device__ __forceinline__ J addc(const J& a, float c) const { return J{is_v ? a.m + c : a.m, a.p, a.v + c}; }
   __device__ __forceinline__ J rsubc(float c, const J& a) const { return J{is_v ? c - a.m : -a.m, -a.p, c - a.v}; }
   __device__ __forceinline__ J recip(const J& a) const { const float r = 1.f / a.v; return unary(a, r, -r * r, 2.f * r * r * r); }
@@ -109,36 +121,48 @@ struct Ctx {
   __device__ __forceinline__ J div(const J& a, const J& b) const { J q = mul(a, recip(b)); q.v = a.v / b.v; if (is_v) q.m = q.v; return q; }
 };
 
+// tanh / sigmoid through ex2.approx + rcp.approx (about 1e-7 absolute error, measured in tests/test_gpu_live.py):
+// the accurate libdevice versions cost ~3x the issue slots and the glue around the MLPs is issue bound.
+__device__ __forceinline__ float fast_tanh(float x) {
+  const float xc = fminf(fmaxf(x, -15.f), 15.f);
+  const float e = __expf(2.f * xc);
+  return 1.f - __fdividef(2.f, e + 1.f);
+}
+__device__ __forceinline__ float fast_sigmoid(float x) {
+  return __fdividef(1.f, 1.f + __expf(-x));
+}
+
 // tanh on a 1-register bundle (MLP hidden layers): needs |grad|^2 on the Laplacian lane.
 template <int D, bool LAP>
 __device__ __forceinline__ float tanh_bundle(const Ctx<D, LAP>& cx, float a) {
   if constexpr (LAP) {
-    const float th = tanhf(cx.bv(a));
+    const float th = fast_tanh(cx.bv(a));
     const float f1 = 1.f - th * th;
     const float gg = cx.gsum(a * a);
     float r = f1 * a;
     if (cx.is_l) r = fmaf(-2.f * th * f1, gg, r);
     return cx.is_v ? th : r;
-  } else return tanhf(a);
+  } else return fast_tanh(a);
 }
 
 __device__ __forceinline__ float4 lds4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 
-// MADE degrees (model_factory.py:8-19): input d -> d, hidden i -> i % (D-1), output d -> d - 1.
-template <int D> __host__ __device__ constexpr bool m1_on(int d, int j) { return (j % (D - 1)) >= d; }
-template <int D> __host__ __device__ constexpr bool m2_on(int i, int j) { return (j % (D - 1)) >= (i % (D - 1)); }
-template <int D> __host__ __device__ constexpr bool m3_on(int i, int d) { return (d - 1) >= (i % (D - 1)); }
+// thread-private scratch column in shared memory: slot-major, so a warp touches 32 consecutive words (conflict-free)
+struct Scratch {
+  float* col;
+  __device__ __forceinline__ float& operator[](int slot) const { return col[slot * LIVE_THREADS]; }
+};
 
-// Two hidden layers of a conditioner: h2 = tanh(tanh(u W1 + b1) W2 + b2), masks compiled in.
+// Hidden layers of one conditioner: h = tanh(tanh(u W1 + b1) W2 + b2) (masked weights are stored as zeros).
+// On return h[] holds the second hidden layer and the scratch column is free.
 template <int D, bool LAP>
 __device__ __forceinline__ void mlp_hidden(const Ctx<D, LAP>& cx, const float* __restrict__ net, const float (&u)[D],
-                                           float (&h2)[WF_HIDDEN]) {
+                                           const Scratch& S, float (&h)[WF_HIDDEN]) {
   const float* W1 = net;
   const float* b1 = W1 + D * WF_HIDDEN;
   const float* W2 = b1 + WF_HIDDEN;
   const float* b2 = W2 + WF_HIDDEN * WF_HIDDEN;
-  float h1[WF_HIDDEN];
-#pragma unroll
+#pragma unroll 1
   for (int j0 = 0; j0 < WF_HIDDEN; j0 += 4) {
     const float4 bb = lds4(b1 + j0);
     float acc[4] = {bb.x, bb.y, bb.z, bb.w};
@@ -147,15 +171,15 @@ __device__ __forceinline__ void mlp_hidden(const Ctx<D, LAP>& cx, const float* _
 #pragma unroll
     for (int d = 0; d < D; ++d) {
       const float4 w4 = lds4(W1 + d * WF_HIDDEN + j0);
-      const float w[4] = {w4.x, w4.y, w4.z, w4.w};
-#pragma unroll
-      for (int t = 0; t < 4; ++t)
-        if (m1_on<D>(d, j0 + t)) acc[t] = fmaf(u[d], w[t], acc[t]);
+      acc[0] = fmaf(u[d], w4.x, acc[0]); acc[1] = fmaf(u[d], w4.y, acc[1]);
+      acc[2] = fmaf(u[d], w4.z, acc[2]); acc[3] = fmaf(u[d], w4.w, acc[3]);
     }
 #pragma unroll
-    for (int t = 0; t < 4; ++t) h1[j0 + t] = tanh_bundle<D, LAP>(cx, acc[t]);
+    for (int t = 0; t < 4; ++t) S[j0 + t] = tanh_bundle<D, LAP>(cx, acc[t]);
   }
 #pragma unroll
+  for (int i = 0; i < WF_HIDDEN; ++i) h[i] = S[i];
+#pragma unroll 1
   for (int j0 = 0; j0 < WF_HIDDEN; j0 += 8) {
     const float4 ba = lds4(b2 + j0), bb = lds4(b2 + j0 + 4);
     float acc[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
@@ -164,56 +188,44 @@ __device__ __forceinline__ void mlp_hidden(const Ctx<D, LAP>& cx, const float* _
 #pragma unroll
     for (int i = 0; i < WF_HIDDEN; ++i) {
       const float4 wa = lds4(W2 + i * WF_HIDDEN + j0), wb = lds4(W2 + i * WF_HIDDEN + j0 + 4);
-      const float w[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
-#pragma unroll
-      for (int t = 0; t < 8; ++t)
-        if (m2_on<D>(i, j0 + t)) acc[t] = fmaf(h1[i], w[t], acc[t]);
+      acc[0] = fmaf(h[i], wa.x, acc[0]); acc[1] = fmaf(h[i], wa.y, acc[1]);
+      acc[2] = fmaf(h[i], wa.z, acc[2]); acc[3] = fmaf(h[i], wa.w, acc[3]);
+      acc[4] = fmaf(h[i], wb.x, acc[4]); acc[5] = fmaf(h[i], wb.y, acc[5]);
+      acc[6] = fmaf(h[i], wb.z, acc[6]); acc[7] = fmaf(h[i], wb.w, acc[7]);
     }
 #pragma unroll
-    for (int t = 0; t < 8; ++t) h2[j0 + t] = tanh_bundle<D, LAP>(cx, acc[t]);
+    for (int t = 0; t < 8; ++t) S[j0 + t] = tanh_bundle<D, LAP>(cx, acc[t]);   // h (layer 1) is already in registers
   }
+#pragma unroll
+  for (int i = 0; i < WF_HIDDEN; ++i) h[i] = S[i];
 }
 
-// Output layer for dimension dd: o[q] = h2 . W3p[:, dd, q] + b3p[dd, q], q < 32 (padded columns carry zero weights).
+// Output layer for dimension dd: S[q] = h . W3p[:, dd, q] + b3p[dd, q], q < 32 (padded columns carry zero weights).
+// Dimension 0 of a MADE conditioner depends on the bias only (output degree -1, model_factory.py:15).
 template <int D, bool LAP>
-__device__ __forceinline__ void mlp_out(const Ctx<D, LAP>& cx, const float* __restrict__ net, const int dd,
-                                        const float (&h2)[WF_HIDDEN], float (&o)[WF_MAX_P]) {
+__device__ __forceinline__ void mlp_out(const Ctx<D, LAP>& cx, const float* __restrict__ net, int dd,
+                                        const float (&h)[WF_HIDDEN], const Scratch& S) {
   const float* W3 = net + D * WF_HIDDEN + WF_HIDDEN + WF_HIDDEN * WF_HIDDEN + WF_HIDDEN;
-  const float* b3 = W3 + WF_HIDDEN * D * WF_MAX_P;
-#pragma unroll
+  const float* b3 = W3 + WF_HIDDEN * D * WF_MAX_P + dd * WF_MAX_P;
+#pragma unroll 1
   for (int q0 = 0; q0 < WF_MAX_P; q0 += 8) {
-    const float4 ba = lds4(b3 + dd * WF_MAX_P + q0), bb = lds4(b3 + dd * WF_MAX_P + q0 + 4);
+    const float4 ba = lds4(b3 + q0), bb = lds4(b3 + q0 + 4);
     float acc[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
 #pragma unroll
     for (int t = 0; t < 8; ++t) acc[t] = cx.is_v ? acc[t] : 0.f;
+    if (dd > 0) {
+      const float* wr0 = W3 + dd * WF_MAX_P + q0;
 #pragma unroll
-    for (int i = 0; i < WF_HIDDEN; ++i) {
-      if (m3_on<D>(i, dd)) {
-        const float* wr = W3 + (i * D + dd) * WF_MAX_P + q0;
-        const float4 wa = lds4(wr), wb = lds4(wr + 4);
-        const float w[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
-#pragma unroll
-        for (int t = 0; t < 8; ++t) acc[t] = fmaf(h2[i], w[t], acc[t]);
+      for (int i = 0; i < WF_HIDDEN; ++i) {
+        const float4 wa = lds4(wr0 + i * D * WF_MAX_P), wb = lds4(wr0 + i * D * WF_MAX_P + 4);
+        acc[0] = fmaf(h[i], wa.x, acc[0]); acc[1] = fmaf(h[i], wa.y, acc[1]);
+        acc[2] = fmaf(h[i], wa.z, acc[2]); acc[3] = fmaf(h[i], wa.w, acc[3]);
+        acc[4] = fmaf(h[i], wb.x, acc[4]); acc[5] = fmaf(h[i], wb.y, acc[5]);
+        acc[6] = fmaf(h[i], wb.z, acc[6]); acc[7] = fmaf(h[i], wb.w, acc[7]);
       }
     }
 #pragma unroll
-    for (int t = 0; t < 8; ++t) o[q0 + t] = acc[t];
-  }
-}
-
-// Interpolated basis values f[k][t] = basis_{q0+t}^{(k)}(x) for k < NK, t < 4, from the dense [T][4][32] table.
-template <int NK>
-__device__ __forceinline__ void table_chunk(const float* __restrict__ tab, const NodeIdx& n, float np_, int q0,
-                                            float (&f)[NK][4]) {
-#pragma unroll
-  for (int k = 0; k < NK; ++k) {
-    const int nd = k < 3 ? k : 3;
-    const float4 a = __ldg(reinterpret_cast<const float4*>(tab + ((size_t)n.l * 4 + nd) * WF_MAX_P + q0));
-    const float4 b = __ldg(reinterpret_cast<const float4*>(tab + ((size_t)n.r * 4 + nd) * WF_MAX_P + q0));
-    f[k][0] = lerp_tab(a.x, b.x, np_, n.dx);
-    f[k][1] = lerp_tab(a.y, b.y, np_, n.dx);
-    f[k][2] = lerp_tab(a.z, b.z, np_, n.dx);
-    f[k][3] = lerp_tab(a.w, b.w, np_, n.dx);
+    for (int t = 0; t < 8; ++t) S[q0 + t] = acc[t];
   }
 }
 
@@ -231,52 +243,94 @@ __device__ __forceinline__ J spline_assemble(const Ctx<D, LAP>& cx, const J& A0,
 //   p = sigmoid(o); p /= sum p; p += reg; remove_bias; boundary mask; renormalise     (model_factory.py:61-69,
 //   made.py:67-72, isplines_jax.py:158-202)  ==  c_q = w_q (s_q / S + reg) / sum_q' w_q' (s_q' / S + reg),
 // with w_q = remove_bias scale x boundary mask (host-computed).  Everything downstream is bilinear in (s_q), 1/S, 1/Z,
-// so only sums over q with lane-uniform coefficients are accumulated.
-// NOUT = 2: value and derivative spline (IMADE), NOUT = 1: value only (M prior).
-// xd: derivative component of the spline argument on this lane; xv: its value (table lookup position).
-template <int D, bool LAP, int NOUT>
-__device__ __forceinline__ void sigmoid_spline(const Ctx<D, LAP>& cx, const float (&o)[WF_MAX_P], int P,
-                                               const float* __restrict__ wq, float reg, const float* __restrict__ tab,
-                                               int T, float xd, float xv, J& y, J& dy) {
+// so only sums over q with lane-uniform coefficients are accumulated:
+//   pass A (all q):   s_q, S = sum s_q, SW = sum w_q s_q, and the prefix sum over the bases below the local-support window
+//                     (identically 1 for an I-spline value, 0 otherwise); s_q is parked in the scratch column;
+//   pass B (8 window bases): the interpolated basis values from the compact node records.
+// NOUT = 2: value and derivative spline (IMADE), NOUT = 1: value only (M prior).  PREFIX_ONE: I-spline tables.
+// In: S[q] = conditioner output o_q (1-register bundle).  xd / xv: derivative component / value of the spline argument.
+template <int D, bool LAP, int NOUT, bool PREFIX_ONE>
+__device__ __forceinline__ void sigmoid_spline(const Ctx<D, LAP>& cx, const Scratch& S, int P, const float* __restrict__ wq,
+                                               float reg, const float* __restrict__ rec, const int32_t* __restrict__ lo,
+                                               const float* __restrict__ dense, int T, float xd, float xv, J& y, J& dy) {
   constexpr int NK = LAP ? NOUT + 2 : NOUT;
   const float np_ = (float)(T - 1);
   const NodeIdx n = node_index(xv, T);
-  J S = {0.f, 0.f, 0.f}, SW = {0.f, 0.f, 0.f};
+  const int lo_l = __ldg(lo + n.l), lo_r = __ldg(lo + n.r);
+  const int sh = lo_r - lo_l;
+  const bool local = (sh == 0) || (sh == 1);      // false only for arguments outside [0, 1] (wrapped gather rows)
+  const int lo_w = local ? lo_l : 0;
+
+  J Ssum = {0.f, 0.f, 0.f}, SW = {0.f, 0.f, 0.f}, PRE = {0.f, 0.f, 0.f};
+  float Wsum = 0.f, Wpre = 0.f;
+#pragma unroll 2
+  for (int q = 0; q < P; ++q) {
+    const float o = S[q];
+    const float ov = cx.bv(o);
+    const float s = fast_sigmoid(ov);
+    const float d1 = s * (1.f - s);
+    const J sq = cx.unary(J{o, 0.f, ov}, s, d1, d1 * (1.f - 2.f * s));
+    const float w = wq[q];
+    Ssum = cx.add(Ssum, sq);
+    SW = cx.axpy(w, sq, SW);
+    Wsum += w;
+    if (PREFIX_ONE) {
+      const float wp = (q < lo_w) ? w : 0.f;
+      PRE = cx.axpy(wp, sq, PRE);
+      Wpre += wp;
+    }
+    S[q] = sq.m;
+    if (LAP) S[WF_MAX_P + q] = sq.p;
+  }
   J Sk[NK];
-  float Wk[NK], Wsum = 0.f;
+  float Wk[NK];
 #pragma unroll
   for (int k = 0; k < NK; ++k) { Sk[k] = J{0.f, 0.f, 0.f}; Wk[k] = 0.f; }
+  if (PREFIX_ONE) { Sk[0] = PRE; Wk[0] = Wpre; }
+  if (local) {
+#pragma unroll 2
+    for (int t = 0; t < WF_WIN; ++t) {
+      const int q = lo_l + t;
+      const int qc = q < P ? q : P - 1;
+      const float w = q < P ? wq[qc] : 0.f;
+      J sq;
+      sq.m = S[qc];
+      sq.p = LAP ? S[WF_MAX_P + qc] : 0.f;
+      sq.v = cx.bv(sq.m);
+      const int tr = t - sh;                     // slot of this basis in the right node's record
 #pragma unroll
-  for (int q0 = 0; q0 < WF_MAX_P; q0 += 4) {
-    if (q0 < P) {
-      float f[NK][4];
-      table_chunk<NK>(tab, n, np_, q0, f);
+      for (int k = 0; k < NK; ++k) {
+        const int nd = k < 3 ? k : 3;
+        const float yl = __ldg(rec + ((size_t)n.l * 4 + nd) * WF_WIN + t);
+        const float yrr = __ldg(rec + ((size_t)n.r * 4 + nd) * WF_WIN + (tr < 0 ? 0 : tr));
+        const float yr = tr < 0 ? ((PREFIX_ONE && nd == 0) ? 1.f : 0.f) : yrr;
+        const float fw = lerp_tab(yl, yr, np_, n.dx) * w;
+        Sk[k] = cx.axpy(fw, sq, Sk[k]);
+        Wk[k] += fw;
+      }
+    }
+  } else {
+    // reference-exact dense evaluation (JAX gather wrap/clamp semantics)
+    if (PREFIX_ONE) { Sk[0] = J{0.f, 0.f, 0.f}; Wk[0] = 0.f; }
+    for (int q = 0; q < P; ++q) {
+      J sq;
+      sq.m = S[q];
+      sq.p = LAP ? S[WF_MAX_P + q] : 0.f;
+      sq.v = cx.bv(sq.m);
+      const float w = wq[q];
 #pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        const int q = q0 + t;
-        if (q < P) {
-          const float ov = cx.bv(o[q]);
-          const float s = 1.f / (1.f + expf(-ov));
-          const float d1 = s * (1.f - s);
-          const J sq = cx.unary(J{o[q], 0.f, ov}, s, d1, d1 * (1.f - 2.f * s));
-          const float w = wq[q];
-          S = cx.add(S, sq);
-          SW.m = fmaf(w, sq.m, SW.m); SW.v = fmaf(w, s, SW.v);
-          if (LAP) SW.p = fmaf(w, sq.p, SW.p);
-          Wsum += w;
-#pragma unroll
-          for (int k = 0; k < NK; ++k) {
-            const float fw = f[k][t] * w;
-            Sk[k].m = fmaf(fw, sq.m, Sk[k].m); Sk[k].v = fmaf(fw, s, Sk[k].v);
-            if (LAP) Sk[k].p = fmaf(fw, sq.p, Sk[k].p);
-            Wk[k] += fw;
-          }
-        }
+      for (int k = 0; k < NK; ++k) {
+        const int nd = k < 3 ? k : 3;
+        const float yl = __ldg(dense + ((size_t)n.l * 4 + nd) * WF_MAX_P + q);
+        const float yr = __ldg(dense + ((size_t)n.r * 4 + nd) * WF_MAX_P + q);
+        const float fw = lerp_tab(yl, yr, np_, n.dx) * w;
+        Sk[k] = cx.axpy(fw, sq, Sk[k]);
+        Wk[k] += fw;
       }
     }
   }
   // r = 1/S;  Z = SW * r + reg * Wsum;  iz = 1/Z;  N_k = Sk * r + reg * Wk;  A_k = N_k * iz
-  const J r = cx.recip(S);
+  const J r = cx.recip(Ssum);
   const J iz = cx.recip(cx.addc(cx.mul(SW, r), reg * Wsum));
   J A[NK];
 #pragma unroll
@@ -294,52 +348,57 @@ __device__ __forceinline__ void sigmoid_spline(const Ctx<D, LAP>& cx, const floa
 // B prior factor (wavefunctions.py:58-65, bsplines_jax.py:127-137,173-198):
 //   w = o / sum o; boundary mask; w /= ||w||; c = w @ ob_to_b; c /= ||c||; phi = sum_j c_j OB_j(clip(u)).
 // Both normalisations are positive rescalings, so phi = sign(sum o) * (sum_j c'_j OB_j) / ||c'||, c' = (mask o) @ ob_to_b.
-// ob_s: ob_to_b zero-padded to [32][32] in shared memory.
+// ob_s: ob_to_b zero-padded to [32][32] in shared memory.  In: S[q] = o_q.
 template <int D, bool LAP>
-__device__ __forceinline__ J bprior_factor(const Ctx<D, LAP>& cx, const float (&o)[WF_MAX_P], int P,
-                                           const float* __restrict__ wq, const float* __restrict__ ob_s,
-                                           const float* __restrict__ tab, int T, float xd_in, float xv) {
+__device__ __forceinline__ J bprior_factor(const Ctx<D, LAP>& cx, const Scratch& S, int P, const float* __restrict__ wq,
+                                           const float* __restrict__ ob_s, const float* __restrict__ tab, int T,
+                                           float xd_in, float xv) {
   constexpr int NK = LAP ? 3 : 1;
   // clip(u, 0, 1): derivative 1 strictly inside, 0 outside
   const float xc = fminf(fmaxf(xv, 0.f), 1.f);
   const float xd = ((xv > 0.f) && (xv < 1.f)) ? xd_in : 0.f;
   const float np_ = (float)(T - 1);
   const NodeIdx n = node_index(xc, T);
-  float ow[WF_MAX_P];
   float osum = 0.f;
-#pragma unroll
+#pragma unroll 4
   for (int q = 0; q < WF_MAX_P; ++q) {
-    if (q < P) osum += o[q];
-    ow[q] = o[q] * wq[q];                 // wq is 0 beyond P and on the constrained ends
+    const float o = S[q];
+    if (q < P) osum += o;
+    S[q] = o * wq[q];                     // wq is 0 beyond P and on the constrained ends
   }
   const float sgn = cx.bv(osum) < 0.f ? -1.f : 1.f;
   J A[NK];
 #pragma unroll
   for (int k = 0; k < NK; ++k) A[k] = J{0.f, 0.f, 0.f};
   J Q = {0.f, 0.f, 0.f};                  // Q = sum_j c'_j^2
+#pragma unroll 1
+  for (int j0 = 0; j0 < P; j0 += 4) {
+    float c[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 8
+    for (int i = 0; i < WF_MAX_P; ++i) {
+      const float ow = S[i];
+      const float4 w4 = lds4(ob_s + i * WF_MAX_P + j0);
+      c[0] = fmaf(ow, w4.x, c[0]); c[1] = fmaf(ow, w4.y, c[1]);
+      c[2] = fmaf(ow, w4.z, c[2]); c[3] = fmaf(ow, w4.w, c[3]);
+    }
+    float f[NK][4];
 #pragma unroll
-  for (int j0 = 0; j0 < WF_MAX_P; j0 += 4) {
-    if (j0 < P) {
-      float c[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int k = 0; k < NK; ++k) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(tab + ((size_t)n.l * 4 + k) * WF_MAX_P + j0));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(tab + ((size_t)n.r * 4 + k) * WF_MAX_P + j0));
+      f[k][0] = lerp_tab(a.x, b.x, np_, n.dx); f[k][1] = lerp_tab(a.y, b.y, np_, n.dx);
+      f[k][2] = lerp_tab(a.z, b.z, np_, n.dx); f[k][3] = lerp_tab(a.w, b.w, np_, n.dx);
+    }
 #pragma unroll
-      for (int i = 0; i < WF_MAX_P; ++i) {
-        const float4 w4 = lds4(ob_s + i * WF_MAX_P + j0);
-        c[0] = fmaf(ow[i], w4.x, c[0]); c[1] = fmaf(ow[i], w4.y, c[1]);
-        c[2] = fmaf(ow[i], w4.z, c[2]); c[3] = fmaf(ow[i], w4.w, c[3]);
-      }
-      float f[NK][4];
-      table_chunk<NK>(tab, n, np_, j0, f);
+    for (int t = 0; t < 4; ++t) {
+      const float cv = cx.bv(c[t]);
 #pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        const float cv = cx.bv(c[t]);
-#pragma unroll
-        for (int k = 0; k < NK; ++k) { A[k].m = fmaf(f[k][t], c[t], A[k].m); A[k].v = fmaf(f[k][t], cv, A[k].v); }
-        Q.v = fmaf(cv, cv, Q.v);
-        if constexpr (LAP) {
-          Q.m = cx.is_v ? Q.v : fmaf(2.f * cv, c[t], Q.m);
-          Q.p = cx.is_g ? fmaf(2.f * c[t], c[t], Q.p) : 0.f;
-        } else Q.m = Q.v;
-      }
+      for (int k = 0; k < NK; ++k) { A[k].m = fmaf(f[k][t], c[t], A[k].m); A[k].v = fmaf(f[k][t], cv, A[k].v); }
+      Q.v = fmaf(cv, cv, Q.v);
+      if constexpr (LAP) {
+        Q.m = cx.is_v ? Q.v : fmaf(2.f * cv, c[t], Q.m);
+        Q.p = cx.is_g ? fmaf(2.f * c[t], c[t], Q.p) : 0.f;
+      } else Q.m = Q.v;
     }
   }
   J num;

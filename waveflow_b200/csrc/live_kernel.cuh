@@ -1,5 +1,5 @@
-// Persistent fused kernel for the live path (see live_device.cuh).  One CTA per SM; conditioner weights of all layers
-// stay resident in shared memory when they fit (136 KB at D=2, 205 KB at D=4, L=3), else they are re-staged per layer.
+// Persistent fused kernel for the live path (see live_device.cuh).  One CTA per SM; the conditioner weights stream through
+// a two-slot shared-memory ring, each net fetched by one cp.async.bulk (TMA) while the previous one is being used.
 #pragma once
 #include "live_device.cuh"
 
@@ -20,21 +20,33 @@ __device__ __forceinline__ float soft_coulomb(const float (&xs)[D], const float*
   return ee - pe;
 }
 
+// Shared memory:  2 x conditioner net (double buffer, filled by cp.async.bulk / TMA one net ahead of the compute)
+//                 | ob_to_b [32][32] | scratch [64][LIVE_THREADS] | reduction buffer | 2 mbarriers
+struct LiveSmem {
+  static __host__ __device__ size_t net_bytes(int D) { return (size_t)net_floats(D) * sizeof(float); }
+  static __host__ __device__ size_t total(int D) {
+    return 2 * net_bytes(D) + (size_t)WF_MAX_P * WF_MAX_P * sizeof(float) + (size_t)LIVE_SCRATCH * LIVE_THREADS * sizeof(float) +
+           4 * (LIVE_THREADS / 32) * sizeof(double) + 2 * sizeof(uint64_t);
+  }
+};
+
 template <int D, bool LAP>
 __global__ void __launch_bounds__(LIVE_THREADS, 1) live_kernel(const __grid_constant__ LiveParams P) {
   using C = Ctx<D, LAP>;
-  extern __shared__ __align__(16) float smem[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr int NETF = net_floats(D);
   const wf_live_model& M = P.m;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  float* nets_s = smem;
-  float* ob_s = smem + (size_t)(P.nets_resident ? P.n_nets : 1) * NETF;     // [32][32], B prior only
-  double* red_s = reinterpret_cast<double*>(ob_s + WF_MAX_P * WF_MAX_P);    // [4][warps]
+  float* nets_s = reinterpret_cast<float*>(smem_raw);                         // [2][NETF]
+  float* ob_s = nets_s + 2 * NETF;                                            // [32][32], B prior only
+  float* scratch = ob_s + WF_MAX_P * WF_MAX_P;                                // [64][LIVE_THREADS]
+  double* red_s = reinterpret_cast<double*>(scratch + LIVE_SCRATCH * LIVE_THREADS);   // [4][warps]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(red_s + 4 * (LIVE_THREADS / 32));
 
-  if (P.nets_resident) {
-    const int n4 = P.n_nets * NETF / 4;
-    for (int i = tid; i < n4; i += LIVE_THREADS)
-      reinterpret_cast<float4*>(nets_s)[i] = __ldg(reinterpret_cast<const float4*>(P.weights) + i);
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    mbar_fence_init();
   }
   if (M.prior_kind == WF_KIND_B) {
     for (int i = tid; i < WF_MAX_P * WF_MAX_P; i += LIVE_THREADS) {
@@ -46,19 +58,24 @@ __global__ void __launch_bounds__(LIVE_THREADS, 1) live_kernel(const __grid_cons
 
   C cx;
   cx.init(lane);
+  const Scratch S{scratch + tid};
   constexpr int WPB = (LIVE_THREADS / 32) * C::WPW;     // walkers per CTA batch
   const int64_t n_batches = (P.N + WPB - 1) / WPB;
+  const int n_nets = P.n_nets;
   const bool has_prior_net = M.prior_kind == WF_KIND_B || M.prior_kind == WF_KIND_M;
   double accE = 0.0, accE2 = 0.0, accN = 0.0, accP2 = 0.0;
 
-  auto stage_net = [&](int idx) -> const float* {
-    if (P.nets_resident) return nets_s + (size_t)idx * NETF;
-    __syncthreads();
-    for (int i = tid; i < NETF / 4; i += LIVE_THREADS)
-      reinterpret_cast<float4*>(nets_s)[i] = __ldg(reinterpret_cast<const float4*>(P.weights + (size_t)idx * NETF) + i);
-    __syncthreads();
-    return nets_s;
+  // weight pipeline: net g (a flat counter over batches x nets) lives in buffer g & 1
+  const uint32_t net_bytes = (uint32_t)(NETF * sizeof(float));
+  auto issue_net = [&](int64_t g) {
+    const int b = (int)(g & 1);
+    mbar_expect_tx(&bars[b], net_bytes);
+    bulk_g2s(nets_s + (size_t)b * NETF, P.weights + (size_t)(g % n_nets) * NETF, net_bytes, &bars[b]);
   };
+  const int64_t my_batches = blockIdx.x < n_batches ? (n_batches - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const int64_t g_total = my_batches * n_nets;
+  int64_t g = 0;
+  if (tid == 0 && g_total > 0) issue_net(0);
 
   for (int64_t batch = blockIdx.x; batch < n_batches; batch += gridDim.x) {
     const int64_t w_raw = batch * WPB + (int64_t)warp * C::WPW + cx.slot;
@@ -118,57 +135,72 @@ __global__ void __launch_bounds__(LIVE_THREADS, 1) live_kernel(const __grid_cons
       }
     }
 
-    // ---------------------------------------------------------------- (IMADE, Reverse) x L   (made.py:66-81)
-    for (int layer = 0; layer < M.n_layers; ++layer) {
-      const float* net = stage_net(layer);
-      float h2[WF_HIDDEN];
-      mlp_hidden<D, LAP>(cx, net, us, h2);
+    float uout[D];      // flow output (value), for the `u` result
+#pragma unroll
+    for (int d = 0; d < D; ++d) uout[d] = 0.f;
+    if (M.n_layers == 0) {
+#pragma unroll
+      for (int d = 0; d < D; ++d) uout[d] = cx.bv(us[d]);
+    }
+    J psi = cx.constant(1.f);
+    float lp = 0.f;
+
+    // ------------------------------------------- conditioner nets: (IMADE, Reverse) x L (made.py:66-81), then the prior
+#pragma unroll 1
+    for (int net_idx = 0; net_idx < n_nets; ++net_idx, ++g) {
+      const bool is_prior = has_prior_net && net_idx == n_nets - 1;
+      // every warp is done with the other buffer (it held net g-1): refill it with net g+1, then wait for net g
+      __syncthreads();
+      if (tid == 0 && g + 1 < g_total) issue_net(g + 1);
+      mbar_wait(&bars[g & 1], (uint32_t)((g >> 1) & 1));
+      const float* net = nets_s + (size_t)(g & 1) * NETF;
+
+      float h[WF_HIDDEN];
+      mlp_hidden<D, LAP>(cx, net, us, S, h);
       float ys[D];
 #pragma unroll
+      for (int d = 0; d < D; ++d) ys[d] = 0.f;
+#pragma unroll 1
       for (int d = 0; d < D; ++d) {
-        float o[WF_MAX_P];
-        mlp_out<D, LAP>(cx, net, d, h2, o);
-        const float xv = cx.bv(us[d]);
-        J y, dy;
-        sigmoid_spline<D, LAP, 2>(cx, o, M.P_I, P.wq_I, M.reg, P.tab_I, M.T, us[d], xv, y, dy);
-        ys[d] = cx.fold(y);
-        ld = cx.add(ld, cx.log(cx.addc(dy, LOG_TOL)));
-      }
+        mlp_out<D, LAP>(cx, net, d, h, S);
+        float xd = us[0];
 #pragma unroll
-      for (int d = 0; d < D; ++d) us[d] = ys[D - 1 - d];      // Reverse (bijections.py:336-345)
-    }
-
-    // ---------------------------------------------------------------- prior
-    float uv[D];
-#pragma unroll
-    for (int d = 0; d < D; ++d) uv[d] = cx.bv(us[d]);
-    J psi = cx.constant(1.f);
-    J lp = cx.constant(0.f);
-    if (has_prior_net) {
-      const float* net = stage_net(M.n_layers);
-      float h2[WF_HIDDEN];
-      mlp_hidden<D, LAP>(cx, net, us, h2);
-#pragma unroll
-      for (int d = 0; d < D; ++d) {
-        float o[WF_MAX_P];
-        mlp_out<D, LAP>(cx, net, d, h2, o);
-        // constrained dimensions (model_factory.py:124-129): 'mean' -> 0..D-2, 'first' -> 1..D-1
-        const bool cons = M.coord_mean ? (d < D - 1) : (d >= 1);
-        if (M.prior_kind == WF_KIND_B) {
-          J phi = bprior_factor<D, LAP>(cx, o, M.P_P, P.wq_P, ob_s, P.tab_P, M.T, us[d], uv[d]);
-          if (!LAP) {
-            float pr = phi.v * phi.v;
-            if (cons) pr = pr / 2.f;
-            lp.v += logf(pr + LOG_TOL);
-          }
-          if (cons) phi = cx.scale(phi, 0.70710678118654752f);
-          psi = cx.mul(psi, phi);
-        } else {
-          const float xc = fminf(fmaxf(uv[d], 0.f), 1.f);
-          const float xd = (uv[d] > 0.f && uv[d] < 1.f) ? us[d] : 0.f;
+        for (int dd = 1; dd < D; ++dd) xd = (d == dd) ? us[dd] : xd;
+        const float xv = cx.bv(xd);
+        if (!is_prior) {
           J y, dy;
-          sigmoid_spline<D, LAP, 1>(cx, o, M.P_P, P.wq_P, 0.f, P.tab_P, M.T, xd, xc, y, dy);
-          lp.v += logf(y.v + LOG_TOL);
+          sigmoid_spline<D, LAP, 2, true>(cx, S, M.P_I, P.wq_I, M.reg, P.rec_I, P.lo_I, P.tab_I, M.T, xd, xv, y, dy);
+          const float yf = cx.fold(y);
+#pragma unroll
+          for (int dd = 0; dd < D; ++dd) ys[dd] = (d == dd) ? yf : ys[dd];
+          ld = cx.add(ld, cx.log(cx.addc(dy, LOG_TOL)));
+        } else {
+          // constrained dimensions (model_factory.py:124-129): 'mean' -> 0..D-2, 'first' -> 1..D-1
+          const bool cons = M.coord_mean ? (d < D - 1) : (d >= 1);
+          if (M.prior_kind == WF_KIND_B) {
+            J phi = bprior_factor<D, LAP>(cx, S, M.P_P, P.wq_P, ob_s, P.tab_P, M.T, xd, xv);
+            if (!LAP) {
+              float pr = phi.v * phi.v;
+              if (cons) pr = pr / 2.f;
+              lp += logf(pr + LOG_TOL);
+            }
+            if (cons) phi = cx.scale(phi, 0.70710678118654752f);
+            psi = cx.mul(psi, phi);
+          } else {
+            const float xc = fminf(fmaxf(xv, 0.f), 1.f);
+            const float xdc = (xv > 0.f && xv < 1.f) ? xd : 0.f;
+            J y, dy;
+            sigmoid_spline<D, LAP, 1, false>(cx, S, M.P_P, P.wq_P, 0.f, P.rec_P, P.lo_P, P.tab_P, M.T, xdc, xc, y, dy);
+            lp += logf(y.v + LOG_TOL);
+          }
+        }
+      }
+      if (!is_prior) {
+#pragma unroll
+        for (int d = 0; d < D; ++d) us[d] = ys[D - 1 - d];      // Reverse (bijections.py:336-345)
+        if (net_idx == M.n_layers - 1) {
+#pragma unroll
+          for (int d = 0; d < D; ++d) uout[d] = cx.bv(us[d]);
         }
       }
     }
@@ -180,10 +212,10 @@ __global__ void __launch_bounds__(LIVE_THREADS, 1) live_kernel(const __grid_cons
     if (lane_live && cx.is_v) {
       if (P.u) {
 #pragma unroll
-        for (int d = 0; d < D; ++d) P.u[w * D + d] = uv[d];
+        for (int d = 0; d < D; ++d) P.u[w * D + d] = uout[d];
       }
       if (P.logdet) P.logdet[w] = ld.v;
-      if (P.logpdf) P.logpdf[w] = lp.v + ld.v;
+      if (P.logpdf) P.logpdf[w] = lp + ld.v;
       if (P.psi) P.psi[w] = psi.v;
     }
     if constexpr (LAP) {
@@ -220,19 +252,11 @@ __global__ void __launch_bounds__(LIVE_THREADS, 1) live_kernel(const __grid_cons
   }
 }
 
-inline size_t live_smem_bytes(int D, int n_nets, bool resident) {
-  return ((size_t)(resident ? n_nets : 1) * net_floats(D) + WF_MAX_P * WF_MAX_P) * sizeof(float) +
-         4 * (LIVE_THREADS / 32) * sizeof(double) + 16;
-}
-
 template <int D, bool LAP>
 int launch_live(LiveParams& P, cudaStream_t s) {
-  constexpr bool lap = LAP;
-  const size_t all = live_smem_bytes(D, P.n_nets, true);
-  P.nets_resident = all <= 227 * 1024 ? 1 : 0;
-  const size_t smem = live_smem_bytes(D, P.n_nets, P.nets_resident != 0);
+  const size_t smem = LiveSmem::total(D);
   if (smem > 227 * 1024) return WF_ERR_UNSUPPORTED;
-  const int wpw = lap ? 32 / (D + 2) : 32;
+  const int wpw = LAP ? 32 / (D + 2) : 32;
   const int64_t wpb = (int64_t)(LIVE_THREADS / 32) * wpw;
   const int64_t n_batches = (P.N + wpb - 1) / wpb;
   const int blocks = (int)(n_batches < num_sms() ? n_batches : num_sms());
