@@ -128,7 +128,7 @@ typedef struct wf_live_model {
   float box;            /* box_side L                                                                              */
   float reg;            /* spline_regularization (made.py:68)                                                      */
   float tol;            /* reverse_fun_tol (made.py:44)                                                            */
-  float reserved;
+  int32_t n_knots_P;    /* length of the prior's knot vector (M prior sampling bound, msplines_jax.py:145-148)     */
 } wf_live_model;
 
 /* Device-resident basis tables of a model (a HOST struct of DEVICE pointers), all produced by wf_table_layout_host:
@@ -144,6 +144,7 @@ typedef struct wf_live_tables {
   const float* rec_P;
   const int32_t* lo_P;
   const float* ob_to_b;
+  const float* b_to_ob;   /* [P_P][P_P], B prior, sampler only (bsplines_jax.py:163-165) */
 } wf_live_tables;
 
 /* Packed weights (device, float32), one block per conditioner, IMADE nets first then the prior net; per net
@@ -171,6 +172,20 @@ int wf_live_forward(const wf_live_model* model_host, const wf_live_tables* table
 int wf_local_energy(const wf_live_model* model_host, const wf_live_tables* tables_host, const float* weights,
                     const float* protons_host, int n_protons, const float* x, int64_t N, float* psi, float* hpsi,
                     float* eloc, float* grad, float* lap, double* sums, void* stream);
+
+/* Serial.inverse_fun for the live flow (bijections.py:462-463): (Reverse, IMADE.inverse) x L then the box inverse.
+ * exact == 0 reproduces the reference (made.py:85-100: coefficients conditioned on the layer INPUT, quirk Q1; bisection
+ * of helpers.py:150-166 returning the lower bracket; box inverse of made.py:186-197, correct for D = 2 only).
+ * exact != 0 conditions each dimension on the already-inverted prefix and uses the true box inverse. */
+int wf_live_inverse(const wf_live_model* model_host, const wf_live_tables* tables_host, const float* weights,
+                    const float* u, int64_t N, int exact, float* x, void* stream);
+
+/* Waveflow.sample / MFlow.sample (wavefunctions.py:74-107, distributions.py:165-190): D rounds of conditioner ->
+ * per-sample rejection sampling of the prior (bsplines_jax.py:144-171, msplines_jax.py:129-154), then the inverse flow,
+ * in one launch.  Counter-based Philox4x32-10 streams keyed by (seed, sample index, column, attempt); NOT
+ * bit-compatible with JAX's threefry stream (statistical parity only).  u_out (nullable) receives the prior-space draws. */
+int wf_live_sample(const wf_live_model* model_host, const wf_live_tables* tables_host, const float* weights,
+                   uint64_t seed, int64_t N, int exact, float* x, float* u_out, void* stream);
 
 #ifdef __cplusplus
 }

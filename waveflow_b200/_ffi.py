@@ -31,12 +31,12 @@ class LiveModelStruct(C.Structure):
     _fields_ = [("D", C.c_int32), ("n_layers", C.c_int32), ("T", C.c_int32), ("P_I", C.c_int32), ("k_I", C.c_int32),
                 ("prior_kind", C.c_int32), ("P_P", C.c_int32), ("k_P", C.c_int32), ("has_box", C.c_int32),
                 ("coord_mean", C.c_int32), ("bc_I", C.c_int32), ("bc_P", C.c_int32), ("box", C.c_float),
-                ("reg", C.c_float), ("tol", C.c_float), ("reserved", C.c_float)]
+                ("reg", C.c_float), ("tol", C.c_float), ("n_knots_P", C.c_int32)]
 
 
 class LiveTablesStruct(C.Structure):
     """struct wf_live_tables (include/waveflow_b200.h): device pointers."""
-    _fields_ = [(n, C.c_void_p) for n in ("dense_I", "rec_I", "lo_I", "dense_P", "rec_P", "lo_P", "ob_to_b")]
+    _fields_ = [(n, C.c_void_p) for n in ("dense_I", "rec_I", "lo_I", "dense_P", "rec_P", "lo_P", "ob_to_b", "b_to_ob")]
 
 
 def _load() -> C.CDLL:
@@ -68,6 +68,8 @@ _SIGS = {
     "wf_rqs_apply": (_i, [_p, _p, _p, _p, _l, _i, _f, _i, _p, _p, _p, _p]),
     "wf_live_net_floats": (_l, [_i]),
     "wf_live_forward": (_i, [C.POINTER(LiveModelStruct), C.POINTER(LiveTablesStruct), _p, _p, _l, _p, _p, _p, _p, _p]),
+    "wf_live_inverse": (_i, [C.POINTER(LiveModelStruct), C.POINTER(LiveTablesStruct), _p, _p, _l, _i, _p, _p]),
+    "wf_live_sample": (_i, [C.POINTER(LiveModelStruct), C.POINTER(LiveTablesStruct), _p, C.c_uint64, _l, _i, _p, _p, _p]),
     "wf_local_energy": (_i, [C.POINTER(LiveModelStruct), C.POINTER(LiveTablesStruct), _p, _p, _i, _p, _l, _p, _p, _p, _p, _p,
                              _p, _p]),
 }

@@ -121,6 +121,7 @@ class LiveSpec:
         s.bc_P = _bc_bits_P(self.bc_P_left, self.bc_P_right)
         s.box = float(self.box or 0.0)
         s.reg, s.tol = float(self.reg), float(self.tol)
+        s.n_knots_P = len(self.tab_P.knots) if self.tab_P is not None else 0
         return s
 
 
@@ -143,7 +144,7 @@ def _tables(spec: LiveSpec, device) -> _ffi.LiveTablesStruct:
     t.dense_I, t.rec_I, t.lo_I = p(dI["dense32"]), p(dI["rec"]), p(dI["lo"])
     if spec.prior == "B":
         dP = spec.tab_P.dev(device)
-        t.dense_P, t.ob_to_b = p(dP["ob_dense32"]), p(dP["ob_to_b"])
+        t.dense_P, t.ob_to_b, t.b_to_ob = p(dP["ob_dense32"]), p(dP["ob_to_b"]), p(dP["b_to_ob"])
     elif spec.prior == "M":
         dP = spec.tab_P.dev(device)
         t.dense_P, t.rec_P, t.lo_P = p(dP["dense32"]), p(dP["rec"]), p(dP["lo"])
@@ -189,3 +190,25 @@ def local_energy(spec: LiveSpec, weights: torch.Tensor, x: torch.Tensor, protons
                              ptr(out.get("lap")), ptr(sums), stream_ptr())
     check(st, "wf_local_energy")
     return out
+
+
+def inverse(spec: LiveSpec, weights: torch.Tensor, u: torch.Tensor, exact: bool = False) -> torch.Tensor:
+    """wf_live_inverse: prior-space points [N, D] -> data space (Serial.inverse_fun)."""
+    u = _ffi.f32(u)
+    N = u.shape[0]
+    x = torch.empty_like(u)
+    tabs = _tables(spec, u.device)
+    st = lib.wf_live_inverse(C.byref(spec.struct()), C.byref(tabs), ptr(weights), ptr(u), N, int(bool(exact)), ptr(x), stream_ptr())
+    check(st, "wf_live_inverse")
+    return x
+
+
+def sample(spec: LiveSpec, weights: torch.Tensor, seed: int, n: int, device, exact: bool = False):
+    """wf_live_sample -> (x [n, D] data-space samples, u [n, D] prior-space draws)."""
+    x = torch.empty(n, spec.D, dtype=torch.float32, device=device)
+    u = torch.empty(n, spec.D, dtype=torch.float32, device=device)
+    tabs = _tables(spec, device)
+    st = lib.wf_live_sample(C.byref(spec.struct()), C.byref(tabs), ptr(weights), C.c_uint64(int(seed) & (2 ** 64 - 1)), n,
+                            int(bool(exact)), ptr(x), ptr(u), stream_ptr())
+    check(st, "wf_live_sample")
+    return x, u

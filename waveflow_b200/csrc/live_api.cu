@@ -1,6 +1,7 @@
 // C-ABI entry points of the fused live path (wf_live_forward, wf_local_energy).
 #include <string.h>
 #include "live_kernel.cuh"
+#include "live_inverse.cuh"
 
 using namespace wf;
 
@@ -91,4 +92,57 @@ extern "C" int wf_local_energy(const wf_live_model* model, const wf_live_tables*
   P.n_protons = n_protons;
   for (int i = 0; i < n_protons; ++i) P.protons[i] = protons[i];   // HOST array (a handful of floats)
   return dispatch(P, true, stream);
+}
+
+namespace {
+int fill_inverse(const wf_live_model* m, const wf_live_tables* t, const float* weights, int64_t N, bool sample, InvParams& P) {
+  LiveParams L;
+  // same validation as the forward path (x is checked by the callers)
+  const float dummy = 0.f;
+  const int st = fill_params(m, t, weights, &dummy, N, L);
+  if (st != WF_OK) return st;
+  if (m->n_layers > 0 && !(m->tol > 0.f)) return WF_ERR_INVALID_ARG;
+  const bool pnet = m->prior_kind == WF_KIND_B || m->prior_kind == WF_KIND_M;
+  if (sample && !pnet) return WF_ERR_INVALID_ARG;
+  if (sample && m->prior_kind == WF_KIND_B && !t->b_to_ob) return WF_ERR_INVALID_ARG;
+  if (sample && m->prior_kind == WF_KIND_M && m->n_knots_P <= 0) return WF_ERR_INVALID_ARG;
+  memset(&P, 0, sizeof(P));
+  P.m = *m; P.weights = weights; P.N = N;
+  P.rec_I = t->rec_I; P.lo_I = t->lo_I; P.tab_I = t->dense_I; P.tab_P = t->dense_P;
+  P.ob_to_b = t->ob_to_b; P.b_to_ob = t->b_to_ob;
+  P.n_knots_P = m->n_knots_P;
+  for (int q = 0; q < WF_MAX_P; ++q) { P.wq_I[q] = L.wq_I[q]; P.wq_P[q] = L.wq_P[q]; }
+  return WF_OK;
+}
+int dispatch_inverse(InvParams& P, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  switch (P.m.D) {
+    case 2: return launch_inverse_d2(P, s);
+    case 3: return launch_inverse_d3(P, s);
+    case 4: return launch_inverse_d4(P, s);
+    default: return WF_ERR_UNSUPPORTED;
+  }
+}
+}  // namespace
+
+extern "C" int wf_live_inverse(const wf_live_model* model, const wf_live_tables* tables, const float* weights, const float* u,
+                               int64_t N, int exact, float* x, void* stream) {
+  if (N == 0) return WF_OK;
+  if (!u || !x) return WF_ERR_INVALID_ARG;
+  InvParams P;
+  const int st = fill_inverse(model, tables, weights, N, false, P);
+  if (st != WF_OK) return st;
+  P.u_in = u; P.x_out = x; P.exact = exact ? 1 : 0; P.do_sample = 0;
+  return dispatch_inverse(P, stream);
+}
+
+extern "C" int wf_live_sample(const wf_live_model* model, const wf_live_tables* tables, const float* weights, uint64_t seed,
+                              int64_t N, int exact, float* x, float* u_out, void* stream) {
+  if (N == 0) return WF_OK;
+  if (!x) return WF_ERR_INVALID_ARG;
+  InvParams P;
+  const int st = fill_inverse(model, tables, weights, N, true, P);
+  if (st != WF_OK) return st;
+  P.x_out = x; P.u_out = u_out; P.seed = seed; P.exact = exact ? 1 : 0; P.do_sample = 1;
+  return dispatch_inverse(P, stream);
 }
