@@ -59,14 +59,19 @@ class EnergyEstimator:
         _live.local_energy(self.spec, self.packed, walkers, self.h_fn.protons, want=(), sums=sums)
         return sums
 
-    def estimate(self, walkers: torch.Tensor):
-        """-> dict(energy, variance, n) over all ranks."""
-        sums = self.local_sums(walkers)
-        if torch.distributed.is_available() and torch.distributed.is_initialized() and torch.distributed.get_world_size(self.group) > 1:
-            torch.distributed.all_reduce(sums, group=self.group)
-        s = sums.cpu().numpy()
+    @staticmethod
+    def reduce(sums: torch.Tensor, group=None):
+        """All-reduce the per-rank {sum E, sum E^2, n, sum psi^2} (float64 [4]) and turn them into the estimator.
+        Backend-agnostic (NCCL on the GPUs, gloo in the CPU tests)."""
+        if torch.distributed.is_available() and torch.distributed.is_initialized() and torch.distributed.get_world_size(group) > 1:
+            torch.distributed.all_reduce(sums, group=group)
+        s = sums.detach().cpu().numpy()
         mean = s[0] / s[2]
         return dict(energy=float(mean), variance=float(s[1] / s[2] - mean * mean), n=int(s[2]), psi2=float(s[3]))
+
+    def estimate(self, walkers: torch.Tensor):
+        """-> dict(energy, variance, n) over all ranks."""
+        return self.reduce(self.local_sums(walkers), self.group)
 
 
 class ModelTrainer:
