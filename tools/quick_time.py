@@ -43,6 +43,26 @@ for K in ((32, 64) if ONLY in ("all", "rqs") else ()):
         med, mn = timeit(lambda: unconstrained_RQS(x, uw, uh, ud, inverse=inv, tail_bound=3.0))
         res[f"rqs_K{K}_inv{int(inv)}"] = dict(ms=med, min_ms=mn, GBs=M * 4 * (3 * K + 2) / med / 1e6, elems_per_s=M / med * 1e3)
     del uw, uh, ud, x
+# 2b. fused coupling flow (BASELINE config 3 ii)
+if ONLY in ("all", "coupling"):
+    from waveflow_b200.flows.neural_splines import coupling_flow
+    from oracle import rqs as orqs
+    for D, hidden in ((2, 8), (8, 8), (2, 64), (8, 64)):
+        rng = np.random.default_rng(0); K = 32
+        out = (3 * K - 1) * D // 2
+        t = lambda a: torch.from_numpy(a).to(dev)
+        layers = []
+        for _ in range(8):
+            pair = []
+            for _f in range(2):
+                (W1, b1), (W2, b2), (W3, b3) = orqs.random_fcnn(rng, D // 2, hidden, out)
+                pair.append([(t(W1), t(b1)), (), (t(W2), t(b2)), (), (t(W3), t(b3))])
+            layers.append(tuple(pair))
+        N = 1 << 22
+        x = torch.rand(N, D, device=dev) * 6 - 3
+        for inv in (False, True):
+            med, mn = timeit(lambda: coupling_flow(layers, x, K, 3.0, hidden, inverse=inv), n=5)
+            res[f"coupling_D{D}_h{hidden}_inv{int(inv)}_N2^22"] = dict(ms=med, samples_per_s=N / med * 1e3)
 # 3. fused live
 sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
 from oracle import fixtures as fx

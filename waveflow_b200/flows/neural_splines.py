@@ -41,3 +41,77 @@ def unconstrained_RQS(inputs, unnormalized_widths, unnormalized_heights, unnorma
     if return_bin_idx:
         return out.reshape(shape), lad.reshape(shape), bins.reshape(shape)
     return out.reshape(shape), lad.reshape(shape)
+
+
+# ---------------------------------------------------------------------------------------------------- coupling layer
+def _pack_fcnn(net, half: int, K: int, Hd: int, device) -> torch.Tensor:
+    """stax.serial(Dense, Tanh, Dense, Tanh, Dense) params -> the chunked layout of wf_rqs_coupling_flow."""
+    (W1, b1), _, (W2, b2), _, (W3, b3) = net
+    t = lambda a: torch.as_tensor(a, dtype=torch.float32, device=device)
+    W1, b1, W2, b2, W3, b3 = t(W1), t(b1), t(W2), t(b2), t(W3), t(b3)
+    if W1.shape != (half, Hd) or W2.shape != (Hd, Hd) or W3.shape != (Hd, (3 * K - 1) * half):
+        raise _ffi.WaveflowB200Error(f"unexpected FCNN shapes {tuple(W1.shape)} {tuple(W2.shape)} {tuple(W3.shape)}")
+    KP = 8 if K <= 8 else 32
+    head = torch.cat([W1.reshape(-1), b1, W2.reshape(-1), b2])
+    pad = (-head.numel()) % 4
+    parts = [head, torch.zeros(pad, dtype=torch.float32, device=device)]
+    W3 = W3.reshape(Hd, half, 3 * K - 1)                                    # out.reshape(-1, dim//2, 3K-1)  (:258)
+    b3 = b3.reshape(half, 3 * K - 1)
+    for j in range(half):
+        Wj = torch.zeros(Hd, 3 * KP, dtype=torch.float32, device=device)
+        bj = torch.zeros(3 * KP, dtype=torch.float32, device=device)
+        for blk, (lo, n) in enumerate([(0, K), (K, K), (2 * K, K - 1)]):     # array_split -> (K, K, K-1)  (:259)
+            Wj[:, blk * KP:blk * KP + n] = W3[:, j, lo:lo + n]
+            bj[blk * KP:blk * KP + n] = b3[j, lo:lo + n]
+        parts += [Wj.reshape(-1), bj]
+    return torch.cat(parts)
+
+
+def coupling_flow(layers, x, K: int, B: float, hidden_dim: int, inverse: bool = False):
+    """Serial(NeuralSplineCoupling * L) in one launch.  layers = [(f1_params, f2_params), ...] -> (y, log_det)."""
+    x = f32(x)
+    N, D = x.shape
+    half = D // 2
+    w = torch.cat([_pack_fcnn(f, half, K, hidden_dim, x.device) for pair in layers for f in pair]).contiguous()
+    expect = lib.wf_rqs_coupling_net_floats(D, K, hidden_dim) * 2 * len(layers)
+    if w.numel() != expect:
+        raise _ffi.WaveflowB200Error("packed coupling weights have the wrong size")
+    y = torch.empty_like(x)
+    ld = torch.empty(N, dtype=torch.float32, device=x.device)
+    st = lib.wf_rqs_coupling_flow(ptr(w), len(layers), D, K, hidden_dim, float(B), int(bool(inverse)), ptr(x), N, ptr(y),
+                                  ptr(ld), stream_ptr())
+    check(st, "wf_rqs_coupling_flow")
+    return y, ld
+
+
+def FCNN(out_dim, hidden_dim):
+    """stax.serial(Dense, Tanh, Dense, Tanh, Dense) (neural_splines.py:187-188): -> init_fun(rng, in_dim) -> params."""
+    def init_fun(rng, in_dim):
+        from ..splines.factories import _gen
+        g = _gen(rng)
+
+        def dense(i, o):       # stax.Dense: glorot-normal W, N(0, 1e-2) b
+            return (torch.randn(i, o, generator=g) * (2.0 / (i + o)) ** 0.5, torch.randn(o, generator=g) * 1e-2)
+        return [dense(in_dim, hidden_dim), (), dense(hidden_dim, hidden_dim), (), dense(hidden_dim, out_dim)]
+    return init_fun
+
+
+def NeuralSplineCoupling(K=5, B=3, hidden_dim=8, network=FCNN):
+    """neural_splines.py:244-296.  Unlike the reference (which closes over its initial parameters and ignores the
+    `params` argument, quirk Q7) the functions here use the parameters they are given."""
+    def init_fun(rng, dim, **kwargs):
+        from .bijections import _split_rng
+        f1_rng, f2_rng = _split_rng(rng)
+        f1_params = network((3 * K - 1) * dim // 2, hidden_dim)(f1_rng, dim // 2)
+        f2_params = network((3 * K - 1) * dim // 2, hidden_dim)(f2_rng, dim // 2)
+
+        def direct_fun(params, x, **kwargs):
+            return coupling_flow([params], x, K, B, hidden_dim, inverse=False)
+
+        def inverse_fun(params, z, **kwargs):
+            return coupling_flow([params], z, K, B, hidden_dim, inverse=True)
+
+        direct_fun.wf_layer = ("coupling", dict(K=K, B=float(B), hidden=hidden_dim))
+        return (f1_params, f2_params), direct_fun, inverse_fun
+
+    return init_fun
