@@ -51,13 +51,17 @@ def pack_net(net, D: int, P: int, device) -> torch.Tensor:
         raise _ffi.WaveflowB200Error(f"unexpected conditioner shapes {tuple(W1.shape)}, {tuple(W2.shape)}, {tuple(W3.shape)} "
                                      f"for D={D}, P={P} (hidden width is fixed at 64, model_factory.py:72)")
     m1, m2, m3 = _masks_on(D, device)
-    W3m = (W3 * m3.repeat(1, P)).reshape(HIDDEN, P, D).permute(0, 2, 1)          # [64, D, P]
+    # hidden units sorted by MADE degree (stable): a relabelling of the units that lets the kernel skip whole masked
+    # segments (csrc/live_device.cuh, deg_prefix); invisible in the results
+    perm = torch.from_numpy(np.argsort(np.arange(HIDDEN) % (D - 1), kind="stable")).to(device)
+    W1m, b1p = (W1 * m1)[:, perm], b1[perm]
+    W2m, b2p = (W2 * m2)[perm][:, perm], b2[perm]
+    W3m = (W3 * m3.repeat(1, P))[perm].reshape(HIDDEN, P, D).permute(0, 2, 1)    # [64, D, P]
     W3p = torch.zeros(HIDDEN, D, MAXP, dtype=torch.float32, device=device)
     W3p[:, :, :P] = W3m
     b3p = torch.zeros(D, MAXP, dtype=torch.float32, device=device)
     b3p[:, :P] = b3.reshape(P, D).t()
-    return torch.cat([(W1 * m1).reshape(-1), b1.reshape(-1), (W2 * m2).reshape(-1), b2.reshape(-1), W3p.reshape(-1),
-                      b3p.reshape(-1)])
+    return torch.cat([W1m.reshape(-1), b1p.reshape(-1), W2m.reshape(-1), b2p.reshape(-1), W3p.reshape(-1), b3p.reshape(-1)])
 
 
 def _bc_bits_I(left: dict, right: dict) -> int | None:

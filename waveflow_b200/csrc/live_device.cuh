@@ -153,6 +153,52 @@ struct Scratch {
   __device__ __forceinline__ float& operator[](int slot) const { return col[slot * LIVE_THREADS]; }
 };
 
+// MADE connectivity (model_factory.py:8-19): hidden unit i has degree i % (D-1); a unit of degree c sees inputs of degree
+// <= c, output dimension dd sees hidden units of degree <= dd-1.  The host packs the hidden units SORTED BY DEGREE
+// (_live.pack_net), so "degree <= c" is the index prefix [0, deg_prefix<D>(c)) and whole segments of the (unrolled)
+// reduction loops can be skipped with warp-uniform branches -- a third of the layer-2/3 FMAs at D = 4.
+template <int D> __host__ __device__ constexpr int deg_prefix(int c) {      // number of hidden units with degree <= c
+  int n = 0;
+  for (int i = 0; i < WF_HIDDEN; ++i) n += ((i % (D - 1)) <= c) ? 1 : 0;
+  return n;
+}
+template <int D> __host__ __device__ constexpr int unit_degree_sorted(int j) {   // degree of the j-th unit in sorted order
+  int c = 0;
+  while (deg_prefix<D>(c) <= j) ++c;
+  return c;
+}
+
+// acc[0..8) += sum over the hidden units of degree C of h[i] * W[i * stride + 0..8)   (compile-time index range)
+template <int D, int C>
+__device__ __forceinline__ void fma_degree_segment(const float (&h)[WF_HIDDEN], const float* __restrict__ W, int stride,
+                                                   float (&acc)[8]) {
+  constexpr int LO = C == 0 ? 0 : deg_prefix<D>(C - 1);
+  constexpr int HI = deg_prefix<D>(C);
+#pragma unroll
+  for (int i = LO; i < HI; ++i) {
+    const float4 wa = lds4(W + i * stride), wb = lds4(W + i * stride + 4);
+    acc[0] = fmaf(h[i], wa.x, acc[0]); acc[1] = fmaf(h[i], wa.y, acc[1]);
+    acc[2] = fmaf(h[i], wa.z, acc[2]); acc[3] = fmaf(h[i], wa.w, acc[3]);
+    acc[4] = fmaf(h[i], wb.x, acc[4]); acc[5] = fmaf(h[i], wb.y, acc[5]);
+    acc[6] = fmaf(h[i], wb.z, acc[6]); acc[7] = fmaf(h[i], wb.w, acc[7]);
+  }
+}
+// all segments of degree <= cmax (cmax is warp-uniform)
+template <int D, int C = 0>
+__device__ __forceinline__ void fma_degree_prefix(const float (&h)[WF_HIDDEN], const float* __restrict__ W, int stride,
+                                                  int cmax, float (&acc)[8]) {
+  if constexpr (C < D - 1) {
+    if (C <= cmax) fma_degree_segment<D, C>(h, W, stride, acc);
+    fma_degree_prefix<D, C + 1>(h, W, stride, cmax, acc);
+  }
+}
+// degree of the last unit of the 8-wide output block starting at j0 (sorted order)
+template <int D, int C = 1>
+__device__ __forceinline__ int block_degree(int j0, int cur = 0) {
+  if constexpr (C < D - 1) return block_degree<D, C + 1>(j0, (j0 + 7 >= deg_prefix<D>(C - 1)) ? C : cur);
+  else return cur;
+}
+
 // Hidden layers of one conditioner: h = tanh(tanh(u W1 + b1) W2 + b2) (masked weights are stored as zeros).
 // On return h[] holds the second hidden layer and the scratch column is free.
 template <int D, bool LAP>
@@ -185,14 +231,8 @@ __device__ __forceinline__ void mlp_hidden(const Ctx<D, LAP>& cx, const float* _
     float acc[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
 #pragma unroll
     for (int t = 0; t < 8; ++t) acc[t] = cx.is_v ? acc[t] : 0.f;
-#pragma unroll
-    for (int i = 0; i < WF_HIDDEN; ++i) {
-      const float4 wa = lds4(W2 + i * WF_HIDDEN + j0), wb = lds4(W2 + i * WF_HIDDEN + j0 + 4);
-      acc[0] = fmaf(h[i], wa.x, acc[0]); acc[1] = fmaf(h[i], wa.y, acc[1]);
-      acc[2] = fmaf(h[i], wa.z, acc[2]); acc[3] = fmaf(h[i], wa.w, acc[3]);
-      acc[4] = fmaf(h[i], wb.x, acc[4]); acc[5] = fmaf(h[i], wb.y, acc[5]);
-      acc[6] = fmaf(h[i], wb.z, acc[6]); acc[7] = fmaf(h[i], wb.w, acc[7]);
-    }
+    // inputs needed by this block of 8 outputs: all units of degree <= degree(last output of the block)
+    fma_degree_prefix<D>(h, W2 + j0, WF_HIDDEN, block_degree<D>(j0), acc);
 #pragma unroll
     for (int t = 0; t < 8; ++t) S[j0 + t] = tanh_bundle<D, LAP>(cx, acc[t]);   // h (layer 1) is already in registers
   }
@@ -213,17 +253,8 @@ __device__ __forceinline__ void mlp_out(const Ctx<D, LAP>& cx, const float* __re
     float acc[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
 #pragma unroll
     for (int t = 0; t < 8; ++t) acc[t] = cx.is_v ? acc[t] : 0.f;
-    if (dd > 0) {
-      const float* wr0 = W3 + dd * WF_MAX_P + q0;
-#pragma unroll
-      for (int i = 0; i < WF_HIDDEN; ++i) {
-        const float4 wa = lds4(wr0 + i * D * WF_MAX_P), wb = lds4(wr0 + i * D * WF_MAX_P + 4);
-        acc[0] = fmaf(h[i], wa.x, acc[0]); acc[1] = fmaf(h[i], wa.y, acc[1]);
-        acc[2] = fmaf(h[i], wa.z, acc[2]); acc[3] = fmaf(h[i], wa.w, acc[3]);
-        acc[4] = fmaf(h[i], wb.x, acc[4]); acc[5] = fmaf(h[i], wb.y, acc[5]);
-        acc[6] = fmaf(h[i], wb.z, acc[6]); acc[7] = fmaf(h[i], wb.w, acc[7]);
-      }
-    }
+    // hidden units of degree c feed output dimension dd iff c <= dd - 1 (dimension 0: bias only)
+    fma_degree_prefix<D>(h, W3 + dd * WF_MAX_P + q0, D * WF_MAX_P, dd - 1, acc);
 #pragma unroll
     for (int t = 0; t < 8; ++t) S[q0 + t] = acc[t];
   }
