@@ -138,7 +138,7 @@ class ClockSampler:
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         self.p = None
         try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "25",
                                        "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
@@ -156,7 +156,8 @@ class ClockSampler:
         os.unlink(self.f.name)
         if not rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        sm = [float(r[1]) for r in rows]
+        busy = [r for r in rows if float(r[3]) > 200.0] or rows     # samples taken under load (warm-up + timed steps)
+        sm = [float(r[1]) for r in busy]
         reasons = set()
         for r in rows:
             for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
@@ -214,13 +215,14 @@ def run_b200(args):
 
     # ---------------- device-timed region: K steps, inputs resident in HBM
     all_sums = torch.zeros(warm + steps, 4, dtype=torch.float64, device=dev)
+    clocks = ClockSampler(local_rank)        # nvidia-smi needs ~0.2 s to start: launched before the warm-up
+    time.sleep(0.3)
     for i in range(warm):
         l2_flush(); step(all_sums[i])
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    clocks = ClockSampler(local_rank)
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
           for _ in range(steps)]
     t_wall0 = time.perf_counter()
@@ -328,10 +330,67 @@ def run_b200(args):
                               "inputs": "2.1 GB per launch (> 126 MB L2)"}}
         del c, xs
 
+    # ---------------- BASELINE config 3: RQS operator (HBM-bound) and the fused 8-layer coupling flow, 2^24 samples
+    rqs_sweep = None
+    coupling = None
+    if world == 1 and not args.no_sweep:
+        from waveflow_b200.flows.neural_splines import coupling_flow, unconstrained_RQS
+        g = torch.Generator(device=dev); g.manual_seed(0)
+        M, K = 1 << 24, 32
+        uw = torch.randn(M, K, device=dev, generator=g); uh = torch.randn(M, K, device=dev, generator=g)
+        ud = torch.randn(M, K - 1, device=dev, generator=g)
+        xs = torch.rand(M, device=dev, generator=g) * 6 - 3
+        res = {}
+        for inv in (False, True):
+            for _ in range(3):
+                unconstrained_RQS(xs, uw, uh, ud, inverse=inv, tail_bound=3.0)
+            ts = []
+            for _ in range(5):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(); unconstrained_RQS(xs, uw, uh, ud, inverse=inv, tail_bound=3.0); b.record(); torch.cuda.synchronize()
+                ts.append(a.elapsed_time(b))
+            ms = float(np.mean(ts))
+            gbs = M * 4 * (3 * K + 2) / (ms * 1e-3) / 1e9
+            res["inverse" if inv else "forward"] = {"ms": ms, "elements_per_s": M / (ms * 1e-3),
+                                                     "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s",
+                                                                  "frac": gbs / hbm_peak, "traffic": None,
+                                                                  "algorithmic_bytes_per_element": 4 * (3 * K + 2), "peak_source": hbm_src}}
+        rqs_sweep = {"kernel": "rqs_kernel<32, true> (wf_rqs_apply)", "elements": M, "K": K, "inputs": "6.6 GB per launch (> L2)", **res}
+        del uw, uh, ud, xs
+        coupling = {}
+        crng = np.random.Generator(np.random.PCG64(0))
+        for D in (2, 8):
+            hidden, L = 8, 8
+            out_dim = (3 * K - 1) * D // 2
+            layers = []
+            for _ in range(L):
+                pair = []
+                for _f in range(2):
+                    gW = lambda a, b: torch.from_numpy((crng.standard_normal((a, b)) / np.sqrt(a)).astype(np.float32)).to(dev)
+                    z = lambda n: torch.zeros(n, device=dev)
+                    pair.append([(gW(D // 2, hidden), z(hidden)), (), (gW(hidden, hidden), z(hidden)), (), (gW(hidden, out_dim), z(out_dim))])
+                layers.append(tuple(pair))
+            x = torch.rand(M, D, device=dev, generator=g) * 6 - 3
+            r = {}
+            for inv in (False, True):
+                for _ in range(2):
+                    coupling_flow(layers, x, K, 3.0, hidden, inverse=inv)
+                ts = []
+                for _ in range(3):
+                    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    a.record(); coupling_flow(layers, x, K, 3.0, hidden, inverse=inv); b.record(); torch.cuda.synchronize()
+                    ts.append(a.elapsed_time(b))
+                ms = float(np.mean(ts))
+                r["inverse" if inv else "density"] = {"ms": ms, "samples_per_s": M / (ms * 1e-3),
+                                                      "hbm_frac_of_measured": M * (8 * D + 4) / (ms * 1e-3) / 1e9 / hbm_peak}
+            coupling[f"D{D}"] = {"samples": M, "K": K, "layers": L, "hidden": hidden, **r,
+                                 "note": "MUFU/issue bound by construction (SURVEY 8d regime ii): 8D+4 bytes per sample"}
+            del x
+
     # ---------------- CPU baseline (rank 0, N = 1): bounded sample of the same workload
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        n_sample = min(wl["n_walkers"], 16384)
+        n_sample = min(wl["n_walkers"], 8192)
         v, sec, thr = cpu_reference(wl, n_sample, reps=5)
         cpu = {"value": v, "unit": UNIT, "cores": thr, "kind": "port", "sample": f"first {n_sample} walkers of the workload, 5 passes, median",
                "seconds_per_pass": sec,
@@ -352,7 +411,7 @@ def run_b200(args):
                     "ms_per_step": e2e_s / steps * 1e3},
             "gpu_launches": steps,
             "kernel_ms_per_step": kern_ms_mean, "wall_s_timed_region": t_wall,
-            "roofline": roofline, "cpu_baseline": cpu, "spline_sweep": sweep,
+            "roofline": roofline, "cpu_baseline": cpu, "spline_sweep": sweep, "rqs_sweep": rqs_sweep, "coupling_flow_sweep": coupling,
             "energy_estimate": {"mean": float(s[0] / s[2]), "n": int(s[2])}}
     print(json.dumps(line))
     if world > 1:
@@ -362,7 +421,7 @@ def run_b200(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="vqmc_c4", choices=["vqmc_c4", "vqmc_c2"])

@@ -56,6 +56,7 @@ struct LiveParams {
   float protons[WF_MAX_D];
   int n_protons;
   int n_nets;
+  int warps_per_cta;      // working warps per CTA (<= LIVE_THREADS / 32), chosen by the launcher
 };
 
 // m: this lane's component; p: pending second derivative (gradient lanes only); v: the VALUE, known to every lane.

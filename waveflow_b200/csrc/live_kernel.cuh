@@ -59,7 +59,9 @@ __global__ void __launch_bounds__(LIVE_THREADS, 1) live_kernel(const __grid_cons
   C cx;
   cx.init(lane);
   const Scratch S{scratch + tid};
-  constexpr int WPB = (LIVE_THREADS / 32) * C::WPW;     // walkers per CTA batch
+  // small problems are spread over more SMs with fewer working warps per CTA (latency, not throughput, matters there)
+  const int WPB = P.warps_per_cta * C::WPW;             // walkers per CTA batch
+  const bool warp_works = warp < P.warps_per_cta;
   const int64_t n_batches = (P.N + WPB - 1) / WPB;
   const int n_nets = P.n_nets;
   const bool has_prior_net = M.prior_kind == WF_KIND_B || M.prior_kind == WF_KIND_M;
@@ -154,6 +156,7 @@ __global__ void __launch_bounds__(LIVE_THREADS, 1) live_kernel(const __grid_cons
       if (tid == 0 && g + 1 < g_total) issue_net(g + 1);
       mbar_wait(&bars[g & 1], (uint32_t)((g >> 1) & 1));
       const float* net = nets_s + (size_t)(g & 1) * NETF;
+      if (!warp_works) continue;               // idle warps only take part in the CTA-wide weight hand-over
 
       float h[WF_HIDDEN];
       mlp_hidden<D, LAP>(cx, net, us, S, h);
@@ -209,7 +212,7 @@ __global__ void __launch_bounds__(LIVE_THREADS, 1) live_kernel(const __grid_cons
     const float psi1 = cx.fold(psi);
 
     // ---------------------------------------------------------------- outputs
-    if (lane_live && cx.is_v) {
+    if (warp_works && lane_live && cx.is_v) {
       if (P.u) {
 #pragma unroll
         for (int d = 0; d < D; ++d) P.u[w * D + d] = uout[d];
@@ -220,8 +223,8 @@ __global__ void __launch_bounds__(LIVE_THREADS, 1) live_kernel(const __grid_cons
     }
     if constexpr (LAP) {
       const float lapv = __shfl_sync(FULL, psi1, cx.gbase + D + 1);
-      if (lane_live && cx.is_g && P.grad) P.grad[w * D + (cx.comp - 1)] = psi1;
-      if (lane_live && cx.is_v) {
+      if (warp_works && lane_live && cx.is_g && P.grad) P.grad[w * D + (cx.comp - 1)] = psi1;
+      if (warp_works && lane_live && cx.is_v) {
         const float V = soft_coulomb<D>(xs, P.protons, P.n_protons);
         const float hp = fmaf(-0.5f, lapv, V * psi.v);           // physics.py:84
         const float el = hp / (psi.v + 1e-8f);                  // vqmc.py:200
@@ -257,7 +260,12 @@ int launch_live(LiveParams& P, cudaStream_t s) {
   const size_t smem = LiveSmem::total(D);
   if (smem > 227 * 1024) return WF_ERR_UNSUPPORTED;
   const int wpw = LAP ? 32 / (D + 2) : 32;
-  const int64_t wpb = (int64_t)(LIVE_THREADS / 32) * wpw;
+  const int64_t warp_tasks = (P.N + wpw - 1) / wpw;
+  int wpc = (int)((warp_tasks + num_sms() - 1) / num_sms());
+  if (wpc < 1) wpc = 1;
+  if (wpc > LIVE_THREADS / 32) wpc = LIVE_THREADS / 32;
+  P.warps_per_cta = wpc;
+  const int64_t wpb = (int64_t)wpc * wpw;
   const int64_t n_batches = (P.N + wpb - 1) / wpb;
   const int blocks = (int)(n_batches < num_sms() ? n_batches : num_sms());
   WF_CUDA(cudaFuncSetAttribute(live_kernel<D, LAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
