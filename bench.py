@@ -180,6 +180,8 @@ def run_b200(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's version banner off stdout: one JSON line only
         dist.init_process_group("nccl", device_id=dev)
 
     from waveflow_b200 import _ffi, _live, model_factory, vqmc
@@ -413,7 +415,7 @@ def run_b200(args):
             "kernel_ms_per_step": kern_ms_mean, "wall_s_timed_region": t_wall,
             "roofline": roofline, "cpu_baseline": cpu, "spline_sweep": sweep, "rqs_sweep": rqs_sweep, "coupling_flow_sweep": coupling,
             "energy_estimate": {"mean": float(s[0] / s[2]), "n": int(s[2])}}
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
