@@ -197,6 +197,21 @@ int64_t wf_rqs_coupling_net_floats(int D, int K, int Hd);
 int wf_rqs_coupling_flow(const float* weights, int n_layers, int D, int K, int Hd, float tail_bound, int inverse,
                          const float* x, int64_t N, float* y, float* logdet, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * Tensor-core (tcgen05 + TMEM + TMA) dense layers with float32-grade accuracy ("3xTF32"), for the wide conditioner MLPs
+ * of the coupling flow (neural_splines.py:187-188 at hidden_dim = 512, BASELINE config 5).
+ * ------------------------------------------------------------------------------------------------------------------ */
+
+/* x -> TF32-exact planes hi = tf32(x), lo = tf32(x - hi)  (n elements). */
+int wf_tf32_split(const float* x, int64_t n, float* hi, float* lo, void* stream);
+
+/* out = act(A W^T + bias):  A = a_hi + a_lo [M][K] (TF32-exact planes), W = w_hi + w_lo [N][K] (row-major, i.e. the
+ * stax.Dense kernel transposed), accumulated as a_hi w_hi + a_hi w_lo + a_lo w_hi in fp32 in tensor memory.
+ * mode 0: out_hi [M][N] = result (+ bias).   mode 1: tanh, then split into TF32-exact planes out_hi / out_lo (the next
+ * layer's A operand).  K % 32 == 0, N % 128 == 0, all pointers 16-byte aligned; bias [N] nullable. */
+int wf_tc_dense(const float* a_hi, const float* a_lo, int64_t M, int K, const float* w_hi, const float* w_lo, int N,
+                const float* bias, int mode, float* out_hi, float* out_lo, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -67,6 +67,8 @@ _SIGS = {
     "wf_spline_reverse": (_i, [_p, _i, _i, _p, _p, _l, _f, _p, _p, _p]),
     "wf_rqs_apply": (_i, [_p, _p, _p, _p, _l, _i, _f, _i, _p, _p, _p, _p]),
     "wf_live_net_floats": (_l, [_i]),
+    "wf_tf32_split": (_i, [_p, _l, _p, _p, _p]),
+    "wf_tc_dense": (_i, [_p, _p, _l, _i, _p, _p, _i, _p, _i, _p, _p, _p]),
     "wf_rqs_coupling_net_floats": (_l, [_i, _i, _i]),
     "wf_rqs_coupling_flow": (_i, [_p, _i, _i, _i, _i, _f, _i, _p, _l, _p, _p, _p]),
     "wf_live_forward": (_i, [C.POINTER(LiveModelStruct), C.POINTER(LiveTablesStruct), _p, _p, _l, _p, _p, _p, _p, _p]),
