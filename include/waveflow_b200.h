@@ -212,6 +212,19 @@ int wf_tf32_split(const float* x, int64_t n, float* hi, float* lo, void* stream)
 int wf_tc_dense(const float* a_hi, const float* a_lo, int64_t M, int K, const float* w_hi, const float* w_lo, int N,
                 const float* bias, int mode, float* out_hi, float* out_lo, void* stream);
 
+/* Serial(NeuralSplineCoupling x L) for D = 64, K = 64 bins, hidden_dim = 512 (BASELINE config 5) on the tensor cores:
+ * three tcgen05 GEMMs per half-update, the rational-quadratic spline evaluated in the epilogue of the third one straight
+ * from tensor memory (the [N, 6112] parameter tensor never exists in HBM).
+ * weights: per layer f1 then f2, each wf_rqs_coupling_tc_net_floats() floats:
+ *   W1t_hi [512][32] | W1t_lo | b1 [512] | W2t_hi [512][512] | W2t_lo | b2 [512] | W3t_hi [32*192][512] | W3t_lo | b3p [32*192]
+ * (transposed stax.Dense kernels as TF32-exact hi/lo planes; third layer regrouped per target dimension: 64 widths,
+ * 64 heights, 63 derivatives, 1 pad).  workspace: wf_rqs_coupling_tc_workspace_floats(rows) floats for a chunk of `rows`
+ * samples (the call loops over chunks); y [N][64] doubles as the state buffer.  All buffers 16-byte aligned. */
+int64_t wf_rqs_coupling_tc_net_floats(void);
+int64_t wf_rqs_coupling_tc_workspace_floats(int64_t rows);
+int wf_rqs_coupling_flow_tc(const float* weights, int n_layers, float tail_bound, int inverse, const float* x, int64_t N,
+                            float* y, float* logdet, float* workspace, int64_t workspace_floats, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -68,6 +68,9 @@ _SIGS = {
     "wf_rqs_apply": (_i, [_p, _p, _p, _p, _l, _i, _f, _i, _p, _p, _p, _p]),
     "wf_live_net_floats": (_l, [_i]),
     "wf_tf32_split": (_i, [_p, _l, _p, _p, _p]),
+    "wf_rqs_coupling_tc_net_floats": (_l, []),
+    "wf_rqs_coupling_tc_workspace_floats": (_l, [_l]),
+    "wf_rqs_coupling_flow_tc": (_i, [_p, _i, _f, _i, _p, _l, _p, _p, _p, _l, _p]),
     "wf_tc_dense": (_i, [_p, _p, _l, _i, _p, _p, _i, _p, _i, _p, _p, _p]),
     "wf_rqs_coupling_net_floats": (_l, [_i, _i, _i]),
     "wf_rqs_coupling_flow": (_i, [_p, _i, _i, _i, _i, _f, _i, _p, _l, _p, _p, _p]),

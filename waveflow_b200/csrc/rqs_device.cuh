@@ -77,24 +77,32 @@ __device__ __forceinline__ void knot_pair(const float (&a)[KMAX], int K, float l
     }
 }
 
-// a/b: unnormalised widths/heights (destroyed).  dget(j), j in [0, K-2]: unnormalised interior derivative j.
-template <int KMAX, class DGet>
-__device__ __forceinline__ void rqs_eval(float x, float (&a)[KMAX], float (&b)[KMAX], int K, float B, bool inverse,
-                                         DGet dget, float& out, float& lad, int& bin) {
+// Located bin of an element: knots of the bin in both directions
+struct RqsBin { int idx; float cwl, in_w, chl, in_h; };
+
+// a/b: unnormalised widths/heights (destroyed: they become the right knots).
+template <int KMAX>
+__device__ __forceinline__ RqsBin rqs_locate(float x, float (&a)[KMAX], float (&b)[KMAX], int K, float B, bool inverse) {
   const int cnt_w = knots_inplace<KMAX>(a, K, -B, B, x);
   const int cnt_h = knots_inplace<KMAX>(b, K, -B, B, x);
-  int idx = (inverse ? cnt_h : cnt_w) - 1;
-  idx = min(max(idx, 0), K - 1);
-  bin = idx;
-  float cwl, cwr, chl, chr;
-  knot_pair<KMAX>(a, K, -B, idx, cwl, cwr);
-  knot_pair<KMAX>(b, K, -B, idx, chl, chr);
-  const float in_w = cwr - cwl, in_h = chr - chl;
+  RqsBin r;
+  r.idx = min(max((inverse ? cnt_h : cnt_w) - 1, 0), K - 1);
+  float cwr, chr;
+  knot_pair<KMAX>(a, K, -B, r.idx, r.cwl, cwr);
+  knot_pair<KMAX>(b, K, -B, r.idx, r.chl, chr);
+  r.in_w = cwr - r.cwl; r.in_h = chr - r.chl;
+  return r;
+}
+
+// ud0 / ud1: unnormalised derivatives at the two knots of the bin (interior entries idx-1 / idx; ignored at the ends,
+// where the reference pads with log(exp(1 - min_derivative) - 1), neural_splines.py:33-42)
+__device__ __forceinline__ void rqs_finish(float x, const RqsBin& r, int K, float ud0_in, float ud1_in, bool inverse,
+                                           float& out, float& lad) {
+  const float in_w = r.in_w, in_h = r.in_h, cwl = r.cwl, chl = r.chl;
   const float delta = in_h / in_w;
-  // boundary derivatives are padded with log(exp(1 - min_derivative) - 1) (neural_splines.py:33-42)
   const float cpad = logf(expf(1.f - RQS_MIN_DER) - 1.f);
-  const float ud0 = (idx == 0) ? cpad : dget(idx - 1);
-  const float ud1 = (idx == K - 1) ? cpad : dget(idx);
+  const float ud0 = (r.idx == 0) ? cpad : ud0_in;
+  const float ud1 = (r.idx == K - 1) ? cpad : ud1_in;
   const float d0 = RQS_MIN_DER + softplus_f(ud0);
   const float d1 = RQS_MIN_DER + softplus_f(ud1);
   const float s = d0 + d1 - 2.f * delta;
@@ -120,6 +128,34 @@ __device__ __forceinline__ void rqs_eval(float x, float (&a)[KMAX], float (&b)[K
   const float num = delta * delta * (d1 * theta * theta + 2.f * delta * t1mt + d0 * omt * omt);
   const float l = logf(num) - 2.f * logf(den);
   lad = inverse ? -l : l;
+}
+
+// dget(j), j in [0, K-2]: unnormalised interior derivative j.
+template <int KMAX, class DGet>
+__device__ __forceinline__ void rqs_eval(float x, float (&a)[KMAX], float (&b)[KMAX], int K, float B, bool inverse,
+                                         DGet dget, float& out, float& lad, int& bin) {
+  const RqsBin r = rqs_locate<KMAX>(x, a, b, K, B, inverse);
+  bin = r.idx;
+  const float ud0 = (r.idx == 0) ? 0.f : dget(r.idx - 1);
+  const float ud1 = (r.idx == K - 1) ? 0.f : dget(r.idx);
+  rqs_finish(x, r, K, ud0, ud1, inverse, out, lad);
+}
+
+// 2B * softmax(raw[0..K))  (neural_splines.py:260-261: the coupling layer's own normalisation, before RQS repeats it), in place
+template <int KP>
+__device__ __forceinline__ void softmax_2b(float (&a)[KP], int K, float twoB) {
+  float mx = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < KP; ++j)
+    if (j < K) mx = fmaxf(mx, a[j]);
+  float sum = 0.f;
+#pragma unroll
+  for (int j = 0; j < KP; ++j)
+    if (j < K) { a[j] = __expf(a[j] - mx); sum += a[j]; }
+  const float s = twoB / sum;
+#pragma unroll
+  for (int j = 0; j < KP; ++j)
+    if (j < K) a[j] *= s;
 }
 
 }  // namespace wf

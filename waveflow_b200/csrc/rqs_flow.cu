@@ -73,23 +73,6 @@ __device__ __forceinline__ void dense_out(const float* __restrict__ W3, const fl
   }
 }
 
-// 2B * softmax(raw[0..K))  (neural_splines.py:260-261), in place
-template <int KP>
-__device__ __forceinline__ void softmax_2b(float (&a)[KP], int K, float twoB) {
-  float mx = -INFINITY;
-#pragma unroll
-  for (int j = 0; j < KP; ++j)
-    if (j < K) mx = fmaxf(mx, a[j]);
-  float sum = 0.f;
-#pragma unroll
-  for (int j = 0; j < KP; ++j)
-    if (j < K) { a[j] = __expf(a[j] - mx); sum += a[j]; }
-  const float s = twoB / sum;
-#pragma unroll
-  for (int j = 0; j < KP; ++j)
-    if (j < K) a[j] *= s;
-}
-
 template <int HALF, int HD, int KP>
 __global__ void __launch_bounds__(CF_THREADS) coupling_flow_kernel(const __grid_constant__ CfParams P) {
   extern __shared__ __align__(128) unsigned char smem_raw[];

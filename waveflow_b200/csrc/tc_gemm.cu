@@ -9,42 +9,6 @@ using namespace wf::tc;
 
 namespace {
 
-// ---------------------------------------------------------------------------------------------- tensor maps (host)
-PFN_cuTensorMapEncodeTiled_v12000 encode_fn() {
-  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
-  if (!fn) {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
-      return nullptr;
-    fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
-  }
-  return fn;
-}
-
-// row-major [rows][cols] float32 matrix, box = [box_rows][32 columns], 128-byte swizzle
-int make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int box_rows) {
-  auto fn = encode_fn();
-  if (!fn) return WF_ERR_UNSUPPORTED;
-  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)cols * sizeof(float)};
-  cuuint32_t box[2] = {(cuuint32_t)KB, (cuuint32_t)box_rows};
-  cuuint32_t estr[2] = {1, 1};
-  const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  return r == CUDA_SUCCESS ? WF_OK : WF_ERR_INVALID_ARG;
-}
-
-int make_maps(Maps& m, const float* a_hi, const float* a_lo, int64_t M, int K, const float* b_hi, const float* b_lo, int64_t N, int nt) {
-  int st;
-  if ((st = make_map(&m.a_hi, a_hi, M, K, TILE_M)) != WF_OK) return st;
-  if ((st = make_map(&m.a_lo, a_lo, M, K, TILE_M)) != WF_OK) return st;
-  if ((st = make_map(&m.b_hi, b_hi, N, K, nt)) != WF_OK) return st;
-  if ((st = make_map(&m.b_lo, b_lo, N, K, nt)) != WF_OK) return st;
-  return WF_OK;
-}
-
 // ---------------------------------------------------------------------------------------------- epilogues
 // mode 0: C = D (+ bias)            -> out_hi [M][N]
 // mode 1: h = tanh(D + bias) split  -> out_hi, out_lo [M][N]  (TF32-exact planes: the next layer's A operand)

@@ -84,6 +84,54 @@ def coupling_flow(layers, x, K: int, B: float, hidden_dim: int, inverse: bool = 
     return y, ld
 
 
+def _tf32_planes(x: torch.Tensor):
+    hi, lo = torch.empty_like(x), torch.empty_like(x)
+    check(lib.wf_tf32_split(ptr(x), x.numel(), ptr(hi), ptr(lo), stream_ptr()), "wf_tf32_split")
+    return hi, lo
+
+
+def pack_fcnn_tc(net, device) -> torch.Tensor:
+    """FCNN(32 -> 512 -> 512 -> 32*191) params -> the layout of wf_rqs_coupling_flow_tc (D = 64, K = 64, hidden 512)."""
+    (W1, b1), _, (W2, b2), _, (W3, b3) = net
+    t = lambda a: torch.as_tensor(a, dtype=torch.float32, device=device).contiguous()
+    W1, b1, W2, b2, W3, b3 = t(W1), t(b1), t(W2), t(b2), t(W3), t(b3)
+    K, half, Hd, NT = 64, 32, 512, 192
+    if W1.shape != (half, Hd) or W2.shape != (Hd, Hd) or W3.shape != (Hd, (3 * K - 1) * half):
+        raise _ffi.WaveflowB200Error("the tensor-core coupling path is built for D = 64, K = 64, hidden_dim = 512")
+    W3 = W3.reshape(Hd, half, 3 * K - 1)
+    W3p = torch.zeros(Hd, half, NT, dtype=torch.float32, device=device)
+    W3p[:, :, :3 * K - 1] = W3
+    b3p = torch.zeros(half, NT, dtype=torch.float32, device=device)
+    b3p[:, :3 * K - 1] = b3.reshape(half, 3 * K - 1)
+    parts = []
+    for Wt in (W1.t().contiguous(), ):
+        parts += list(_tf32_planes(Wt))
+    parts.append(b1)
+    parts += list(_tf32_planes(W2.t().contiguous()))
+    parts.append(b2)
+    parts += list(_tf32_planes(W3p.reshape(Hd, half * NT).t().contiguous()))
+    parts.append(b3p.reshape(-1))
+    out = torch.cat([p.reshape(-1) for p in parts]).contiguous()
+    assert out.numel() == lib.wf_rqs_coupling_tc_net_floats()
+    return out
+
+
+def coupling_flow_tc(packed_weights: torch.Tensor, n_layers: int, x, B: float, inverse: bool = False, chunk_rows: int = 1 << 17):
+    """Tensor-core Serial(NeuralSplineCoupling * L) for D = 64 / K = 64 / hidden 512 -> (y, log_det)."""
+    x = f32(x)
+    N, D = x.shape
+    if D != 64:
+        raise _ffi.WaveflowB200Error("D must be 64")
+    rows = min(chunk_rows, (N + 127) // 128 * 128)
+    ws = torch.empty(lib.wf_rqs_coupling_tc_workspace_floats(rows), dtype=torch.float32, device=x.device)
+    y = torch.empty_like(x)
+    ld = torch.empty(N, dtype=torch.float32, device=x.device)
+    st = lib.wf_rqs_coupling_flow_tc(ptr(packed_weights), n_layers, float(B), int(bool(inverse)), ptr(x), N, ptr(y), ptr(ld),
+                                     ptr(ws), ws.numel(), stream_ptr())
+    check(st, "wf_rqs_coupling_flow_tc")
+    return y, ld
+
+
 def FCNN(out_dim, hidden_dim):
     """stax.serial(Dense, Tanh, Dense, Tanh, Dense) (neural_splines.py:187-188): -> init_fun(rng, in_dim) -> params."""
     def init_fun(rng, in_dim):
