@@ -225,6 +225,38 @@ int64_t wf_rqs_coupling_tc_workspace_floats(int64_t rows);
 int wf_rqs_coupling_flow_tc(const float* weights, int n_layers, float tail_bound, int inverse, const float* x, int64_t N,
                             float* y, float* logdet, float* workspace, int64_t workspace_floats, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * VQMC training step: value_and_grad(loss_fn_efficient) + Adam  (vqmc.py:193-221, jax.example_libraries.optimizers.adam)
+ * ------------------------------------------------------------------------------------------------------------------ */
+
+/* Parameter layout of the training path ("reference-flat", float32): conditioners in the order IMADE_0 .. IMADE_{L-1},
+ * prior; per conditioner the stax.Dense kernels AS STORED by the reference (unmasked, model_factory.py:21-35):
+ *   W1 [D][64] | b1 [64] | W2 [64][64] | b2 [64] | W3 [64][D*P] | b3 [D*P] | zero_params [D*P]
+ * with P = P_I for the flow and P_P for the prior, i.e. the leaves of the reference's parameter pytree in traversal order
+ * (zero_params, model_factory.py:83-84, is unused by this configuration: read by nothing, gradient 0).
+ * Gradients use the same layout.  Returns the number of floats, or -1 for an unsupported model.
+ * Supported: Waveflow models (B prior, BoxTransformLayer, constraints {0:0}|{0:1} / {0:0}|{0:0}), D in 2..4, D*P <= 128. */
+int64_t wf_vqmc_param_floats(const wf_live_model* model_host);
+
+/* Floats of scratch needed to process `walkers` walkers in one chunk (activation jets of every layer). */
+int64_t wf_vqmc_grad_workspace_floats(const wf_live_model* model_host, int64_t walkers);
+
+/* Loss and parameter gradient of vqmc.py:193-212 for the walkers x [N][D]:
+ *   E_w = H psi_w / (psi_w + 1e-8),   grad += inv_n_total * sum_w [ a_w dpsi_w/dtheta + b_w d(H psi)_w/dtheta ],
+ *   a_w = 2 (E_w - running_average) / psi_w - H psi_w / psi_w^2,  b_w = 1 / psi_w     (the custom_jvp of the reference),
+ * evaluated by a reverse pass through the forward-mode Laplacian (table derivatives = next table; order 4 clamps to 3).
+ * grad [wf_vqmc_param_floats] is ACCUMULATED into (zero it first; NULL = forward only; masked-out weights get 0);
+ * inv_n_total = 1 / (number of walkers over all ranks).  psi, hpsi, eloc [N] nullable; sums (nullable, double[4]) +=
+ * {sum E, sum E^2, count, sum psi^2}.  The call loops over chunks sized to the workspace; deterministic summation. */
+int wf_vqmc_loss_grad(const wf_live_model* model_host, const wf_live_tables* tables_host, const float* params,
+                      const float* protons_host, int n_protons, const float* x, int64_t N, float running_average,
+                      float inv_n_total, float* grad, float* psi, float* hpsi, float* eloc, double* sums, float* workspace,
+                      int64_t workspace_floats, void* stream);
+
+/* One Adam update (optimizers.adam: m, v moment buffers, bias correction with exponent step + 1), in place. */
+int wf_adam_step(float* params, float* m, float* v, const float* grad, int64_t n, int64_t step, float lr, float b1, float b2,
+                 float eps, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -231,13 +231,30 @@ def local_energy_bundle(m: live.LiveModel, params, x: np.ndarray, protons: np.nd
 
 
 # =========================================================================== torch double-autograd
-def local_energy_autograd(m: live.LiveModel, params, x: np.ndarray, protons: np.ndarray):
-    """Independent check: torch float64, two autograd.grad passes per dimension (what jax.hessian's trace is)."""
+def autograd_psi_lap(m: live.LiveModel, params, x: np.ndarray, param_grad: bool = False, dtype=np.float64):
+    """torch float64 (psi, grad, lap) with the table lookup differentiated as jax does (custom_jvp -> next table).
+
+    param_grad=True keeps the graph and makes every weight a leaf, so that oracle/grad.py can take one more reverse
+    pass w.r.t. the parameters (what value_and_grad(loss_fn_efficient) does, vqmc.py:214-221).
+    -> (psi, g, lap, leaves) with leaves = {id(numpy leaf): torch leaf}.
+    """
     import torch
 
-    m = m.cast(np.float64)
-    tt = lambda a: torch.as_tensor(np.asarray(a, dtype=np.float64))
-    tabs = {"I": tt(m.tab_I), "OB": tt(m.tab_OB)}
+    tdt = torch.float64 if dtype == np.float64 else torch.float32
+    m = m.cast(dtype)
+    leaves = {}
+
+    def tt(a):
+        if param_grad and id(a) in leaves:
+            return leaves[id(a)]
+        return torch.as_tensor(np.asarray(a, dtype=dtype))
+
+    if param_grad:
+        for net in [p for p in params[0] if len(p)] + [params[1]]:
+            for lay in net[0]:
+                for a in lay:
+                    leaves[id(a)] = torch.tensor(np.asarray(a, dtype=dtype), requires_grad=True)
+    tabs = {"I": torch.as_tensor(np.asarray(m.tab_I, dtype=dtype)), "OB": torch.as_tensor(np.asarray(m.tab_OB, dtype=dtype))}
 
     class Lookup(torch.autograd.Function):
         """value = lerp(table[nd]); d/dx := Lookup(nd+1) (isplines_jax.py:60-66); nd clamps at 3."""
@@ -275,11 +292,11 @@ def local_energy_autograd(m: live.LiveModel, params, x: np.ndarray, protons: np.
         N, D = xx.shape
         L = float(m.box)
         cols = [xx[:, d] for d in range(D)]
-        ld = torch.zeros(N, dtype=torch.float64)
+        ld = torch.zeros(N, dtype=tdt)
         if m.coord == "mean":
             mean = xx.mean(-1)
             l = mean - cols[0]; w = cols[-1] - cols[0]
-            us = []; space = torch.full((N,), 2 * L, dtype=torch.float64)
+            us = []; space = torch.full((N,), 2 * L, dtype=tdt)
             for i in range(D - 1):
                 diff = cols[i + 1] - cols[i]
                 us.append(diff / (space + 1e-7)); ld = ld - torch.log(space + 1e-7); space = space - diff
@@ -291,11 +308,11 @@ def local_energy_autograd(m: live.LiveModel, params, x: np.ndarray, protons: np.
                 us.append((cols[i] - cols[i - 1]) / (L - cols[i - 1] + 1e-7)); ld = ld - torch.log(L - cols[i - 1] + 1e-7)
         u = torch.stack(us, -1)
         k, P = m.k_i, m.P_I
-        scale = torch.ones(P, dtype=torch.float64)
+        scale = torch.ones(P, dtype=tdt)
         for i in range(k):
             scale[i + 1] = scale[i + 1] * (i + 1) / k
             scale[P - (i + 2)] = scale[P - (i + 2)] * (i + 1) / k
-        mask = torch.ones(P, dtype=torch.float64); mask[0] = 0; mask[-1] = 0
+        mask = torch.ones(P, dtype=tdt); mask[0] = 0; mask[-1] = 0
         for net in [p for p in params[0] if len(p)]:
             c = cond(net, u, P, False) + m.reg
             c = c * scale; c = c / c.sum(-1, keepdim=True)
@@ -308,11 +325,11 @@ def local_energy_autograd(m: live.LiveModel, params, x: np.ndarray, protons: np.
             u = torch.stack(ys[::-1], -1)
         PB = m.P_P
         w = cond(params[1], u, PB, True)
-        maskb = torch.ones(PB, dtype=torch.float64); maskb[0] = 0; maskb[-1] = 0
+        maskb = torch.ones(PB, dtype=tdt); maskb[0] = 0; maskb[-1] = 0
         w = w * maskb; w = w / torch.sqrt((w ** 2).sum(-1, keepdim=True))
         c = w @ tt(m.ob_to_b); c = c / torch.sqrt((c ** 2).sum(-1, keepdim=True))
         uc = torch.clamp(u, 0.0, 1.0)
-        psi = torch.ones(N, dtype=torch.float64)
+        psi = torch.ones(N, dtype=tdt)
         cons = set(live._constrained(m).tolist())
         for d in range(D):
             phi = (c[:, d, :].T * Lookup.apply(uc[:, d], "OB", 0)).sum(0)
@@ -321,13 +338,19 @@ def local_energy_autograd(m: live.LiveModel, params, x: np.ndarray, protons: np.
             psi = psi * phi
         return psi * torch.exp(0.5 * ld)
 
-    xx = torch.tensor(np.asarray(x, dtype=np.float64), requires_grad=True)
+    xx = torch.tensor(np.asarray(x, dtype=dtype), requires_grad=True)
     psi = psi_fn(xx)
     (g,) = torch.autograd.grad(psi.sum(), xx, create_graph=True)
     lap = torch.zeros_like(psi)
     for d in range(xx.shape[1]):
-        (g2,) = torch.autograd.grad(g[:, d].sum(), xx, retain_graph=True)
+        (g2,) = torch.autograd.grad(g[:, d].sum(), xx, retain_graph=True, create_graph=param_grad)
         lap = lap + g2[:, d]
+    return psi, g, lap, leaves
+
+
+def local_energy_autograd(m: live.LiveModel, params, x: np.ndarray, protons: np.ndarray):
+    """Independent check: torch float64, two autograd.grad passes per dimension (what jax.hessian's trace is)."""
+    psi, g, lap, _ = autograd_psi_lap(m, params, x)
     V = live.potential(np.asarray(x, dtype=np.float64), np.asarray(protons, dtype=np.float64))
     psi_n, lap_n = psi.detach().numpy(), lap.detach().numpy()
     hpsi = -0.5 * lap_n + V * psi_n

@@ -101,7 +101,8 @@ def test_mflow_get_model_and_energy_estimator(cuda):
     s = sample(11, tp, 256, device=cuda)
     assert tuple(s.shape) == (256, 2)
     # VQMC estimator over emulated shards == single call
-    psi, log_pdf_w, sample_w, wparams = vqmc.create_train_state(10, 1e-4, n_particle=2, rng=0, cached_bases_root=None)
+    psi, log_pdf_w, sample_w, opt_state, opt_update, get_params = vqmc.create_train_state(10, 1e-4, n_particle=2, rng=0,
+                                                                                         cached_bases_root=None)
     h_fn = physics.construct_hamiltonian_function(psi, protons=np.array([[0.0], [0.0]]), n_space_dimensions=1)
     hparams, gold = fx.load_he_checkpoint()
     est = vqmc.EnergyEstimator(h_fn, hparams, cuda)
@@ -116,5 +117,3 @@ def test_mflow_get_model_and_energy_estimator(cuda):
     assert [est.shard(10, r, 4) for r in range(4)] == [(0, 3), (3, 6), (6, 8), (8, 10)]
     loss = vqmc.loss_fn_efficient(hparams, psi, h_fn, walkers)
     assert abs(float(loss) - full["energy"]) <= 1e-4 * abs(full["energy"])
-    with pytest.raises(NotImplementedError):
-        vqmc.train_step_efficient()

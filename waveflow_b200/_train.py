@@ -1,0 +1,127 @@
+"""Host-side driver of the VQMC training step (wf_vqmc_loss_grad / wf_adam_step).
+
+The parameter pytree of the reference ((transform_params, sp_params), model_factory.py:86-88, wavefunctions.py:110) is
+kept as ONE flat float32 device buffer whose order is the pytree's own leaf order; `unravel` hands out views into it, so
+the tree the user sees, the buffer the kernels read and the buffer Adam updates are the same memory.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _ffi, _live
+from ._ffi import check, lib, ptr, stream_ptr
+
+
+def tree_leaves(tree):
+    """Leaves in jax.tree_util order (tuples / lists flattened in place, () and [] contribute nothing)."""
+    if isinstance(tree, (tuple, list)):
+        out = []
+        for t in tree:
+            out.extend(tree_leaves(t))
+        return out
+    return [tree]
+
+
+def tree_unflatten(like, leaves):
+    it = iter(leaves)
+
+    def build(t):
+        if isinstance(t, (tuple, list)):
+            return type(t)(build(c) for c in t)
+        return next(it)
+
+    return build(like)
+
+
+def ravel(params, device) -> torch.Tensor:
+    """Pytree -> flat float32 device buffer."""
+    parts = [torch.as_tensor(np.asarray(a) if not isinstance(a, torch.Tensor) else a).to(device=device, dtype=torch.float32).reshape(-1)
+             for a in tree_leaves(params)]
+    return torch.cat(parts).contiguous()
+
+
+def unravel(like, flat: torch.Tensor):
+    """Flat buffer -> pytree of VIEWS with the shapes of `like`."""
+    leaves, o = [], 0
+    for a in tree_leaves(like):
+        shape = tuple(a.shape)
+        n = int(np.prod(shape)) if shape else 1
+        leaves.append(flat[o:o + n].view(shape))
+        o += n
+    if o != flat.numel():
+        raise _ffi.WaveflowB200Error(f"parameter tree has {o} elements, flat buffer {flat.numel()}")
+    return tree_unflatten(like, leaves)
+
+
+_WS: dict = {}
+
+
+def _workspace(spec: _live.LiveSpec, n: int, device, max_chunk: int) -> torch.Tensor:
+    chunk = max(1, min(n, max_chunk))
+    need = int(lib.wf_vqmc_grad_workspace_floats(C.byref(spec.struct()), chunk))
+    if need < 0:
+        raise _ffi.WaveflowB200Error("wf_vqmc_loss_grad does not support this model (Waveflow, D in 2..4, D*P <= 128)")
+    key = str(device)
+    ws = _WS.get(key)
+    if ws is None or ws.numel() < need:
+        ws = torch.empty(need, dtype=torch.float32, device=device)
+        _WS[key] = ws
+    return ws
+
+
+def loss_grad(spec: _live.LiveSpec, flat: torch.Tensor, x: torch.Tensor, protons, running_average: float,
+              n_total: int | None = None, grad: torch.Tensor | None = None, want=(), sums: torch.Tensor | None = None,
+              with_grad: bool = True, max_chunk: int = 16384):
+    """wf_vqmc_loss_grad -> (grad flat [n_params] (accumulated into `grad` when given), dict of the `want`ed outputs)."""
+    x = _ffi.f32(x)
+    N, dev = x.shape[0], x.device
+    nparam = int(lib.wf_vqmc_param_floats(C.byref(spec.struct())))
+    if nparam < 0:
+        raise _ffi.WaveflowB200Error("wf_vqmc_loss_grad does not support this model (Waveflow, D in 2..4, D*P <= 128)")
+    if flat.numel() != nparam or flat.dtype != torch.float32:
+        raise _ffi.WaveflowB200Error(f"flat parameter buffer must hold {nparam} float32 values, got {flat.numel()}")
+    if with_grad and grad is None:
+        grad = torch.zeros(nparam, dtype=torch.float32, device=dev)
+    out = {k: torch.empty(N, dtype=torch.float32, device=dev) for k in ("psi", "hpsi", "eloc") if k in want}
+    prot = _ffi.host_f32(np.asarray(protons, dtype=np.float32).reshape(-1))
+    ws = _workspace(spec, N, dev, max_chunk)
+    tabs = _live._tables(spec, dev)
+    st = lib.wf_vqmc_loss_grad(C.byref(spec.struct()), C.byref(tabs), ptr(flat), _ffi.np_ptr(prot), int(prot.size), ptr(x), N,
+                               float(running_average), 1.0 / float(n_total or N), ptr(grad if with_grad else None),
+                               ptr(out.get("psi")), ptr(out.get("hpsi")), ptr(out.get("eloc")), ptr(sums), ptr(ws), ws.numel(),
+                               stream_ptr())
+    check(st, "wf_vqmc_loss_grad")
+    return grad, out
+
+
+class AdamState:
+    """optimizers.adam state: (x, m, v) as three flat buffers + the pytree template."""
+
+    def __init__(self, like, flat: torch.Tensor):
+        self.like, self.flat = like, flat
+        self.m = torch.zeros_like(flat)
+        self.v = torch.zeros_like(flat)
+        self.tree = unravel(like, flat)
+
+
+def adam(step_size, b1=0.9, b2=0.999, eps=1e-8, device="cuda"):
+    """jax.example_libraries.optimizers.adam -> (opt_init, opt_update, get_params); the update is wf_adam_step, in place."""
+
+    def opt_init(params):
+        return AdamState(params, ravel(params, torch.device(device)))
+
+    def opt_update(i, grads, state: AdamState):
+        g = grads if isinstance(grads, torch.Tensor) else ravel(grads, state.flat.device)
+        lr = step_size(i) if callable(step_size) else step_size
+        st = lib.wf_adam_step(ptr(state.flat), ptr(state.m), ptr(state.v), ptr(g), state.flat.numel(), int(i), float(lr),
+                              float(b1), float(b2), float(eps), stream_ptr())
+        check(st, "wf_adam_step")
+        return state
+
+    def get_params(state: AdamState):
+        return state.tree
+
+    return opt_init, opt_update, get_params

@@ -1,0 +1,897 @@
+// Parameter gradient of the VQMC loss (value_and_grad(loss_fn_efficient), vqmc.py:193-221): a reverse pass through the
+// forward-mode Laplacian of psi.  Layer-wise formulation: every activation is a second-order jet (value, d/dx_1..D,
+// Laplacian) stored as G = D + 2 consecutive rows, so the conditioner layers are plain [N*G, K] x [K, N_out] products
+// (bias on the value rows only) and their weight gradients are X^T dY over all N*G rows; the element-wise pieces
+// (tanh, coefficient normalisation, table splines, psi assembly) carry the jet algebra of train_jets.cuh.
+//
+//   forward : box -> { linear, tanh, linear, tanh, linear, spline head } x (L flow nets + prior) -> psi, H psi, E_loc
+//   seed    : psi_bar = (a + V b) / N, lap_bar = -b / (2N),  a = 2 (E - avg) / psi - H psi / psi^2, b = 1 / psi
+//   backward: the same chain in reverse; table derivatives are the next table, order 4 clamps to 3.
+#include <math.h>
+#include "train_jets.cuh"
+
+using namespace wf;
+using namespace wf::train;
+
+namespace {
+
+constexpr int HID = 64;            // conditioner width (model_factory.py:40)
+constexpr int LIN_BM = 64;         // rows per tile of the linear / weight-gradient kernels
+constexpr int LIN_THREADS = 256;
+constexpr int MAX_W = 128;         // widest layer (D * P)
+constexpr int HEAD_THREADS = 128;
+
+// ---------------------------------------------------------------------------------------------- MADE masks
+// model_factory.py:8-19: degrees in = arange(D), hidden = h % (D-1), out = d - 1; mask[in][out] = deg_out >= deg_in.
+__host__ __device__ inline bool made_mask(int layer, int D, int k, int n) {
+  if (layer == 1) return (n % (D - 1)) >= k;
+  if (layer == 2) return (n % (D - 1)) >= (k % (D - 1));
+  return ((n % D) - 1) >= (k % (D - 1));
+}
+
+__global__ void mask_weights_kernel(const float* __restrict__ W, float* __restrict__ Wm, int layer, int D, int K, int N) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= K * N) return;
+  const int k = i / N, n = i % N;
+  Wm[i] = made_mask(layer, D, k, n) ? W[i] : 0.f;
+}
+
+// ---------------------------------------------------------------------------------------------- linear layers
+// C[R][Nc] (+)= A[R][Kc] * B (+ bias on the value rows r % G == 0).  TRANS_B == false: B [Kc][Nc]; true: B given as [Nc][Kc].
+template <bool TRANS_B, bool ACCUM>
+__global__ void __launch_bounds__(LIN_THREADS) linear_kernel(const float* __restrict__ A, const float* __restrict__ B,
+                                                             const float* __restrict__ bias, float* __restrict__ C,
+                                                             int64_t R, int Kc, int Nc, int G) {
+  extern __shared__ float sm[];
+  const int NcP = (Nc + 15) & ~15;
+  float* Bs = sm;                         // [Kc][NcP]
+  float* As = sm + Kc * NcP;              // [LIN_BM][Kc]
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  for (int i = tid; i < Kc * NcP; i += LIN_THREADS) {
+    const int k = i / NcP, n = i % NcP;
+    Bs[i] = n < Nc ? (TRANS_B ? B[(int64_t)n * Kc + k] : B[(int64_t)k * Nc + n]) : 0.f;
+  }
+  const int NJ = NcP >> 4;
+  const int64_t tiles = (R + LIN_BM - 1) / LIN_BM;
+  for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const int64_t r0 = tile * LIN_BM;
+    const int rows = (int)min((int64_t)LIN_BM, R - r0);
+    __syncthreads();
+    const float* Ag = A + r0 * Kc;
+    for (int i = tid; i < LIN_BM * Kc; i += LIN_THREADS) As[i] = i < rows * Kc ? Ag[i] : 0.f;
+    __syncthreads();
+    float acc[4][8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+    for (int k = 0; k < Kc; ++k) {
+      float a[4], b[8];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[(ty * 4 + i) * Kc + k];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) b[j] = j < NJ ? Bs[k * NcP + tx + 16 * j] : 0.f;
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int rl = ty * 4 + i;
+      if (rl >= rows) continue;
+      const int64_t r = r0 + rl;
+      const bool value_row = (r % G) == 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int n = tx + 16 * j;
+        if (j < NJ && n < Nc) {
+          float v = acc[i][j];
+          if (bias && value_row) v += bias[n];
+          if (ACCUM) v += C[r * Nc + n];
+          C[r * Nc + n] = v;
+        }
+      }
+    }
+  }
+}
+
+// partial[cta][Kc + 1][Nc] = sum over the CTA's rows of X[r][k] * dY[r][n]; row Kc = value-row indicator (bias gradient)
+__global__ void __launch_bounds__(LIN_THREADS) wgrad_kernel(const float* __restrict__ X, const float* __restrict__ dY,
+                                                            float* __restrict__ partial, int64_t R, int Kc, int Nc, int G) {
+  extern __shared__ float sm[];
+  const int K1 = Kc + 1;
+  const int NcP = (Nc + 15) & ~15;
+  float* Xs = sm;                       // [LIN_BM][K1]
+  float* Ys = sm + LIN_BM * K1;         // [LIN_BM][NcP]
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int NI = (K1 + 15) >> 4, NJ = NcP >> 4;
+  float acc[5][8];
+#pragma unroll
+  for (int i = 0; i < 5; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+  const int64_t tiles = (R + LIN_BM - 1) / LIN_BM;
+  for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const int64_t r0 = tile * LIN_BM;
+    const int rows = (int)min((int64_t)LIN_BM, R - r0);
+    __syncthreads();
+    for (int i = tid; i < LIN_BM * K1; i += LIN_THREADS) {
+      const int rl = i / K1, k = i % K1;
+      float v = 0.f;
+      if (rl < rows) v = k < Kc ? X[(r0 + rl) * Kc + k] : (((r0 + rl) % G) == 0 ? 1.f : 0.f);
+      Xs[i] = v;
+    }
+    for (int i = tid; i < LIN_BM * NcP; i += LIN_THREADS) {
+      const int rl = i / NcP, n = i % NcP;
+      Ys[i] = (rl < rows && n < Nc) ? dY[(r0 + rl) * Nc + n] : 0.f;
+    }
+    __syncthreads();
+    for (int r = 0; r < rows; ++r) {
+      float x[5], y[8];
+#pragma unroll
+      for (int i = 0; i < 5; ++i) x[i] = (i < NI && ty + 16 * i < K1) ? Xs[r * K1 + ty + 16 * i] : 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) y[j] = j < NJ ? Ys[r * NcP + tx + 16 * j] : 0.f;
+#pragma unroll
+      for (int i = 0; i < 5; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(x[i], y[j], acc[i][j]);
+    }
+  }
+  float* out = partial + (int64_t)blockIdx.x * K1 * Nc;
+#pragma unroll
+  for (int i = 0; i < 5; ++i) {
+    const int k = ty + 16 * i;
+    if (i >= NI || k >= K1) continue;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int n = tx + 16 * j;
+      if (j < NJ && n < Nc) out[(int64_t)k * Nc + n] = acc[i][j];
+    }
+  }
+}
+
+// gW[k][n] += mask * sum_cta partial[cta][k][n];  gb[n] += sum_cta partial[cta][Kc][n]   (fixed summation order)
+__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int n_cta, float* __restrict__ gW, float* __restrict__ gb,
+                                    int layer, int D, int Kc, int Nc) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (Kc + 1) * Nc) return;
+  const int k = i / Nc, n = i % Nc;
+  float s = 0.f;
+  for (int c = 0; c < n_cta; ++c) s += partial[(int64_t)c * (Kc + 1) * Nc + i];
+  if (k < Kc) {
+    if (made_mask(layer, D, k, n)) gW[i] += s;
+  } else {
+    gb[n] += s;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- tanh on jets
+template <int D>
+__global__ void tanh_fwd_kernel(const float* __restrict__ Z, float* __restrict__ Hh, int64_t N) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * HID) return;
+  const int64_t n = i / HID;
+  const int c = (int)(i % HID);
+  const Jet<D> z = jload<D>(Z, n, HID, c);
+  const float t = tanhf(z.v), d1 = 1.f - t * t;
+  jstore<D>(Hh, n, HID, c, junary(z, t, d1, -2.f * t * d1));
+}
+// Hbar -> Zbar in place
+template <int D>
+__global__ void tanh_bwd_kernel(const float* __restrict__ Z, float* __restrict__ Hbar, int64_t N) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * HID) return;
+  const int64_t n = i / HID;
+  const int c = (int)(i % HID);
+  const Jet<D> z = jload<D>(Z, n, HID, c);
+  const Jet<D> ob = jload<D>(Hbar, n, HID, c);
+  const float t = tanhf(z.v), d1 = 1.f - t * t, d2 = -2.f * t * d1, d3 = -2.f * d1 * d1 - 2.f * t * d2;
+  Jet<D> zb = jzero<D>();
+  junary_bwd(z, d1, d2, d3, ob, zb);
+  jstore<D>(Hbar, n, HID, c, zb);
+}
+
+// ---------------------------------------------------------------------------------------------- box transform (made.py:108-183)
+template <int D>
+__global__ void box_kernel(const float* __restrict__ x, int64_t N, float L, int coord_mean, float* __restrict__ U,
+                           float* __restrict__ LD) {
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  Jet<D> X[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    X[d] = jzero<D>();
+    X[d].v = x[n * D + d];
+    X[d].g[d] = 1.f;
+  }
+  const float tol = 1e-7f;
+  Jet<D> ld = jzero<D>();
+  if (coord_mean) {
+    Jet<D> mean = jzero<D>();
+#pragma unroll
+    for (int d = 0; d < D; ++d) jacc(mean, X[d]);
+    mean = jscale(mean, 1.f / (float)D);
+    const Jet<D> l = jsub(mean, X[0]);
+    const Jet<D> w = jsub(X[D - 1], X[0]);
+    Jet<D> space = jzero<D>();
+    space.v = 2.f * L;
+#pragma unroll
+    for (int i = 0; i < D - 1; ++i) {
+      const Jet<D> diff = jsub(X[i + 1], X[i]);
+      Jet<D> den = space;
+      den.v += tol;
+      jstore<D>(U, n, D, i, jmul(diff, jrecip(den)));
+      ld = jsub(ld, jlog(den));
+      space = jsub(space, diff);
+    }
+    Jet<D> den = jscale(w, -1.f);
+    den.v = (2.f * L - w.v) + tol;
+    Jet<D> num = jsub(mean, l);
+    num.v = (mean.v + L) - l.v;
+    jstore<D>(U, n, D, D - 1, jmul(num, jrecip(den)));
+    ld = jsub(ld, jlog(den));
+  } else {
+    Jet<D> u0 = jscale(X[0], 1.f / (2.f * L));
+    u0.v = (X[0].v + L) / (2.f * L);
+    jstore<D>(U, n, D, 0, u0);
+    ld.v -= logf(2.f * L);
+#pragma unroll
+    for (int i = 1; i < D; ++i) {
+      Jet<D> den = jscale(X[i - 1], -1.f);
+      den.v = (L - X[i - 1].v) + tol;
+      jstore<D>(U, n, D, i, jmul(jsub(X[i], X[i - 1]), jrecip(den)));
+      ld = jsub(ld, jlog(den));
+    }
+  }
+  jstore<D>(LD, n, 1, 0, ld);
+}
+
+// ---------------------------------------------------------------------------------------------- IMADE spline head (made.py:66-81)
+struct HeadArgs {
+  const float* O;      // [R][D*P] conditioner output jets
+  const float* U;      // [R][D]   layer input jets
+  const float* tab;    // dense [T][4][32]
+  int64_t N;
+  int P, T;
+  float reg;
+  float wq[WF_MAX_P];  // remove_bias scale with the boundary constraints folded in (0 at constrained ends)
+};
+
+template <int D>
+struct ImadeFwd {
+  Jet<D> S1, r1, S2, r2;
+};
+
+template <int D>
+__device__ __forceinline__ Jet<D> imade_b(const HeadArgs& a, const Jet<D>& s, const Jet<D>& r1, int p) {
+  Jet<D> b = jmul(s, r1);
+  b.v += a.reg;
+  return jscale(b, a.wq[p]);
+}
+template <int D>
+__device__ __forceinline__ Jet<D> sig_jet(const Jet<D>& o) {
+  const Sig g = sigmoid_derivs(o.v);
+  return junary(o, g.s, g.d1, g.d2);
+}
+
+template <int D>
+__device__ __forceinline__ ImadeFwd<D> imade_norms(const HeadArgs& a, int64_t n, int d) {
+  ImadeFwd<D> f;
+  const int DP = D * a.P;
+  f.S1 = jzero<D>();
+#pragma unroll 1
+  for (int p = 0; p < a.P; ++p) jacc(f.S1, sig_jet(jload<D>(a.O, n, DP, p * D + d)));
+  f.r1 = jrecip(f.S1);
+  f.S2 = jzero<D>();
+#pragma unroll 1
+  for (int p = 0; p < a.P; ++p) {
+    if (a.wq[p] == 0.f) continue;
+    jacc(f.S2, imade_b(a, sig_jet(jload<D>(a.O, n, DP, p * D + d)), f.r1, p));
+  }
+  f.r2 = jrecip(f.S2);
+  return f;
+}
+
+// Y [R][D] receives y at the REVERSED column (the Reverse layer, bijections.py:317-347); LDC [R][D] the log-det terms
+template <int D>
+__global__ void __launch_bounds__(HEAD_THREADS) imade_fwd_kernel(const __grid_constant__ HeadArgs a, float* __restrict__ Y,
+                                                                 float* __restrict__ LDC) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.N * D) return;
+  const int64_t n = i / D;
+  const int d = (int)(i % D);
+  const int DP = D * a.P;
+  const ImadeFwd<D> f = imade_norms<D>(a, n, d);
+  const Jet<D> u = jload<D>(a.U, n, D, d);
+  const NodeIdx ni = node_index(u.v, a.T);
+  const float np_ = (float)(a.T - 1);
+  Jet<D> y = jzero<D>(), dy = jzero<D>();
+#pragma unroll 1
+  for (int p = 0; p < a.P; ++p) {
+    if (a.wq[p] == 0.f) continue;
+    const Jet<D> c = jmul(imade_b(a, sig_jet(jload<D>(a.O, n, DP, p * D + d)), f.r1, p), f.r2);
+    const Basis4 b = basis4(a.tab, ni, np_, p);
+    jacc(y, jmul(c, junary(u, b.f[0], b.f[1], b.f[2])));
+    jacc(dy, jmul(c, junary(u, b.f[1], b.f[2], b.f[3])));
+  }
+  dy.v += LOG_TOL;
+  jstore<D>(Y, n, D, D - 1 - d, y);
+  jstore<D>(LDC, n, D, d, jlog(dy));
+}
+
+// Ybar [R][D]: adjoint of the NEXT layer's input (so y_d's adjoint sits at column D-1-d); LDbar [R]: adjoint of log|det|
+template <int D>
+__global__ void __launch_bounds__(HEAD_THREADS) imade_bwd_kernel(const __grid_constant__ HeadArgs a, const float* __restrict__ Ybar,
+                                                                 const float* __restrict__ LDbar, float* __restrict__ Obar,
+                                                                 float* __restrict__ Ubar) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.N * D) return;
+  const int64_t n = i / D;
+  const int d = (int)(i % D);
+  const int DP = D * a.P;
+  const ImadeFwd<D> f = imade_norms<D>(a, n, d);
+  const Jet<D> u = jload<D>(a.U, n, D, d);
+  const NodeIdx ni = node_index(u.v, a.T);
+  const float np_ = (float)(a.T - 1);
+  const Jet<D> ybar = jload<D>(Ybar, n, D, D - 1 - d);
+  const Jet<D> lbar = jload<D>(LDbar, n, 1, 0);
+  // dy is needed for the adjoint of log(dy + 1e-7)
+  Jet<D> dy = jzero<D>();
+#pragma unroll 1
+  for (int p = 0; p < a.P; ++p) {
+    if (a.wq[p] == 0.f) continue;
+    const Jet<D> c = jmul(imade_b(a, sig_jet(jload<D>(a.O, n, DP, p * D + d)), f.r1, p), f.r2);
+    const Basis4 b = basis4(a.tab, ni, np_, p);
+    jacc(dy, jmul(c, junary(u, b.f[1], b.f[2], b.f[3])));
+  }
+  dy.v += LOG_TOL;
+  Jet<D> dybar = jzero<D>();
+  jlog_bwd(dy, lbar, dybar);
+
+  Jet<D> bb[WF_MAX_P];
+  Jet<D> ubar = jzero<D>(), r2bar = jzero<D>();
+#pragma unroll 1
+  for (int p = 0; p < a.P; ++p) {
+    bb[p] = jzero<D>();
+    if (a.wq[p] == 0.f) continue;
+    const Jet<D> bq = imade_b(a, sig_jet(jload<D>(a.O, n, DP, p * D + d)), f.r1, p);
+    const Jet<D> c = jmul(bq, f.r2);
+    const Basis4 b = basis4(a.tab, ni, np_, p);
+    const Jet<D> B0 = junary(u, b.f[0], b.f[1], b.f[2]);
+    const Jet<D> B1 = junary(u, b.f[1], b.f[2], b.f[3]);
+    Jet<D> cbar = jzero<D>(), B0bar = jzero<D>(), B1bar = jzero<D>();
+    jmul_bwd(B0, ybar, cbar);
+    jmul_bwd(B1, dybar, cbar);
+    jmul_bwd(c, ybar, B0bar);
+    jmul_bwd(c, dybar, B1bar);
+    junary_bwd(u, b.f[1], b.f[2], b.f[3], B0bar, ubar);
+    junary_bwd(u, b.f[2], b.f[3], b.f[3], B1bar, ubar);   // table order 4 clamps to 3 (quirk Q5)
+    jmul_bwd(f.r2, cbar, bb[p]);
+    jmul_bwd(bq, cbar, r2bar);
+  }
+  Jet<D> S2bar = jzero<D>();
+  jrecip_bwd(f.S2, r2bar, S2bar);
+  Jet<D> r1bar = jzero<D>();
+#pragma unroll 1
+  for (int p = 0; p < a.P; ++p) {
+    if (a.wq[p] == 0.f) continue;
+    const Jet<D> s = sig_jet(jload<D>(a.O, n, DP, p * D + d));
+    Jet<D> bbar = bb[p];
+    jacc(bbar, S2bar);
+    const Jet<D> abar = jscale(bbar, a.wq[p]);
+    Jet<D> sbar = jzero<D>();
+    jmul_bwd(f.r1, abar, sbar);
+    jmul_bwd(s, abar, r1bar);
+    bb[p] = sbar;
+  }
+  Jet<D> S1bar = jzero<D>();
+  jrecip_bwd(f.S1, r1bar, S1bar);
+#pragma unroll 1
+  for (int p = 0; p < a.P; ++p) {
+    const Jet<D> o = jload<D>(a.O, n, DP, p * D + d);
+    Jet<D> sbar = bb[p];
+    jacc(sbar, S1bar);
+    const Sig g = sigmoid_derivs(o.v);
+    Jet<D> obar = jzero<D>();
+    junary_bwd(o, g.d1, g.d2, g.d3, sbar, obar);
+    jstore<D>(Obar, n, DP, p * D + d, obar);
+  }
+  jstore<D>(Ubar, n, D, d, ubar);
+}
+
+// ---------------------------------------------------------------------------------------------- prior head (wavefunctions.py:54-71)
+struct PriorArgs {
+  const float* O;        // [R][D*P]
+  const float* U;        // [R][D]
+  const float* tab;      // orthonormalised tables, dense [T][4][32]
+  const float* ob_to_b;  // [P][P]
+  int64_t N;
+  int P, T;
+  int cons_lo, cons_hi;  // dimensions [cons_lo, cons_hi) carry the 1/sqrt(2) (model_factory.py:124-129)
+  float mb[WF_MAX_P];    // 0 at the constrained end coefficients (bsplines_jax.py:173-198 with {0: 0} | {0: 0})
+};
+
+template <int D>
+__device__ __forceinline__ void prior_coeffs(const PriorArgs& a, int64_t n, int d, Jet<D>* cpre, Jet<D>& S, Jet<D>& nrm) {
+  const int P = a.P, DP = D * P;
+#pragma unroll 1
+  for (int q = 0; q < P; ++q) cpre[q] = jzero<D>();
+#pragma unroll 1
+  for (int p = 0; p < P; ++p) {
+    if (a.mb[p] == 0.f) continue;
+    const Jet<D> o = jscale(jload<D>(a.O, n, DP, p * D + d), a.mb[p]);
+    const float* row = a.ob_to_b + p * P;
+#pragma unroll 1
+    for (int q = 0; q < P; ++q) jaxpy(cpre[q], __ldg(row + q), o);
+  }
+  S = jzero<D>();
+#pragma unroll 1
+  for (int q = 0; q < P; ++q) jacc(S, jmul(cpre[q], cpre[q]));
+  nrm = jrsqrt(S);
+}
+// The conditioner divides by sum_p o_p even when negative outputs are allowed (model_factory.py:69-70); the L2
+// normalisations that follow cancel its magnitude and keep its sign.
+template <int D>
+__device__ __forceinline__ float prior_sign(const PriorArgs& a, int64_t n, int d) {
+  const float* p = a.O + n * (D + 2) * (int64_t)(D * a.P) + d;
+  float s = 0.f;
+#pragma unroll 1
+  for (int q = 0; q < a.P; ++q) s += p[q * D];
+  return s < 0.f ? -1.f : 1.f;
+}
+template <int D>
+__device__ __forceinline__ Jet<D> clip01(const Jet<D>& u, bool& inside) {
+  inside = (u.v > 0.f) && (u.v < 1.f);
+  Jet<D> c = inside ? u : jzero<D>();
+  c.v = fminf(fmaxf(u.v, 0.f), 1.f);
+  return c;
+}
+
+template <int D>
+__global__ void __launch_bounds__(HEAD_THREADS) prior_fwd_kernel(const __grid_constant__ PriorArgs a, float* __restrict__ PHI) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.N * D) return;
+  const int64_t n = i / D;
+  const int d = (int)(i % D);
+  Jet<D> cpre[WF_MAX_P], S, nrm;
+  prior_coeffs<D>(a, n, d, cpre, S, nrm);
+  bool inside;
+  const Jet<D> uc = clip01(jload<D>(a.U, n, D, d), inside);
+  const NodeIdx ni = node_index(uc.v, a.T);
+  const float np_ = (float)(a.T - 1);
+  Jet<D> phi = jzero<D>();
+#pragma unroll 1
+  for (int q = 0; q < a.P; ++q) {
+    const Basis4 b = basis4(a.tab, ni, np_, q);
+    jacc(phi, jmul(jmul(cpre[q], nrm), junary(uc, b.f[0], b.f[1], b.f[2])));
+  }
+  phi = jscale(phi, prior_sign<D>(a, n, d));
+  if (d >= a.cons_lo && d < a.cons_hi) phi = jscale(phi, 0.70710678118654752f);
+  jstore<D>(PHI, n, D, d, phi);
+}
+
+template <int D>
+__global__ void __launch_bounds__(HEAD_THREADS) prior_bwd_kernel(const __grid_constant__ PriorArgs a, const float* __restrict__ PHIbar,
+                                                                 float* __restrict__ Obar, float* __restrict__ Ubar) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.N * D) return;
+  const int64_t n = i / D;
+  const int d = (int)(i % D);
+  const int P = a.P, DP = D * P;
+  Jet<D> cpre[WF_MAX_P], cb[WF_MAX_P], S, nrm;
+  prior_coeffs<D>(a, n, d, cpre, S, nrm);
+  bool inside;
+  const Jet<D> uc = clip01(jload<D>(a.U, n, D, d), inside);
+  const NodeIdx ni = node_index(uc.v, a.T);
+  const float np_ = (float)(a.T - 1);
+  Jet<D> phibar = jscale(jload<D>(PHIbar, n, D, d), prior_sign<D>(a, n, d));
+  if (d >= a.cons_lo && d < a.cons_hi) phibar = jscale(phibar, 0.70710678118654752f);
+  Jet<D> nbar = jzero<D>(), ucbar = jzero<D>();
+#pragma unroll 1
+  for (int q = 0; q < P; ++q) {
+    const Jet<D> c = jmul(cpre[q], nrm);
+    const Basis4 b = basis4(a.tab, ni, np_, q);
+    const Jet<D> B0 = junary(uc, b.f[0], b.f[1], b.f[2]);
+    Jet<D> cbar = jzero<D>(), B0bar = jzero<D>();
+    jmul_bwd(B0, phibar, cbar);
+    jmul_bwd(c, phibar, B0bar);
+    junary_bwd(uc, b.f[1], b.f[2], b.f[3], B0bar, ucbar);
+    cb[q] = jzero<D>();
+    jmul_bwd(nrm, cbar, cb[q]);
+    jmul_bwd(cpre[q], cbar, nbar);
+  }
+  Jet<D> Sbar = jzero<D>();
+  jrsqrt_bwd(S, nbar, Sbar);
+#pragma unroll 1
+  for (int q = 0; q < P; ++q) {
+    Jet<D> t = jzero<D>();
+    jmul_bwd(cpre[q], Sbar, t);          // d(c*c) = 2 * (one-sided adjoint)
+    jaxpy(cb[q], 2.f, t);
+  }
+#pragma unroll 1
+  for (int p = 0; p < P; ++p) {
+    Jet<D> ob = jzero<D>();
+    if (a.mb[p] != 0.f) {
+      const float* row = a.ob_to_b + p * P;
+#pragma unroll 1
+      for (int q = 0; q < P; ++q) jaxpy(ob, __ldg(row + q), cb[q]);
+      ob = jscale(ob, a.mb[p]);
+    }
+    jstore<D>(Obar, n, DP, p * D + d, ob);
+  }
+  if (!inside) {
+    const float keep = (uc.v >= 0.f && uc.v <= 1.f && jload<D>(a.U, n, D, d).v == uc.v) ? ucbar.v : 0.f;
+    ucbar = jzero<D>();
+    ucbar.v = keep;
+  }
+  jstore<D>(Ubar, n, D, d, ucbar);
+}
+
+// ---------------------------------------------------------------------------------------------- psi, H psi, E_loc and the adjoint seeds
+struct FinalArgs {
+  const float* x;         // [N][D]
+  const float* PHI;       // [R][D]
+  const float* LDbox;     // [R]
+  const float* LDC;       // [L][R][D]
+  int64_t N, ldc_stride;
+  int n_layers, n_protons;
+  float protons[WF_MAX_D];
+  float running_average, inv_n;
+  float* PHIbar;          // [R][D]
+  float* LDbar;           // [R]
+  float* psi; float* hpsi; float* eloc;   // nullable [N]
+  double* sums;           // nullable [4]: += {sum E, sum E^2, count, sum psi^2}
+};
+
+template <int D>
+__global__ void final_kernel(const __grid_constant__ FinalArgs a) {
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  float e = 0.f, e2 = 0.f, cnt = 0.f, p2 = 0.f;
+  if (n < a.N) {
+    Jet<D> ld = jload<D>(a.LDbox, n, 1, 0);
+    for (int l = 0; l < a.n_layers; ++l)
+#pragma unroll
+      for (int d = 0; d < D; ++d) jacc(ld, jload<D>(a.LDC + (int64_t)l * a.ldc_stride, n, D, d));
+    Jet<D> phi[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) phi[d] = jload<D>(a.PHI, n, D, d);
+    Jet<D> prod = phi[0];
+#pragma unroll
+    for (int d = 1; d < D; ++d) prod = jmul(prod, phi[d]);
+    const Jet<D> half = jscale(ld, 0.5f);
+    const float ex = expf(half.v);
+    const Jet<D> E = junary(half, ex, ex, ex);
+    const Jet<D> psi = jmul(prod, E);
+    // soft-Coulomb potential (physics.py:60-76)
+    float xs[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) xs[d] = a.x[n * D + d];
+    float V = 0.f;
+    for (int p = 0; p < a.n_protons; ++p)
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        const float r = a.protons[p] - xs[d];
+        V -= rsqrtf(fmaf(r, r, 1.f));
+      }
+#pragma unroll
+    for (int i = 0; i < D; ++i)
+#pragma unroll
+      for (int j = 0; j < i; ++j) {
+        const float r = xs[i] - xs[j];
+        V += rsqrtf(fmaf(r, r, 1.f));
+      }
+    const float hpsi = fmaf(-0.5f, psi.l, V * psi.v);
+    const float eloc = hpsi / (psi.v + 1e-8f);
+    if (a.psi) a.psi[n] = psi.v;
+    if (a.hpsi) a.hpsi[n] = hpsi;
+    if (a.eloc) a.eloc[n] = eloc;
+    if (isfinite(eloc)) { e = eloc; e2 = eloc * eloc; cnt = 1.f; p2 = psi.v * psi.v; }
+    // custom_jvp of _loss_fn_efficient (vqmc.py:202-212)
+    const float ca = 2.f * (eloc - a.running_average) / psi.v - hpsi / (psi.v * psi.v);
+    const float cb = 1.f / psi.v;
+    Jet<D> psibar = jzero<D>();
+    psibar.v = (ca + V * cb) * a.inv_n;
+    psibar.l = -0.5f * cb * a.inv_n;
+    Jet<D> prodbar = jzero<D>(), Ebar = jzero<D>(), halfbar = jzero<D>();
+    jmul_bwd(E, psibar, prodbar);
+    jmul_bwd(prod, psibar, Ebar);
+    junary_bwd(half, ex, ex, ex, Ebar, halfbar);
+    jstore<D>(a.LDbar, n, 1, 0, jscale(halfbar, 0.5f));
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      Jet<D> others = jzero<D>();
+      others.v = 1.f;
+#pragma unroll
+      for (int k = 0; k < D; ++k)
+        if (k != d) others = jmul(others, phi[k]);
+      Jet<D> pb = jzero<D>();
+      jmul_bwd(others, prodbar, pb);
+      jstore<D>(a.PHIbar, n, D, d, pb);
+    }
+  }
+  if (a.sums) {
+    double v[4] = {(double)e, (double)e2, (double)cnt, (double)p2};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+    }
+    if ((threadIdx.x & 31) == 0 && v[2] > 0.0) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) atomicAdd(a.sums + k, v[k]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- Adam (jax.example_libraries.optimizers.adam)
+__global__ void adam_kernel(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v, const float* __restrict__ g,
+                            int64_t n, float lr, float b1, float b2, float eps, float c1, float c2) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float gi = g[i];
+  const float mi = (1.f - b1) * gi + b1 * m[i];
+  const float vi = (1.f - b2) * gi * gi + b2 * v[i];
+  m[i] = mi; v[i] = vi;
+  p[i] = p[i] - lr * (mi / c1) / (sqrtf(vi / c2) + eps);
+}
+
+// ---------------------------------------------------------------------------------------------- host orchestration
+struct NetOff { int64_t W1, b1, W2, b2, W3, b3, zero, end; };
+
+NetOff net_offsets(int D, int P, int64_t base) {
+  NetOff o;
+  o.W1 = base; o.b1 = o.W1 + (int64_t)D * HID; o.W2 = o.b1 + HID; o.b2 = o.W2 + HID * HID; o.W3 = o.b2 + HID;
+  o.b3 = o.W3 + (int64_t)HID * D * P; o.zero = o.b3 + (int64_t)D * P; o.end = o.zero + (int64_t)D * P;
+  return o;
+}
+int n_nets_of(const wf_live_model* m) { return m->n_layers + 1; }
+int net_P(const wf_live_model* m, int i) { return i < m->n_layers ? m->P_I : m->P_P; }
+int max_DP(const wf_live_model* m) { return m->D * (m->P_I > m->P_P ? m->P_I : m->P_P); }
+
+int check_model(const wf_live_model* m) {
+  if (!m) return WF_ERR_INVALID_ARG;
+  if (m->D < 2 || m->D > 4) return WF_ERR_UNSUPPORTED;
+  if (m->prior_kind != WF_KIND_B || !m->has_box || m->bc_I != 3 || m->bc_P != 3) return WF_ERR_UNSUPPORTED;
+  if (m->n_layers < 0 || m->n_layers > WF_MAX_LAYERS || m->P_I < 2 || m->P_I > WF_MAX_P || m->P_P < 2 || m->P_P > WF_MAX_P)
+    return WF_ERR_INVALID_ARG;
+  if (max_DP(m) > MAX_W) return WF_ERR_UNSUPPORTED;
+  return WF_OK;
+}
+
+constexpr int WGRAD_CTAS = 296;
+
+struct Fixed { int64_t wm, partial, total; };
+Fixed fixed_floats(const wf_live_model* m) {
+  Fixed f;
+  f.wm = 0;
+  for (int i = 0; i < n_nets_of(m); ++i) f.wm += (int64_t)m->D * HID + HID * HID + (int64_t)HID * m->D * net_P(m, i);
+  f.partial = (int64_t)WGRAD_CTAS * (HID + 1) * MAX_W;
+  f.total = f.wm + f.partial;
+  return f;
+}
+int64_t per_row_floats(const wf_live_model* m) {
+  const int D = m->D, nn = n_nets_of(m), DPm = max_DP(m);
+  // U[nn+1], per net Z1 H1 Z2 H2 O, LDbox, LDC[L], PHI, PHIbar, LDbar, Obar, HbarA, HbarB, Ubar x2
+  return (int64_t)(nn + 1) * D + (int64_t)nn * (4 * HID + DPm) + 1 + (int64_t)m->n_layers * D + 2 * D + 1 + DPm + 2 * HID + 2 * D;
+}
+
+int smem_linear(int Kc, int Nc) { return (Kc * ((Nc + 15) & ~15) + LIN_BM * Kc) * (int)sizeof(float); }
+int smem_wgrad(int Kc, int Nc) { return (LIN_BM * (Kc + 1) + LIN_BM * ((Nc + 15) & ~15)) * (int)sizeof(float); }
+
+template <bool T, bool A>
+int launch_linear(const float* Ain, const float* B, const float* bias, float* C, int64_t R, int Kc, int Nc, int G, cudaStream_t s) {
+  static bool attr = false;
+  if (!attr) {
+    WF_CUDA(cudaFuncSetAttribute(linear_kernel<T, A>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    attr = true;
+  }
+  const int64_t tiles = (R + LIN_BM - 1) / LIN_BM;
+  const int grid = (int)(tiles < 2 * num_sms() ? tiles : 2 * num_sms());
+  linear_kernel<T, A><<<grid, LIN_THREADS, smem_linear(Kc, Nc), s>>>(Ain, B, bias, C, R, Kc, Nc, G);
+  WF_LAUNCH_CHECK();
+  return WF_OK;
+}
+
+int launch_wgrad(const float* X, const float* dY, float* partial, float* gW, float* gb, int layer, int D, int64_t R, int Kc, int Nc,
+                 int G, cudaStream_t s) {
+  static bool attr = false;
+  if (!attr) {
+    WF_CUDA(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    attr = true;
+  }
+  const int64_t tiles = (R + LIN_BM - 1) / LIN_BM;
+  const int grid = (int)(tiles < WGRAD_CTAS ? tiles : WGRAD_CTAS);
+  wgrad_kernel<<<grid, LIN_THREADS, smem_wgrad(Kc, Nc), s>>>(X, dY, partial, R, Kc, Nc, G);
+  WF_LAUNCH_CHECK();
+  const int tot = (Kc + 1) * Nc;
+  wgrad_reduce_kernel<<<(tot + 127) / 128, 128, 0, s>>>(partial, grid, gW, gb, layer, D, Kc, Nc);
+  WF_LAUNCH_CHECK();
+  return WF_OK;
+}
+
+void fill_wq_I(const wf_live_model* m, float* w) {
+  // remove_bias on ones (isplines_jax.py:196-199), then {0:0} | {0:1} zero the end coefficients (isplines_jax.py:160-176)
+  const int P = m->P_I, k = m->k_I;
+  for (int q = 0; q < WF_MAX_P; ++q) w[q] = q < P ? 1.f : 0.f;
+  for (int i = 0; i < k; ++i) {
+    const int a = i + 1, b = P - (i + 2);
+    if (a >= 0 && a < P) w[a] = w[a] * (float)(i + 1) / (float)k;
+    if (b >= 0 && b < P) w[b] = w[b] * (float)(i + 1) / (float)k;
+  }
+  w[0] = 0.f; w[P - 1] = 0.f;
+}
+
+template <int D>
+int run_chunk(const wf_live_model* m, const wf_live_tables* t, const float* params, const float* protons, int n_protons,
+              const float* x, int64_t N, float running_average, float inv_n, float* grad, float* psi, float* hpsi, float* eloc,
+              double* sums, float* ws, cudaStream_t s) {
+  constexpr int G = D + 2;
+  const int nn = n_nets_of(m), L = m->n_layers, DPm = max_DP(m);
+  const int64_t R = N * G;
+  const Fixed fx = fixed_floats(m);
+  float* Wm = ws;
+  float* partial = Wm + fx.wm;
+  float* p = partial + fx.partial;
+  auto take = [&](int64_t n) { float* q = p; p += n; return q; };
+  float* U[WF_MAX_LAYERS + 2];
+  for (int i = 0; i <= nn; ++i) U[i] = take(R * D);
+  float *Z1[WF_MAX_LAYERS + 1], *H1[WF_MAX_LAYERS + 1], *Z2[WF_MAX_LAYERS + 1], *H2[WF_MAX_LAYERS + 1], *O[WF_MAX_LAYERS + 1];
+  for (int i = 0; i < nn; ++i) { Z1[i] = take(R * HID); H1[i] = take(R * HID); Z2[i] = take(R * HID); H2[i] = take(R * HID); O[i] = take(R * DPm); }
+  float* LDbox = take(R);
+  float* LDC = take((int64_t)L * R * D);
+  float* PHI = take(R * D);
+  float* PHIbar = take(R * D);
+  float* LDbar = take(R);
+  float* Obar = take(R * DPm);
+  float* HbA = take(R * HID);
+  float* HbB = take(R * HID);
+  float* Ub[2] = {take(R * D), take(R * D)};
+
+  // masked weights (model_factory.py:31-33)
+  NetOff off[WF_MAX_LAYERS + 1];
+  float *W1m[WF_MAX_LAYERS + 1], *W2m[WF_MAX_LAYERS + 1], *W3m[WF_MAX_LAYERS + 1];
+  {
+    int64_t base = 0;
+    float* w = Wm;
+    for (int i = 0; i < nn; ++i) {
+      const int P = net_P(m, i), DP = D * P;
+      off[i] = net_offsets(D, P, base);
+      base = off[i].end;
+      W1m[i] = w; w += D * HID;
+      W2m[i] = w; w += HID * HID;
+      W3m[i] = w; w += HID * DP;
+      mask_weights_kernel<<<(D * HID + 127) / 128, 128, 0, s>>>(params + off[i].W1, W1m[i], 1, D, D, HID);
+      mask_weights_kernel<<<(HID * HID + 127) / 128, 128, 0, s>>>(params + off[i].W2, W2m[i], 2, D, HID, HID);
+      mask_weights_kernel<<<(HID * DP + 127) / 128, 128, 0, s>>>(params + off[i].W3, W3m[i], 3, D, HID, DP);
+    }
+    WF_LAUNCH_CHECK();
+  }
+
+  HeadArgs ha;
+  ha.tab = t->dense_I; ha.N = N; ha.P = m->P_I; ha.T = m->T; ha.reg = m->reg;
+  fill_wq_I(m, ha.wq);
+  PriorArgs pa;
+  pa.tab = t->dense_P; pa.ob_to_b = t->ob_to_b; pa.N = N; pa.P = m->P_P; pa.T = m->T;
+  pa.cons_lo = m->coord_mean ? 0 : 1;
+  pa.cons_hi = m->coord_mean ? D - 1 : D;
+  for (int q = 0; q < WF_MAX_P; ++q) pa.mb[q] = (q > 0 && q < m->P_P - 1) ? 1.f : 0.f;
+
+  const int eb = 256;
+  const int64_t nh = N * HID, nd = N * D;
+  const int hb = (int)((nd + HEAD_THREADS - 1) / HEAD_THREADS);
+
+  // ---------------- forward
+  box_kernel<D><<<(int)((N + 127) / 128), 128, 0, s>>>(x, N, m->box, m->coord_mean, U[0], LDbox);
+  WF_LAUNCH_CHECK();
+  for (int i = 0; i < nn; ++i) {
+    const int P = net_P(m, i), DP = D * P;
+    int st;
+    if ((st = launch_linear<false, false>(U[i], W1m[i], params + off[i].b1, Z1[i], R, D, HID, G, s)) != WF_OK) return st;
+    tanh_fwd_kernel<D><<<(int)((nh + eb - 1) / eb), eb, 0, s>>>(Z1[i], H1[i], N);
+    if ((st = launch_linear<false, false>(H1[i], W2m[i], params + off[i].b2, Z2[i], R, HID, HID, G, s)) != WF_OK) return st;
+    tanh_fwd_kernel<D><<<(int)((nh + eb - 1) / eb), eb, 0, s>>>(Z2[i], H2[i], N);
+    if ((st = launch_linear<false, false>(H2[i], W3m[i], params + off[i].b3, O[i], R, HID, DP, G, s)) != WF_OK) return st;
+    if (i < L) {
+      ha.O = O[i]; ha.U = U[i];
+      imade_fwd_kernel<D><<<hb, HEAD_THREADS, 0, s>>>(ha, U[i + 1], LDC + (int64_t)i * R * D);
+    } else {
+      pa.O = O[i]; pa.U = U[i];
+      prior_fwd_kernel<D><<<hb, HEAD_THREADS, 0, s>>>(pa, PHI);
+    }
+    WF_LAUNCH_CHECK();
+  }
+  FinalArgs fa;
+  fa.x = x; fa.PHI = PHI; fa.LDbox = LDbox; fa.LDC = LDC; fa.N = N; fa.ldc_stride = R * D; fa.n_layers = L;
+  fa.n_protons = n_protons;
+  for (int i = 0; i < WF_MAX_D; ++i) fa.protons[i] = i < n_protons ? protons[i] : 0.f;
+  fa.running_average = running_average; fa.inv_n = inv_n;
+  fa.PHIbar = PHIbar; fa.LDbar = LDbar; fa.psi = psi; fa.hpsi = hpsi; fa.eloc = eloc; fa.sums = sums;
+  final_kernel<D><<<(int)((N + 127) / 128), 128, 0, s>>>(fa);
+  WF_LAUNCH_CHECK();
+  if (!grad) return WF_OK;
+
+  // ---------------- backward
+  int cur = 0;
+  for (int i = nn - 1; i >= 0; --i) {
+    const int P = net_P(m, i), DP = D * P;
+    float* Ucur = Ub[cur];
+    if (i == L) {
+      pa.O = O[i]; pa.U = U[i];
+      prior_bwd_kernel<D><<<hb, HEAD_THREADS, 0, s>>>(pa, PHIbar, Obar, Ucur);
+    } else {
+      ha.O = O[i]; ha.U = U[i];
+      imade_bwd_kernel<D><<<hb, HEAD_THREADS, 0, s>>>(ha, Ub[cur ^ 1], LDbar, Obar, Ucur);
+    }
+    WF_LAUNCH_CHECK();
+    int st;
+    if ((st = launch_wgrad(H2[i], Obar, partial, grad + off[i].W3, grad + off[i].b3, 3, D, R, HID, DP, G, s)) != WF_OK) return st;
+    if ((st = launch_linear<true, false>(Obar, W3m[i], nullptr, HbA, R, DP, HID, G, s)) != WF_OK) return st;
+    tanh_bwd_kernel<D><<<(int)((nh + eb - 1) / eb), eb, 0, s>>>(Z2[i], HbA, N);
+    if ((st = launch_wgrad(H1[i], HbA, partial, grad + off[i].W2, grad + off[i].b2, 2, D, R, HID, HID, G, s)) != WF_OK) return st;
+    if ((st = launch_linear<true, false>(HbA, W2m[i], nullptr, HbB, R, HID, HID, G, s)) != WF_OK) return st;
+    tanh_bwd_kernel<D><<<(int)((nh + eb - 1) / eb), eb, 0, s>>>(Z1[i], HbB, N);
+    if ((st = launch_wgrad(U[i], HbB, partial, grad + off[i].W1, grad + off[i].b1, 1, D, R, D, HID, G, s)) != WF_OK) return st;
+    if (i > 0 && (st = launch_linear<true, true>(HbB, W1m[i], nullptr, Ucur, R, HID, D, G, s)) != WF_OK) return st;
+    WF_LAUNCH_CHECK();
+    cur ^= 1;
+  }
+  return WF_OK;
+}
+
+}  // namespace
+
+extern "C" int64_t wf_vqmc_param_floats(const wf_live_model* m) {
+  if (check_model(m) != WF_OK) return -1;
+  int64_t base = 0;
+  for (int i = 0; i < n_nets_of(m); ++i) base = net_offsets(m->D, net_P(m, i), base).end;
+  return base;
+}
+
+extern "C" int64_t wf_vqmc_grad_workspace_floats(const wf_live_model* m, int64_t walkers) {
+  if (check_model(m) != WF_OK || walkers < 0) return -1;
+  return fixed_floats(m).total + walkers * (m->D + 2) * per_row_floats(m) + 64;
+}
+
+extern "C" int wf_vqmc_loss_grad(const wf_live_model* m, const wf_live_tables* t, const float* params, const float* protons_host,
+                                 int n_protons, const float* x, int64_t N, float running_average, float inv_n_total, float* grad,
+                                 float* psi, float* hpsi, float* eloc, double* sums, float* workspace, int64_t workspace_floats,
+                                 void* stream) {
+  const int st = check_model(m);
+  if (st != WF_OK) return st;
+  if (N == 0) return WF_OK;
+  if (!t || !t->dense_I || !t->dense_P || !t->ob_to_b || !params || !x || !workspace || N < 0) return WF_ERR_INVALID_ARG;
+  if (n_protons < 0 || n_protons > WF_MAX_D || (n_protons > 0 && !protons_host)) return WF_ERR_INVALID_ARG;
+  const int64_t avail = workspace_floats - fixed_floats(m).total - 64;
+  const int64_t per_walker = (m->D + 2) * per_row_floats(m);
+  int64_t chunk = avail / per_walker;
+  if (chunk < 1) return WF_ERR_INVALID_ARG;
+  if (chunk > N) chunk = N;
+  cudaStream_t s = (cudaStream_t)stream;
+  for (int64_t lo = 0; lo < N; lo += chunk) {
+    const int64_t n = (N - lo) < chunk ? (N - lo) : chunk;
+    const float* xc = x + lo * m->D;
+    float* pc = psi ? psi + lo : nullptr;
+    float* hc = hpsi ? hpsi + lo : nullptr;
+    float* ec = eloc ? eloc + lo : nullptr;
+    int r;
+    switch (m->D) {
+      case 2: r = run_chunk<2>(m, t, params, protons_host, n_protons, xc, n, running_average, inv_n_total, grad, pc, hc, ec, sums, workspace, s); break;
+      case 3: r = run_chunk<3>(m, t, params, protons_host, n_protons, xc, n, running_average, inv_n_total, grad, pc, hc, ec, sums, workspace, s); break;
+      default: r = run_chunk<4>(m, t, params, protons_host, n_protons, xc, n, running_average, inv_n_total, grad, pc, hc, ec, sums, workspace, s); break;
+    }
+    if (r != WF_OK) return r;
+  }
+  return WF_OK;
+}
+
+extern "C" int wf_adam_step(float* params, float* m, float* v, const float* grad, int64_t n, int64_t step, float lr, float b1,
+                            float b2, float eps, void* stream) {
+  if (n == 0) return WF_OK;
+  if (!params || !m || !v || !grad || n < 0 || step < 0) return WF_ERR_INVALID_ARG;
+  const float c1 = 1.f - powf(b1, (float)(step + 1)), c2 = 1.f - powf(b2, (float)(step + 1));
+  adam_kernel<<<(int)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(params, m, v, grad, n, lr, b1, b2, eps, c1, c2);
+  WF_LAUNCH_CHECK();
+  return WF_OK;
+}

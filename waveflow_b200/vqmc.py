@@ -1,29 +1,30 @@
 """VQMC entry points -- reference: vqmc.py:19-221.
 
-What is built here is the reference's *energy evaluation* path: create_train_state (model construction, vqmc.py:123-139),
-loss_fn_efficient's forward value mean(H psi / (psi + 1e-8)) (vqmc.py:193-200) and a sharded energy estimator.  The
-parameter gradient / Adam step of train_step_efficient (vqmc.py:202-221) is the next row of the scope table
-and raises NotImplementedError.
+create_train_state (model construction + Adam state, vqmc.py:123-139), loss_fn_efficient (vqmc.py:193-200),
+train_step_efficient = value_and_grad(loss_fn_efficient) + Adam update (vqmc.py:202-221) and a walker-sharded energy
+estimator.  The gradient is wf_vqmc_loss_grad: a reverse pass through the forward-mode Laplacian (csrc/train.cu).
 """
 from __future__ import annotations
 
 import numpy as np
 import torch
 
-from . import _live
+from . import _live, _train
 from .model_factory import get_waveflow_model
 from .utils import physics
 
 
 def create_train_state(box_length, learning_rate, n_particle, rng=0, xu_coord_type='mean', spline_degree=6, num_knots=23,
-                       n_flow_layers=3, cached_bases_root='./cached_splines_bases'):
-    """-> (psi, log_pdf, sample, params).  The reference also returns the Adam state (vqmc.py:136-139); see module doc."""
+                       n_flow_layers=3, cached_bases_root='./cached_splines_bases', device='cuda'):
+    """-> (psi, log_pdf, sample, opt_state, opt_update, get_params)  (vqmc.py:123-139)."""
     init_fun = get_waveflow_model(n_particle, base_spline_degree=spline_degree, i_spline_degree=spline_degree,
                                   n_prior_internal_knots=num_knots, n_i_internal_knots=num_knots, i_spline_reg=0.05,
                                   i_spline_reverse_fun_tol=0.000001, n_flow_layers=n_flow_layers, box_size=box_length,
                                   xu_coord_type=xu_coord_type, cached_bases_root=cached_bases_root)
     params, psi, log_pdf, sample = init_fun(rng, n_particle)
-    return psi, log_pdf, sample, params
+    opt_init, opt_update, get_params = _train.adam(step_size=learning_rate, device=device)
+    opt_state = opt_init(params)
+    return psi, log_pdf, sample, opt_state, opt_update, get_params
 
 
 def loss_fn_efficient(params, psi, h_fn, batch, running_average=None):
@@ -32,8 +33,47 @@ def loss_fn_efficient(params, psi, h_fn, batch, running_average=None):
     return out["eloc"].mean()
 
 
-def train_step_efficient(*args, **kwargs):
-    raise NotImplementedError("parameter gradients of the local energy (vqmc.py:202-221) are not built yet (SURVEY 8f rank 1)")
+def _flat_of(params, opt_state, device):
+    """The flat buffer behind `params`: opt_state's own buffer when params is get_params(opt_state), else a copy."""
+    if opt_state is not None and params is opt_state.tree:
+        return opt_state.flat
+    return _train.ravel(params, device)
+
+
+def value_and_grad_efficient(params, psi, h_fn, batch, running_average, group=None, opt_state=None, flat_grad=False):
+    """value_and_grad(loss_fn_efficient, argnums=0)(params, psi, h_fn, batch, running_average)  (vqmc.py:220).
+
+    -> (loss, gradients in the structure of `params`).  With torch.distributed initialised, `batch` is this rank's shard of
+    the walkers: the loss sums and the flat gradient are all-reduced, so every rank gets the global result.
+    """
+    spec = h_fn.wf_spec
+    if spec is None:
+        raise _live._ffi.WaveflowB200Error("train_step_efficient needs the fused Waveflow configuration of get_waveflow_model")
+    x = _live._ffi.f32(batch)
+    dev = x.device
+    flat = _flat_of(params, opt_state, dev)
+    dist = torch.distributed
+    world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+    n_total = x.shape[0]
+    if world > 1:
+        cnt = torch.tensor([x.shape[0]], dtype=torch.int64, device=dev)
+        dist.all_reduce(cnt, group=group)
+        n_total = int(cnt.item())
+    sums = torch.zeros(4, dtype=torch.float64, device=dev)
+    grad, _ = _train.loss_grad(spec, flat, x, h_fn.protons, float(running_average), n_total=n_total, sums=sums)
+    if world > 1:
+        dist.all_reduce(grad, group=group)
+        dist.all_reduce(sums, group=group)
+    # the mean is over ALL walkers, as jnp.mean does (non-finite E_loc are not dropped by the reference; sums[2] counts the finite ones)
+    loss = (sums[0] / float(n_total)).to(torch.float32)
+    return loss, (grad if flat_grad else _train.unravel(params, grad))
+
+
+def train_step_efficient(epoch, psi, h_fn, opt_update, opt_state, params, batch, running_average, group=None):
+    """vqmc.py:214-221: -> (opt_update(epoch, gradients, opt_state), loss_val)."""
+    loss_val, gradients = value_and_grad_efficient(params, psi, h_fn, batch, running_average, group=group, opt_state=opt_state,
+                                                   flat_grad=True)
+    return opt_update(epoch, gradients, opt_state), loss_val
 
 
 class EnergyEstimator:
@@ -93,13 +133,37 @@ class ModelTrainer:
         self.save_dir = f'./results/{self.system_name}_{self.n_space_dimension}d_L{self.box_length}box'
 
     def build(self, rng=2, cached_bases_root='./cached_splines_bases'):
-        psi, log_pdf, sample, params = create_train_state(self.box_length, self.learning_rate, n_particle=self.n_particle,
-                                                          rng=rng, xu_coord_type=self.xu_coord_type,
-                                                          spline_degree=self.spline_degree, num_knots=self.num_knots,
-                                                          n_flow_layers=self.n_flow_layer, cached_bases_root=cached_bases_root)
+        psi, log_pdf, sample, opt_state, opt_update, get_params = create_train_state(
+            self.box_length, self.learning_rate, n_particle=self.n_particle, rng=rng, xu_coord_type=self.xu_coord_type,
+            spline_degree=self.spline_degree, num_knots=self.num_knots, n_flow_layers=self.n_flow_layer,
+            cached_bases_root=cached_bases_root)
         h_fn = physics.construct_hamiltonian_function(psi, protons=self.system, n_space_dimensions=self.n_space_dimension, eps=0.0)
-        return psi, log_pdf, sample, params, h_fn
+        self.opt_state, self.opt_update, self.get_params = opt_state, opt_update, get_params
+        return psi, log_pdf, sample, get_params(opt_state), h_fn
 
-    def start_training(self, restart=False):
-        raise NotImplementedError("the optimisation loop needs parameter gradients (SURVEY 8f rank 1); "
-                                  "use build() + EnergyEstimator for the energy evaluation path")
+    def start_training(self, restart=False, num_epochs=None, rng=2, cached_bases_root='./cached_splines_bases', save=False,
+                       callback=None):
+        """The optimisation loop of vqmc.py:53-117: sample a batch from |psi|^2, one train_step_efficient, running average
+        of the last 100 losses refreshed every 100 epochs.  -> (params, loss history).  Checkpoint / plot writers
+        (helpers.create_checkpoint_wavefunc) are not part of this path; save=True stores loss.npy / energies.npy only."""
+        psi, log_pdf, sample, params, h_fn = self.build(rng=rng, cached_bases_root=cached_bases_root)
+        opt_state, opt_update, get_params = self.opt_state, self.opt_update, self.get_params
+        running_average = 0.0
+        loss = [0.0]
+        for epoch in range(1, (num_epochs or self.num_epochs) + 1):
+            batch = sample(rng * 1000003 + epoch, params, self.batch_size)
+            opt_state, new_loss = train_step_efficient(epoch, psi, h_fn, opt_update, opt_state, params, batch, running_average)
+            if epoch % 100 == 0:
+                running_average = float(np.mean(loss[-100:]))
+            params = get_params(opt_state)
+            loss.append(float(new_loss))
+            if callback is not None:
+                callback(epoch, loss[-1], params)
+            if epoch % self.log_every == 0:
+                print(f"epoch {epoch} | Loss: {loss[-1]:.3f}")
+        if save:
+            from pathlib import Path
+            Path(self.save_dir).mkdir(parents=True, exist_ok=True)
+            np.save(f"{self.save_dir}/loss.npy", np.asarray(loss))
+            np.save(f"{self.save_dir}/energies.npy", np.asarray(loss[1:])[:, None])
+        return params, loss
