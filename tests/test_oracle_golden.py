@@ -117,3 +117,33 @@ def test_rqs_coupling_bijective_atol_1e_3():
     x2, l2 = rqs.coupling_flow_inverse(layers, z, K, B)
     assert z.shape == x.shape and l1.shape == (20,)
     assert np.allclose(x, x2, atol=1e-3)
+
+
+def test_gradient_oracle_against_finite_differences(he):
+    """oracle/grad.py (three reverse passes) vs central differences of the surrogate through the independent numpy
+    bundle oracle, on prior-net parameters: their gradient does not pass through a table argument, so the custom_jvp
+    table derivative (next table, Q5 clamp) and the true slope of the interpolant coincide there."""
+    from oracle import grad as ograd
+    params, _ = he
+    m = fx.waveflow_model(2)
+    p = fx.cast_params(params, np.float64)
+    x = np.sort(np.random.default_rng(1).uniform(-3, 3, (6, 2)), axis=1)
+    protons = np.array([[0.0], [0.0]])
+    loss, g = ograd.loss_and_grad(m, p, x, protons, -1.8)
+    r = lap.local_energy_bundle(m, p, x, protons)
+    eloc, a, b = ograd.coefficients(r["psi"], r["hpsi"], -1.8)
+    assert abs(loss - eloc.mean()) < 1e-9 * abs(loss)
+    for layer, idx in [((4, 1), (5,)), ((4, 0), (3, 7)), ((2, 0), (3, 7)), ((0, 0), (0, 7))]:
+        arr = p[1][0][layer[0]][layer[1]]
+        orig = arr[idx]
+        vals = []
+        for h in (1e-6, -1e-6):
+            arr[idx] = orig + h
+            vals.append(ograd.surrogate_value(m, p, x, protons, a, b))
+        arr[idx] = orig
+        fd = (vals[0] - vals[1]) / 2e-6
+        got = g[1][0][layer[0]][layer[1]][idx]
+        assert abs(got - fd) <= 1e-6 * abs(fd) + 1e-7, (layer, got, fd)
+    # flow-layer gradients exist and are finite; zero_params get zeros
+    for net in [n for n in g[0] if len(n)]:
+        assert all(np.all(np.isfinite(a_)) for lay in net[0] for a_ in lay) and not np.any(net[1])

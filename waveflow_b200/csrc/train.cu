@@ -16,7 +16,6 @@ using namespace wf::train;
 namespace {
 
 constexpr int HID = 64;            // conditioner width (model_factory.py:40)
-constexpr int LIN_BM = 64;         // rows per tile of the linear / weight-gradient kernels
 constexpr int LIN_THREADS = 256;
 constexpr int MAX_W = 128;         // widest layer (D * P)
 constexpr int HEAD_THREADS = 128;
@@ -38,132 +37,187 @@ __global__ void mask_weights_kernel(const float* __restrict__ W, float* __restri
 
 // ---------------------------------------------------------------------------------------------- linear layers
 // C[R][Nc] (+)= A[R][Kc] * B (+ bias on the value rows r % G == 0).  TRANS_B == false: B [Kc][Nc]; true: B given as [Nc][Kc].
-template <bool TRANS_B, bool ACCUM>
+// CTA tile GM rows x BN (padded) columns, the whole K extent resident in shared memory; thread tile RM x 8 with 128-bit
+// shared loads (A row-major with k contiguous, B k-major).
+constexpr int GM = 128;
+template <int BN, bool TRANS_B, bool ACCUM>
 __global__ void __launch_bounds__(LIN_THREADS) linear_kernel(const float* __restrict__ A, const float* __restrict__ B,
                                                              const float* __restrict__ bias, float* __restrict__ C,
                                                              int64_t R, int Kc, int Nc, int G) {
-  extern __shared__ float sm[];
-  const int NcP = (Nc + 15) & ~15;
-  float* Bs = sm;                         // [Kc][NcP]
-  float* As = sm + Kc * NcP;              // [LIN_BM][Kc]
-  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-  for (int i = tid; i < Kc * NcP; i += LIN_THREADS) {
-    const int k = i / NcP, n = i % NcP;
-    Bs[i] = n < Nc ? (TRANS_B ? B[(int64_t)n * Kc + k] : B[(int64_t)k * Nc + n]) : 0.f;
+  extern __shared__ __align__(16) float sm[];
+  constexpr int TX = BN / 8, TY = LIN_THREADS / TX, RM = GM / TY;
+  const int KcP = (Kc + 3) & ~3, LDA = KcP + 4;
+  float* Bs = sm;                         // [KcP][BN]
+  float* As = sm + KcP * BN;              // [GM][LDA]
+  const int tid = threadIdx.x, tx = tid % TX, ty = tid / TX;
+  for (int i = tid; i < KcP * BN; i += LIN_THREADS) {
+    const int k = i / BN, n = i % BN;
+    Bs[i] = (k < Kc && n < Nc) ? (TRANS_B ? B[(int64_t)n * Kc + k] : B[(int64_t)k * Nc + n]) : 0.f;
   }
-  const int NJ = NcP >> 4;
-  const int64_t tiles = (R + LIN_BM - 1) / LIN_BM;
+  const int64_t tiles = (R + GM - 1) / GM;
   for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-    const int64_t r0 = tile * LIN_BM;
-    const int rows = (int)min((int64_t)LIN_BM, R - r0);
+    const int64_t r0 = tile * GM;
+    const int rows = (int)min((int64_t)GM, R - r0);
     __syncthreads();
-    const float* Ag = A + r0 * Kc;
-    for (int i = tid; i < LIN_BM * Kc; i += LIN_THREADS) As[i] = i < rows * Kc ? Ag[i] : 0.f;
+    if ((Kc & 3) == 0) {
+      const int k4n = Kc >> 2;
+      for (int i = tid; i < GM * k4n; i += LIN_THREADS) {
+        const int row = i / k4n, k4 = i % k4n;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (row < rows) v = *reinterpret_cast<const float4*>(A + (r0 + row) * Kc + 4 * k4);
+        *reinterpret_cast<float4*>(As + row * LDA + 4 * k4) = v;
+      }
+    } else {
+      for (int i = tid; i < GM * KcP; i += LIN_THREADS) {
+        const int row = i / KcP, k = i % KcP;
+        As[row * LDA + k] = (row < rows && k < Kc) ? A[(r0 + row) * Kc + k] : 0.f;
+      }
+    }
     __syncthreads();
-    float acc[4][8];
+    float acc[RM][8];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < RM; ++i)
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
-    for (int k = 0; k < Kc; ++k) {
-      float a[4], b[8];
+#pragma unroll 2
+    for (int k = 0; k < KcP; k += 4) {
+      float4 a[RM];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) a[i] = As[(ty * 4 + i) * Kc + k];
+      for (int i = 0; i < RM; ++i) a[i] = *reinterpret_cast<const float4*>(As + (ty * RM + i) * LDA + k);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) b[j] = j < NJ ? Bs[k * NcP + tx + 16 * j] : 0.f;
+      for (int kk = 0; kk < 4; ++kk) {
+        const float4 b0 = *reinterpret_cast<const float4*>(Bs + (k + kk) * BN + tx * 4);
+        const float4 b1 = *reinterpret_cast<const float4*>(Bs + (k + kk) * BN + BN / 2 + tx * 4);
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        for (int i = 0; i < RM; ++i) {
+          const float av = kk == 0 ? a[i].x : (kk == 1 ? a[i].y : (kk == 2 ? a[i].z : a[i].w));
+          acc[i][0] = fmaf(av, b0.x, acc[i][0]); acc[i][1] = fmaf(av, b0.y, acc[i][1]);
+          acc[i][2] = fmaf(av, b0.z, acc[i][2]); acc[i][3] = fmaf(av, b0.w, acc[i][3]);
+          acc[i][4] = fmaf(av, b1.x, acc[i][4]); acc[i][5] = fmaf(av, b1.y, acc[i][5]);
+          acc[i][6] = fmaf(av, b1.z, acc[i][6]); acc[i][7] = fmaf(av, b1.w, acc[i][7]);
+        }
+      }
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int rl = ty * 4 + i;
+    for (int i = 0; i < RM; ++i) {
+      const int rl = ty * RM + i;
       if (rl >= rows) continue;
       const int64_t r = r0 + rl;
-      const bool value_row = (r % G) == 0;
+      const bool value_row = bias && (r % G) == 0;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int n = tx + 16 * j;
-        if (j < NJ && n < Nc) {
-          float v = acc[i][j];
-          if (bias && value_row) v += bias[n];
-          if (ACCUM) v += C[r * Nc + n];
-          C[r * Nc + n] = v;
+      for (int h = 0; h < 2; ++h) {
+        const int n0 = h * (BN / 2) + tx * 4;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int n = n0 + j;
+          if (n < Nc) {
+            float v = acc[i][h * 4 + j];
+            if (value_row) v += bias[n];
+            if (ACCUM) v += C[r * Nc + n];
+            C[r * Nc + n] = v;
+          }
         }
       }
     }
   }
 }
 
-// partial[cta][Kc + 1][Nc] = sum over the CTA's rows of X[r][k] * dY[r][n]; row Kc = value-row indicator (bias gradient)
+// partial[cta][Kc + 1][Nc] = sum over the CTA's rows of X[r][k] * dY[r][n]; row Kc = sum over the value rows (bias gradient).
+// Thread tile 4 (k) x BN/16 (n), 64-row tiles, 128-bit shared loads.
+constexpr int WG_ROWS = 64;
+template <int BN>
 __global__ void __launch_bounds__(LIN_THREADS) wgrad_kernel(const float* __restrict__ X, const float* __restrict__ dY,
                                                             float* __restrict__ partial, int64_t R, int Kc, int Nc, int G) {
-  extern __shared__ float sm[];
-  const int K1 = Kc + 1;
-  const int NcP = (Nc + 15) & ~15;
-  float* Xs = sm;                       // [LIN_BM][K1]
-  float* Ys = sm + LIN_BM * K1;         // [LIN_BM][NcP]
+  extern __shared__ __align__(16) float sm[];
+  constexpr int NB = BN / 16;
+  const int KcP = (Kc + 3) & ~3, LDX = KcP + 4;
+  float* Xs = sm;                          // [WG_ROWS][LDX]
+  float* Ys = Xs + WG_ROWS * LDX;          // [WG_ROWS][BN]
+  float* Ind = Ys + WG_ROWS * BN;          // [WG_ROWS]
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-  const int NI = (K1 + 15) >> 4, NJ = NcP >> 4;
-  float acc[5][8];
+  const bool kact = ty * 4 < KcP;
+  float acc[4][NB], accb[NB];
 #pragma unroll
-  for (int i = 0; i < 5; ++i)
+  for (int j = 0; j < NB; ++j) {
+    accb[j] = 0.f;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
-  const int64_t tiles = (R + LIN_BM - 1) / LIN_BM;
+    for (int i = 0; i < 4; ++i) acc[i][j] = 0.f;
+  }
+  const int64_t tiles = (R + WG_ROWS - 1) / WG_ROWS;
   for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-    const int64_t r0 = tile * LIN_BM;
-    const int rows = (int)min((int64_t)LIN_BM, R - r0);
+    const int64_t r0 = tile * WG_ROWS;
+    const int rows = (int)min((int64_t)WG_ROWS, R - r0);
     __syncthreads();
-    for (int i = tid; i < LIN_BM * K1; i += LIN_THREADS) {
-      const int rl = i / K1, k = i % K1;
-      float v = 0.f;
-      if (rl < rows) v = k < Kc ? X[(r0 + rl) * Kc + k] : (((r0 + rl) % G) == 0 ? 1.f : 0.f);
-      Xs[i] = v;
+    for (int i = tid; i < WG_ROWS * KcP; i += LIN_THREADS) {
+      const int rl = i / KcP, k = i % KcP;
+      Xs[rl * LDX + k] = (rl < rows && k < Kc) ? X[(r0 + rl) * Kc + k] : 0.f;
     }
-    for (int i = tid; i < LIN_BM * NcP; i += LIN_THREADS) {
-      const int rl = i / NcP, n = i % NcP;
+    for (int i = tid; i < WG_ROWS * BN; i += LIN_THREADS) {
+      const int rl = i / BN, n = i % BN;
       Ys[i] = (rl < rows && n < Nc) ? dY[(r0 + rl) * Nc + n] : 0.f;
     }
+    if (tid < WG_ROWS) Ind[tid] = (tid < rows && ((r0 + tid) % G) == 0) ? 1.f : 0.f;
     __syncthreads();
-    for (int r = 0; r < rows; ++r) {
-      float x[5], y[8];
+#pragma unroll 2
+    for (int r = 0; r < WG_ROWS; ++r) {
+      float y[NB];
+      {
+        const float4 y0 = *reinterpret_cast<const float4*>(Ys + r * BN + tx * 4);
+        y[0] = y0.x; y[1] = y0.y; y[2] = y0.z; y[3] = y0.w;
+        if (NB == 8) {
+          const float4 y1 = *reinterpret_cast<const float4*>(Ys + r * BN + BN / 2 + tx * 4);
+          y[NB - 4] = y1.x; y[NB - 3] = y1.y; y[NB - 2] = y1.z; y[NB - 1] = y1.w;
+        }
+      }
+      const float ind = Ind[r];
 #pragma unroll
-      for (int i = 0; i < 5; ++i) x[i] = (i < NI && ty + 16 * i < K1) ? Xs[r * K1 + ty + 16 * i] : 0.f;
+      for (int j = 0; j < NB; ++j) accb[j] = fmaf(ind, y[j], accb[j]);
+      if (kact) {
+        const float4 x4 = *reinterpret_cast<const float4*>(Xs + r * LDX + ty * 4);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) y[j] = j < NJ ? Ys[r * NcP + tx + 16 * j] : 0.f;
-#pragma unroll
-      for (int i = 0; i < 5; ++i)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(x[i], y[j], acc[i][j]);
+        for (int j = 0; j < NB; ++j) {
+          acc[0][j] = fmaf(x4.x, y[j], acc[0][j]); acc[1][j] = fmaf(x4.y, y[j], acc[1][j]);
+          acc[2][j] = fmaf(x4.z, y[j], acc[2][j]); acc[3][j] = fmaf(x4.w, y[j], acc[3][j]);
+        }
+      }
     }
   }
-  float* out = partial + (int64_t)blockIdx.x * K1 * Nc;
+  float* out = partial + (int64_t)blockIdx.x * (Kc + 1) * Nc;
 #pragma unroll
-  for (int i = 0; i < 5; ++i) {
-    const int k = ty + 16 * i;
-    if (i >= NI || k >= K1) continue;
+  for (int j = 0; j < NB; ++j) {
+    const int n = (NB == 8 && j >= 4) ? BN / 2 + tx * 4 + (j - 4) : tx * 4 + j;
+    if (n >= Nc) continue;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int n = tx + 16 * j;
-      if (j < NJ && n < Nc) out[(int64_t)k * Nc + n] = acc[i][j];
+    for (int i = 0; i < 4; ++i) {
+      const int k = ty * 4 + i;
+      if (k < Kc) out[(int64_t)k * Nc + n] = acc[i][j];
     }
+    if (ty == 0) out[(int64_t)Kc * Nc + n] = accb[j];
   }
 }
 
 // gW[k][n] += mask * sum_cta partial[cta][k][n];  gb[n] += sum_cta partial[cta][Kc][n]   (fixed summation order)
-__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int n_cta, float* __restrict__ gW, float* __restrict__ gb,
-                                    int layer, int D, int Kc, int Nc) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (Kc + 1) * Nc) return;
-  const int k = i / Nc, n = i % Nc;
+// block = 32 outputs x 8 slices of the CTA axis: coalesced partial reads, then a shared-memory tree over the slices
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ partial, int n_cta, float* __restrict__ gW,
+                                                           float* __restrict__ gb, int layer, int D, int Kc, int Nc) {
+  __shared__ float red[8][33];
+  const int ii = threadIdx.x & 31, ci = threadIdx.x >> 5;
+  const int tot = (Kc + 1) * Nc;
+  const int i = blockIdx.x * 32 + ii;
   float s = 0.f;
-  for (int c = 0; c < n_cta; ++c) s += partial[(int64_t)c * (Kc + 1) * Nc + i];
-  if (k < Kc) {
-    if (made_mask(layer, D, k, n)) gW[i] += s;
-  } else {
-    gb[n] += s;
+  if (i < tot)
+    for (int c = ci; c < n_cta; c += 8) s += partial[(int64_t)c * tot + i];
+  red[ci][ii] = s;
+  __syncthreads();
+  if (ci == 0 && i < tot) {
+#pragma unroll
+    for (int c = 1; c < 8; ++c) s += red[c][ii];
+    const int k = i / Nc, n = i % Nc;
+    if (k < Kc) {
+      if (made_mask(layer, D, k, n)) gW[i] += s;
+    } else {
+      gb[n] += s;
+    }
   }
 }
 
@@ -248,7 +302,36 @@ __global__ void box_kernel(const float* __restrict__ x, int64_t N, float L, int 
   jstore<D>(LD, n, 1, 0, ld);
 }
 
-// ---------------------------------------------------------------------------------------------- IMADE spline head (made.py:66-81)
+// ---------------------------------------------------------------------------------------------- spline heads
+// One WARP per (walker, dimension): lane q owns coefficient q (P <= 32), so the per-coefficient jets live in registers,
+// table rows are read 128 bytes at a time, and the sums over coefficients are warp all-reduces of whole jets.
+template <int D>
+__device__ __forceinline__ Jet<D> warp_sum(Jet<D> j) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    j.v += __shfl_xor_sync(0xffffffffu, j.v, o);
+    j.l += __shfl_xor_sync(0xffffffffu, j.l, o);
+#pragma unroll
+    for (int i = 0; i < D; ++i) j.g[i] += __shfl_xor_sync(0xffffffffu, j.g[i], o);
+  }
+  return j;
+}
+template <int D>
+__device__ __forceinline__ Jet<D> warp_bcast(const Jet<D>& j, int src) {
+  Jet<D> o;
+  o.v = __shfl_sync(0xffffffffu, j.v, src);
+  o.l = __shfl_sync(0xffffffffu, j.l, src);
+#pragma unroll
+  for (int i = 0; i < D; ++i) o.g[i] = __shfl_sync(0xffffffffu, j.g[i], src);
+  return o;
+}
+template <int D>
+__device__ __forceinline__ Jet<D> sig_jet(const Jet<D>& o) {
+  const Sig g = sigmoid_derivs(o.v);
+  return junary(o, g.s, g.d1, g.d2);
+}
+
+// ---- IMADE head (made.py:66-81)
 struct HeadArgs {
   const float* O;      // [R][D*P] conditioner output jets
   const float* U;      // [R][D]   layer input jets
@@ -260,65 +343,57 @@ struct HeadArgs {
 };
 
 template <int D>
-struct ImadeFwd {
-  Jet<D> S1, r1, S2, r2;
+struct ImadeLane {
+  Jet<D> o, s, S1, r1, b, S2, r2, c, u, B0, B1, y, dy;
+  Basis4 f;
+  float wq;
+  bool act;
 };
 
+// everything the forward pass of one (walker, dimension) produces, per lane
 template <int D>
-__device__ __forceinline__ Jet<D> imade_b(const HeadArgs& a, const Jet<D>& s, const Jet<D>& r1, int p) {
-  Jet<D> b = jmul(s, r1);
-  b.v += a.reg;
-  return jscale(b, a.wq[p]);
-}
-template <int D>
-__device__ __forceinline__ Jet<D> sig_jet(const Jet<D>& o) {
-  const Sig g = sigmoid_derivs(o.v);
-  return junary(o, g.s, g.d1, g.d2);
-}
-
-template <int D>
-__device__ __forceinline__ ImadeFwd<D> imade_norms(const HeadArgs& a, int64_t n, int d) {
-  ImadeFwd<D> f;
+__device__ __forceinline__ void imade_lane_fwd(const HeadArgs& a, int64_t n, int d, int lane, ImadeLane<D>& L) {
   const int DP = D * a.P;
-  f.S1 = jzero<D>();
-#pragma unroll 1
-  for (int p = 0; p < a.P; ++p) jacc(f.S1, sig_jet(jload<D>(a.O, n, DP, p * D + d)));
-  f.r1 = jrecip(f.S1);
-  f.S2 = jzero<D>();
-#pragma unroll 1
-  for (int p = 0; p < a.P; ++p) {
-    if (a.wq[p] == 0.f) continue;
-    jacc(f.S2, imade_b(a, sig_jet(jload<D>(a.O, n, DP, p * D + d)), f.r1, p));
+  L.act = lane < a.P;
+  L.wq = L.act ? a.wq[lane] : 0.f;
+  L.o = L.act ? jload<D>(a.O, n, DP, lane * D + d) : jzero<D>();
+  L.s = L.act ? sig_jet(L.o) : jzero<D>();
+  L.S1 = warp_sum(L.s);
+  L.r1 = jrecip(L.S1);
+  L.b = jzero<D>();
+  if (L.wq != 0.f) {
+    L.b = jmul(L.s, L.r1);
+    L.b.v += a.reg;
+    L.b = jscale(L.b, L.wq);
   }
-  f.r2 = jrecip(f.S2);
-  return f;
+  L.S2 = warp_sum(L.b);
+  L.r2 = jrecip(L.S2);
+  L.c = jmul(L.b, L.r2);
+  L.u = jload<D>(a.U, n, D, d);
+  const NodeIdx ni = node_index(L.u.v, a.T);
+  L.f = basis4(a.tab, ni, (float)(a.T - 1), lane);     // padded table columns (lane >= P) are zero
+  L.B0 = junary(L.u, L.f.f[0], L.f.f[1], L.f.f[2]);
+  L.B1 = junary(L.u, L.f.f[1], L.f.f[2], L.f.f[3]);
+  L.y = warp_sum(jmul(L.c, L.B0));
+  L.dy = warp_sum(jmul(L.c, L.B1));
+  L.dy.v += LOG_TOL;
 }
 
 // Y [R][D] receives y at the REVERSED column (the Reverse layer, bijections.py:317-347); LDC [R][D] the log-det terms
 template <int D>
 __global__ void __launch_bounds__(HEAD_THREADS) imade_fwd_kernel(const __grid_constant__ HeadArgs a, float* __restrict__ Y,
                                                                  float* __restrict__ LDC) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= a.N * D) return;
-  const int64_t n = i / D;
-  const int d = (int)(i % D);
-  const int DP = D * a.P;
-  const ImadeFwd<D> f = imade_norms<D>(a, n, d);
-  const Jet<D> u = jload<D>(a.U, n, D, d);
-  const NodeIdx ni = node_index(u.v, a.T);
-  const float np_ = (float)(a.T - 1);
-  Jet<D> y = jzero<D>(), dy = jzero<D>();
-#pragma unroll 1
-  for (int p = 0; p < a.P; ++p) {
-    if (a.wq[p] == 0.f) continue;
-    const Jet<D> c = jmul(imade_b(a, sig_jet(jload<D>(a.O, n, DP, p * D + d)), f.r1, p), f.r2);
-    const Basis4 b = basis4(a.tab, ni, np_, p);
-    jacc(y, jmul(c, junary(u, b.f[0], b.f[1], b.f[2])));
-    jacc(dy, jmul(c, junary(u, b.f[1], b.f[2], b.f[3])));
+  const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= a.N * D) return;
+  const int64_t n = w / D;
+  const int d = (int)(w % D);
+  ImadeLane<D> L;
+  imade_lane_fwd<D>(a, n, d, lane, L);
+  if (lane == 0) {
+    jstore<D>(Y, n, D, D - 1 - d, L.y);
+    jstore<D>(LDC, n, D, d, jlog(L.dy));
   }
-  dy.v += LOG_TOL;
-  jstore<D>(Y, n, D, D - 1 - d, y);
-  jstore<D>(LDC, n, D, d, jlog(dy));
 }
 
 // Ybar [R][D]: adjoint of the NEXT layer's input (so y_d's adjoint sits at column D-1-d); LDbar [R]: adjoint of log|det|
@@ -326,82 +401,52 @@ template <int D>
 __global__ void __launch_bounds__(HEAD_THREADS) imade_bwd_kernel(const __grid_constant__ HeadArgs a, const float* __restrict__ Ybar,
                                                                  const float* __restrict__ LDbar, float* __restrict__ Obar,
                                                                  float* __restrict__ Ubar) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= a.N * D) return;
-  const int64_t n = i / D;
-  const int d = (int)(i % D);
-  const int DP = D * a.P;
-  const ImadeFwd<D> f = imade_norms<D>(a, n, d);
-  const Jet<D> u = jload<D>(a.U, n, D, d);
-  const NodeIdx ni = node_index(u.v, a.T);
-  const float np_ = (float)(a.T - 1);
+  const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= a.N * D) return;
+  const int64_t n = w / D;
+  const int d = (int)(w % D);
+  ImadeLane<D> L;
+  imade_lane_fwd<D>(a, n, d, lane, L);
   const Jet<D> ybar = jload<D>(Ybar, n, D, D - 1 - d);
   const Jet<D> lbar = jload<D>(LDbar, n, 1, 0);
-  // dy is needed for the adjoint of log(dy + 1e-7)
-  Jet<D> dy = jzero<D>();
-#pragma unroll 1
-  for (int p = 0; p < a.P; ++p) {
-    if (a.wq[p] == 0.f) continue;
-    const Jet<D> c = jmul(imade_b(a, sig_jet(jload<D>(a.O, n, DP, p * D + d)), f.r1, p), f.r2);
-    const Basis4 b = basis4(a.tab, ni, np_, p);
-    jacc(dy, jmul(c, junary(u, b.f[1], b.f[2], b.f[3])));
-  }
-  dy.v += LOG_TOL;
   Jet<D> dybar = jzero<D>();
-  jlog_bwd(dy, lbar, dybar);
-
-  Jet<D> bb[WF_MAX_P];
-  Jet<D> ubar = jzero<D>(), r2bar = jzero<D>();
-#pragma unroll 1
-  for (int p = 0; p < a.P; ++p) {
-    bb[p] = jzero<D>();
-    if (a.wq[p] == 0.f) continue;
-    const Jet<D> bq = imade_b(a, sig_jet(jload<D>(a.O, n, DP, p * D + d)), f.r1, p);
-    const Jet<D> c = jmul(bq, f.r2);
-    const Basis4 b = basis4(a.tab, ni, np_, p);
-    const Jet<D> B0 = junary(u, b.f[0], b.f[1], b.f[2]);
-    const Jet<D> B1 = junary(u, b.f[1], b.f[2], b.f[3]);
-    Jet<D> cbar = jzero<D>(), B0bar = jzero<D>(), B1bar = jzero<D>();
-    jmul_bwd(B0, ybar, cbar);
-    jmul_bwd(B1, dybar, cbar);
-    jmul_bwd(c, ybar, B0bar);
-    jmul_bwd(c, dybar, B1bar);
-    junary_bwd(u, b.f[1], b.f[2], b.f[3], B0bar, ubar);
-    junary_bwd(u, b.f[2], b.f[3], b.f[3], B1bar, ubar);   // table order 4 clamps to 3 (quirk Q5)
-    jmul_bwd(f.r2, cbar, bb[p]);
-    jmul_bwd(bq, cbar, r2bar);
-  }
+  jlog_bwd(L.dy, lbar, dybar);
+  Jet<D> cbar = jzero<D>(), B0bar = jzero<D>(), B1bar = jzero<D>(), ub = jzero<D>();
+  jmul_bwd(L.B0, ybar, cbar);
+  jmul_bwd(L.B1, dybar, cbar);
+  jmul_bwd(L.c, ybar, B0bar);
+  jmul_bwd(L.c, dybar, B1bar);
+  junary_bwd(L.u, L.f.f[1], L.f.f[2], L.f.f[3], B0bar, ub);
+  junary_bwd(L.u, L.f.f[2], L.f.f[3], L.f.f[3], B1bar, ub);   // table order 4 clamps to 3 (quirk Q5)
+  const Jet<D> ubar = warp_sum(ub);
+  Jet<D> bbar = jzero<D>(), r2b = jzero<D>();
+  jmul_bwd(L.r2, cbar, bbar);
+  jmul_bwd(L.b, cbar, r2b);
+  const Jet<D> r2bar = warp_sum(r2b);
   Jet<D> S2bar = jzero<D>();
-  jrecip_bwd(f.S2, r2bar, S2bar);
-  Jet<D> r1bar = jzero<D>();
-#pragma unroll 1
-  for (int p = 0; p < a.P; ++p) {
-    if (a.wq[p] == 0.f) continue;
-    const Jet<D> s = sig_jet(jload<D>(a.O, n, DP, p * D + d));
-    Jet<D> bbar = bb[p];
+  jrecip_bwd(L.S2, r2bar, S2bar);
+  Jet<D> sbar = jzero<D>(), r1b = jzero<D>();
+  if (L.wq != 0.f) {
     jacc(bbar, S2bar);
-    const Jet<D> abar = jscale(bbar, a.wq[p]);
-    Jet<D> sbar = jzero<D>();
-    jmul_bwd(f.r1, abar, sbar);
-    jmul_bwd(s, abar, r1bar);
-    bb[p] = sbar;
+    const Jet<D> abar = jscale(bbar, L.wq);
+    jmul_bwd(L.r1, abar, sbar);
+    jmul_bwd(L.s, abar, r1b);
   }
+  const Jet<D> r1bar = warp_sum(r1b);
   Jet<D> S1bar = jzero<D>();
-  jrecip_bwd(f.S1, r1bar, S1bar);
-#pragma unroll 1
-  for (int p = 0; p < a.P; ++p) {
-    const Jet<D> o = jload<D>(a.O, n, DP, p * D + d);
-    Jet<D> sbar = bb[p];
+  jrecip_bwd(L.S1, r1bar, S1bar);
+  if (L.act) {
     jacc(sbar, S1bar);
-    const Sig g = sigmoid_derivs(o.v);
+    const Sig g = sigmoid_derivs(L.o.v);
     Jet<D> obar = jzero<D>();
-    junary_bwd(o, g.d1, g.d2, g.d3, sbar, obar);
-    jstore<D>(Obar, n, DP, p * D + d, obar);
+    junary_bwd(L.o, g.d1, g.d2, g.d3, sbar, obar);
+    jstore<D>(Obar, n, D * a.P, lane * D + d, obar);
   }
-  jstore<D>(Ubar, n, D, d, ubar);
+  if (lane == 0) jstore<D>(Ubar, n, D, d, ubar);
 }
 
-// ---------------------------------------------------------------------------------------------- prior head (wavefunctions.py:54-71)
+// ---- prior head (wavefunctions.py:54-71)
 struct PriorArgs {
   const float* O;        // [R][D*P]
   const float* U;        // [R][D]
@@ -412,121 +457,112 @@ struct PriorArgs {
   int cons_lo, cons_hi;  // dimensions [cons_lo, cons_hi) carry the 1/sqrt(2) (model_factory.py:124-129)
   float mb[WF_MAX_P];    // 0 at the constrained end coefficients (bsplines_jax.py:173-198 with {0: 0} | {0: 0})
 };
+constexpr int MS_LD = 33;   // ob_to_b in shared memory, row stride 33: conflict-free by row and by column
 
 template <int D>
-__device__ __forceinline__ void prior_coeffs(const PriorArgs& a, int64_t n, int d, Jet<D>* cpre, Jet<D>& S, Jet<D>& nrm) {
+struct PriorLane {
+  Jet<D> cpre, S, nrm, c, uc, B0, phi;
+  Basis4 f;
+  float sign, scale, uraw;
+  bool inside;
+};
+
+template <int D>
+__device__ __forceinline__ void prior_lane_fwd(const PriorArgs& a, const float* Ms, int64_t n, int d, int lane, PriorLane<D>& L) {
   const int P = a.P, DP = D * P;
+  // The conditioner divides by sum_p o_p even when negative outputs are allowed (model_factory.py:69-70); the L2
+  // normalisations that follow cancel its magnitude and keep its sign.
+  float sv = lane < P ? a.O[n * (D + 2) * (int64_t)DP + lane * D + d] : 0.f;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sv += __shfl_xor_sync(0xffffffffu, sv, o);
+  L.sign = sv < 0.f ? -1.f : 1.f;
+  // c' = (mask o) @ ob_to_b: lane q accumulates column q
+  L.cpre = jzero<D>();
 #pragma unroll 1
-  for (int q = 0; q < P; ++q) cpre[q] = jzero<D>();
-#pragma unroll 1
-  for (int p = 0; p < P; ++p) {
-    if (a.mb[p] == 0.f) continue;
-    const Jet<D> o = jscale(jload<D>(a.O, n, DP, p * D + d), a.mb[p]);
-    const float* row = a.ob_to_b + p * P;
-#pragma unroll 1
-    for (int q = 0; q < P; ++q) jaxpy(cpre[q], __ldg(row + q), o);
+  for (int p = 1; p < P - 1; ++p) jaxpy(L.cpre, Ms[p * MS_LD + lane], jload<D>(a.O, n, DP, p * D + d));
+  if (lane >= P) L.cpre = jzero<D>();
+  L.S = warp_sum(jmul(L.cpre, L.cpre));
+  L.nrm = jrsqrt(L.S);
+  L.c = jmul(L.cpre, L.nrm);
+  const Jet<D> u = jload<D>(a.U, n, D, d);
+  L.uraw = u.v;
+  L.inside = (u.v > 0.f) && (u.v < 1.f);
+  L.uc = L.inside ? u : jzero<D>();
+  L.uc.v = fminf(fmaxf(u.v, 0.f), 1.f);
+  const NodeIdx ni = node_index(L.uc.v, a.T);
+  L.f = basis4(a.tab, ni, (float)(a.T - 1), lane);
+  L.B0 = junary(L.uc, L.f.f[0], L.f.f[1], L.f.f[2]);
+  L.scale = L.sign * ((d >= a.cons_lo && d < a.cons_hi) ? 0.70710678118654752f : 1.f);
+  L.phi = jscale(warp_sum(jmul(L.c, L.B0)), L.scale);
+}
+
+__device__ __forceinline__ void load_ob_to_b(const PriorArgs& a, float* Ms) {
+  for (int i = threadIdx.x; i < WF_MAX_P * MS_LD; i += blockDim.x) {
+    const int p = i / MS_LD, q = i % MS_LD;
+    Ms[i] = (p < a.P && q < a.P) ? a.ob_to_b[p * a.P + q] : 0.f;
   }
-  S = jzero<D>();
-#pragma unroll 1
-  for (int q = 0; q < P; ++q) jacc(S, jmul(cpre[q], cpre[q]));
-  nrm = jrsqrt(S);
-}
-// The conditioner divides by sum_p o_p even when negative outputs are allowed (model_factory.py:69-70); the L2
-// normalisations that follow cancel its magnitude and keep its sign.
-template <int D>
-__device__ __forceinline__ float prior_sign(const PriorArgs& a, int64_t n, int d) {
-  const float* p = a.O + n * (D + 2) * (int64_t)(D * a.P) + d;
-  float s = 0.f;
-#pragma unroll 1
-  for (int q = 0; q < a.P; ++q) s += p[q * D];
-  return s < 0.f ? -1.f : 1.f;
-}
-template <int D>
-__device__ __forceinline__ Jet<D> clip01(const Jet<D>& u, bool& inside) {
-  inside = (u.v > 0.f) && (u.v < 1.f);
-  Jet<D> c = inside ? u : jzero<D>();
-  c.v = fminf(fmaxf(u.v, 0.f), 1.f);
-  return c;
+  __syncthreads();
 }
 
 template <int D>
 __global__ void __launch_bounds__(HEAD_THREADS) prior_fwd_kernel(const __grid_constant__ PriorArgs a, float* __restrict__ PHI) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= a.N * D) return;
-  const int64_t n = i / D;
-  const int d = (int)(i % D);
-  Jet<D> cpre[WF_MAX_P], S, nrm;
-  prior_coeffs<D>(a, n, d, cpre, S, nrm);
-  bool inside;
-  const Jet<D> uc = clip01(jload<D>(a.U, n, D, d), inside);
-  const NodeIdx ni = node_index(uc.v, a.T);
-  const float np_ = (float)(a.T - 1);
-  Jet<D> phi = jzero<D>();
-#pragma unroll 1
-  for (int q = 0; q < a.P; ++q) {
-    const Basis4 b = basis4(a.tab, ni, np_, q);
-    jacc(phi, jmul(jmul(cpre[q], nrm), junary(uc, b.f[0], b.f[1], b.f[2])));
-  }
-  phi = jscale(phi, prior_sign<D>(a, n, d));
-  if (d >= a.cons_lo && d < a.cons_hi) phi = jscale(phi, 0.70710678118654752f);
-  jstore<D>(PHI, n, D, d, phi);
+  __shared__ float Ms[WF_MAX_P * MS_LD];
+  load_ob_to_b(a, Ms);
+  const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= a.N * D) return;
+  const int64_t n = w / D;
+  const int d = (int)(w % D);
+  PriorLane<D> L;
+  prior_lane_fwd<D>(a, Ms, n, d, lane, L);
+  if (lane == 0) jstore<D>(PHI, n, D, d, L.phi);
 }
 
 template <int D>
 __global__ void __launch_bounds__(HEAD_THREADS) prior_bwd_kernel(const __grid_constant__ PriorArgs a, const float* __restrict__ PHIbar,
                                                                  float* __restrict__ Obar, float* __restrict__ Ubar) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= a.N * D) return;
-  const int64_t n = i / D;
-  const int d = (int)(i % D);
-  const int P = a.P, DP = D * P;
-  Jet<D> cpre[WF_MAX_P], cb[WF_MAX_P], S, nrm;
-  prior_coeffs<D>(a, n, d, cpre, S, nrm);
-  bool inside;
-  const Jet<D> uc = clip01(jload<D>(a.U, n, D, d), inside);
-  const NodeIdx ni = node_index(uc.v, a.T);
-  const float np_ = (float)(a.T - 1);
-  Jet<D> phibar = jscale(jload<D>(PHIbar, n, D, d), prior_sign<D>(a, n, d));
-  if (d >= a.cons_lo && d < a.cons_hi) phibar = jscale(phibar, 0.70710678118654752f);
-  Jet<D> nbar = jzero<D>(), ucbar = jzero<D>();
-#pragma unroll 1
-  for (int q = 0; q < P; ++q) {
-    const Jet<D> c = jmul(cpre[q], nrm);
-    const Basis4 b = basis4(a.tab, ni, np_, q);
-    const Jet<D> B0 = junary(uc, b.f[0], b.f[1], b.f[2]);
-    Jet<D> cbar = jzero<D>(), B0bar = jzero<D>();
-    jmul_bwd(B0, phibar, cbar);
-    jmul_bwd(c, phibar, B0bar);
-    junary_bwd(uc, b.f[1], b.f[2], b.f[3], B0bar, ucbar);
-    cb[q] = jzero<D>();
-    jmul_bwd(nrm, cbar, cb[q]);
-    jmul_bwd(cpre[q], cbar, nbar);
-  }
+  __shared__ float Ms[WF_MAX_P * MS_LD];
+  load_ob_to_b(a, Ms);
+  const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= a.N * D) return;
+  const int64_t n = w / D;
+  const int d = (int)(w % D);
+  const int P = a.P;
+  PriorLane<D> L;
+  prior_lane_fwd<D>(a, Ms, n, d, lane, L);
+  const Jet<D> phibar = jscale(jload<D>(PHIbar, n, D, d), L.scale);
+  Jet<D> cbar = jzero<D>(), B0bar = jzero<D>(), ub = jzero<D>();
+  jmul_bwd(L.B0, phibar, cbar);
+  jmul_bwd(L.c, phibar, B0bar);
+  junary_bwd(L.uc, L.f.f[1], L.f.f[2], L.f.f[3], B0bar, ub);
+  Jet<D> ucbar = warp_sum(ub);
+  Jet<D> cb = jzero<D>(), nb = jzero<D>();
+  jmul_bwd(L.nrm, cbar, cb);
+  jmul_bwd(L.cpre, cbar, nb);
+  const Jet<D> nbar = warp_sum(nb);
   Jet<D> Sbar = jzero<D>();
-  jrsqrt_bwd(S, nbar, Sbar);
+  jrsqrt_bwd(L.S, nbar, Sbar);
+  Jet<D> t = jzero<D>();
+  jmul_bwd(L.cpre, Sbar, t);            // d(c*c) = 2 * (one-sided adjoint)
+  jaxpy(cb, 2.f, t);
+  if (lane >= P) cb = jzero<D>();
+  // o_bar_p = mask_p * sum_q ob_to_b[p][q] cb_q : lane p gathers the cb of every lane q
+  Jet<D> ob = jzero<D>();
 #pragma unroll 1
-  for (int q = 0; q < P; ++q) {
-    Jet<D> t = jzero<D>();
-    jmul_bwd(cpre[q], Sbar, t);          // d(c*c) = 2 * (one-sided adjoint)
-    jaxpy(cb[q], 2.f, t);
+  for (int q = 0; q < P; ++q) jaxpy(ob, Ms[lane * MS_LD + q], warp_bcast(cb, q));
+  if (lane < P) {
+    if (a.mb[lane] == 0.f) ob = jzero<D>();
+    jstore<D>(Obar, n, D * P, lane * D + d, ob);
   }
-#pragma unroll 1
-  for (int p = 0; p < P; ++p) {
-    Jet<D> ob = jzero<D>();
-    if (a.mb[p] != 0.f) {
-      const float* row = a.ob_to_b + p * P;
-#pragma unroll 1
-      for (int q = 0; q < P; ++q) jaxpy(ob, __ldg(row + q), cb[q]);
-      ob = jscale(ob, a.mb[p]);
+  if (lane == 0) {
+    if (!L.inside) {
+      const float keep = (L.uraw == L.uc.v) ? ucbar.v : 0.f;   // clip passes the gradient only where it did not clamp
+      ucbar = jzero<D>();
+      ucbar.v = keep;
     }
-    jstore<D>(Obar, n, DP, p * D + d, ob);
+    jstore<D>(Ubar, n, D, d, ucbar);
   }
-  if (!inside) {
-    const float keep = (uc.v >= 0.f && uc.v <= 1.f && jload<D>(a.U, n, D, d).v == uc.v) ? ucbar.v : 0.f;
-    ucbar = jzero<D>();
-    ucbar.v = keep;
-  }
-  jstore<D>(Ubar, n, D, d, ucbar);
 }
 
 // ---------------------------------------------------------------------------------------------- psi, H psi, E_loc and the adjoint seeds
@@ -677,36 +713,49 @@ int64_t per_row_floats(const wf_live_model* m) {
   return (int64_t)(nn + 1) * D + (int64_t)nn * (4 * HID + DPm) + 1 + (int64_t)m->n_layers * D + 2 * D + 1 + DPm + 2 * HID + 2 * D;
 }
 
-int smem_linear(int Kc, int Nc) { return (Kc * ((Nc + 15) & ~15) + LIN_BM * Kc) * (int)sizeof(float); }
-int smem_wgrad(int Kc, int Nc) { return (LIN_BM * (Kc + 1) + LIN_BM * ((Nc + 15) & ~15)) * (int)sizeof(float); }
+int smem_linear(int Kc, int BN) { const int KcP = (Kc + 3) & ~3; return (KcP * BN + GM * (KcP + 4)) * (int)sizeof(float); }
+int smem_wgrad(int Kc, int BN) { const int KcP = (Kc + 3) & ~3; return (WG_ROWS * (KcP + 4) + WG_ROWS * BN + WG_ROWS) * (int)sizeof(float); }
 
-template <bool T, bool A>
-int launch_linear(const float* Ain, const float* B, const float* bias, float* C, int64_t R, int Kc, int Nc, int G, cudaStream_t s) {
+template <int BN, bool T, bool A>
+int launch_linear_bn(const float* Ain, const float* B, const float* bias, float* C, int64_t R, int Kc, int Nc, int G, cudaStream_t s) {
   static bool attr = false;
   if (!attr) {
-    WF_CUDA(cudaFuncSetAttribute(linear_kernel<T, A>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    WF_CUDA(cudaFuncSetAttribute(linear_kernel<BN, T, A>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     attr = true;
   }
-  const int64_t tiles = (R + LIN_BM - 1) / LIN_BM;
+  const int64_t tiles = (R + GM - 1) / GM;
   const int grid = (int)(tiles < 2 * num_sms() ? tiles : 2 * num_sms());
-  linear_kernel<T, A><<<grid, LIN_THREADS, smem_linear(Kc, Nc), s>>>(Ain, B, bias, C, R, Kc, Nc, G);
+  linear_kernel<BN, T, A><<<grid, LIN_THREADS, smem_linear(Kc, BN), s>>>(Ain, B, bias, C, R, Kc, Nc, G);
+  WF_LAUNCH_CHECK();
+  return WF_OK;
+}
+template <bool T, bool A>
+int launch_linear(const float* Ain, const float* B, const float* bias, float* C, int64_t R, int Kc, int Nc, int G, cudaStream_t s) {
+  return Nc <= 64 ? launch_linear_bn<64, T, A>(Ain, B, bias, C, R, Kc, Nc, G, s)
+                  : launch_linear_bn<128, T, A>(Ain, B, bias, C, R, Kc, Nc, G, s);
+}
+
+template <int BN>
+int launch_wgrad_bn(const float* X, const float* dY, float* partial, int grid, int64_t R, int Kc, int Nc, int G, cudaStream_t s) {
+  static bool attr = false;
+  if (!attr) {
+    WF_CUDA(cudaFuncSetAttribute(wgrad_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    attr = true;
+  }
+  wgrad_kernel<BN><<<grid, LIN_THREADS, smem_wgrad(Kc, BN), s>>>(X, dY, partial, R, Kc, Nc, G);
   WF_LAUNCH_CHECK();
   return WF_OK;
 }
 
 int launch_wgrad(const float* X, const float* dY, float* partial, float* gW, float* gb, int layer, int D, int64_t R, int Kc, int Nc,
                  int G, cudaStream_t s) {
-  static bool attr = false;
-  if (!attr) {
-    WF_CUDA(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    attr = true;
-  }
-  const int64_t tiles = (R + LIN_BM - 1) / LIN_BM;
+  const int64_t tiles = (R + WG_ROWS - 1) / WG_ROWS;
   const int grid = (int)(tiles < WGRAD_CTAS ? tiles : WGRAD_CTAS);
-  wgrad_kernel<<<grid, LIN_THREADS, smem_wgrad(Kc, Nc), s>>>(X, dY, partial, R, Kc, Nc, G);
-  WF_LAUNCH_CHECK();
+  const int st = Nc <= 64 ? launch_wgrad_bn<64>(X, dY, partial, grid, R, Kc, Nc, G, s)
+                          : launch_wgrad_bn<128>(X, dY, partial, grid, R, Kc, Nc, G, s);
+  if (st != WF_OK) return st;
   const int tot = (Kc + 1) * Nc;
-  wgrad_reduce_kernel<<<(tot + 127) / 128, 128, 0, s>>>(partial, grid, gW, gb, layer, D, Kc, Nc);
+  wgrad_reduce_kernel<<<(tot + 31) / 32, 256, 0, s>>>(partial, grid, gW, gb, layer, D, Kc, Nc);
   WF_LAUNCH_CHECK();
   return WF_OK;
 }
@@ -734,7 +783,7 @@ int run_chunk(const wf_live_model* m, const wf_live_tables* t, const float* para
   float* Wm = ws;
   float* partial = Wm + fx.wm;
   float* p = partial + fx.partial;
-  auto take = [&](int64_t n) { float* q = p; p += n; return q; };
+  auto take = [&](int64_t n) { float* q = p; p += (n + 3) & ~(int64_t)3; return q; };   // keeps every array 16-byte aligned
   float* U[WF_MAX_LAYERS + 2];
   for (int i = 0; i <= nn; ++i) U[i] = take(R * D);
   float *Z1[WF_MAX_LAYERS + 1], *H1[WF_MAX_LAYERS + 1], *Z2[WF_MAX_LAYERS + 1], *H2[WF_MAX_LAYERS + 1], *O[WF_MAX_LAYERS + 1];
@@ -780,7 +829,7 @@ int run_chunk(const wf_live_model* m, const wf_live_tables* t, const float* para
 
   const int eb = 256;
   const int64_t nh = N * HID, nd = N * D;
-  const int hb = (int)((nd + HEAD_THREADS - 1) / HEAD_THREADS);
+  const int hb = (int)((nd * 32 + HEAD_THREADS - 1) / HEAD_THREADS);   // one warp per (walker, dimension)
 
   // ---------------- forward
   box_kernel<D><<<(int)((N + 127) / 128), 128, 0, s>>>(x, N, m->box, m->coord_mean, U[0], LDbox);
@@ -851,7 +900,7 @@ extern "C" int64_t wf_vqmc_param_floats(const wf_live_model* m) {
 
 extern "C" int64_t wf_vqmc_grad_workspace_floats(const wf_live_model* m, int64_t walkers) {
   if (check_model(m) != WF_OK || walkers < 0) return -1;
-  return fixed_floats(m).total + walkers * (m->D + 2) * per_row_floats(m) + 64;
+  return fixed_floats(m).total + walkers * (m->D + 2) * per_row_floats(m) + 512;
 }
 
 extern "C" int wf_vqmc_loss_grad(const wf_live_model* m, const wf_live_tables* t, const float* params, const float* protons_host,
@@ -862,8 +911,9 @@ extern "C" int wf_vqmc_loss_grad(const wf_live_model* m, const wf_live_tables* t
   if (st != WF_OK) return st;
   if (N == 0) return WF_OK;
   if (!t || !t->dense_I || !t->dense_P || !t->ob_to_b || !params || !x || !workspace || N < 0) return WF_ERR_INVALID_ARG;
+  if (reinterpret_cast<uintptr_t>(workspace) & 15) return WF_ERR_INVALID_ARG;
   if (n_protons < 0 || n_protons > WF_MAX_D || (n_protons > 0 && !protons_host)) return WF_ERR_INVALID_ARG;
-  const int64_t avail = workspace_floats - fixed_floats(m).total - 64;
+  const int64_t avail = workspace_floats - fixed_floats(m).total - 512;
   const int64_t per_walker = (m->D + 2) * per_row_floats(m);
   int64_t chunk = avail / per_walker;
   if (chunk < 1) return WF_ERR_INVALID_ARG;
