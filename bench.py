@@ -361,18 +361,18 @@ def run_b200(args):
         del uw, uh, ud, xs
         coupling = {}
         crng = np.random.Generator(np.random.PCG64(0))
-        for D in (2, 8):
+        for Dc in (2, 8):
             hidden, L = 8, 8
-            out_dim = (3 * K - 1) * D // 2
+            out_dim = (3 * K - 1) * Dc // 2
             layers = []
             for _ in range(L):
                 pair = []
                 for _f in range(2):
                     gW = lambda a, b: torch.from_numpy((crng.standard_normal((a, b)) / np.sqrt(a)).astype(np.float32)).to(dev)
                     z = lambda n: torch.zeros(n, device=dev)
-                    pair.append([(gW(D // 2, hidden), z(hidden)), (), (gW(hidden, hidden), z(hidden)), (), (gW(hidden, out_dim), z(out_dim))])
+                    pair.append([(gW(Dc // 2, hidden), z(hidden)), (), (gW(hidden, hidden), z(hidden)), (), (gW(hidden, out_dim), z(out_dim))])
                 layers.append(tuple(pair))
-            x = torch.rand(M, D, device=dev, generator=g) * 6 - 3
+            x = torch.rand(M, Dc, device=dev, generator=g) * 6 - 3
             r = {}
             for inv in (False, True):
                 for _ in range(2):
@@ -384,8 +384,8 @@ def run_b200(args):
                     ts.append(a.elapsed_time(b))
                 ms = float(np.mean(ts))
                 r["inverse" if inv else "density"] = {"ms": ms, "samples_per_s": M / (ms * 1e-3),
-                                                      "hbm_frac_of_measured": M * (8 * D + 4) / (ms * 1e-3) / 1e9 / hbm_peak}
-            coupling[f"D{D}"] = {"samples": M, "K": K, "layers": L, "hidden": hidden, **r,
+                                                      "hbm_frac_of_measured": M * (8 * Dc + 4) / (ms * 1e-3) / 1e9 / hbm_peak}
+            coupling[f"D{Dc}"] = {"samples": M, "K": K, "layers": L, "hidden": hidden, **r,
                                  "note": "MUFU/issue bound by construction (SURVEY 8d regime ii): 8D+4 bytes per sample"}
             del x
 
@@ -424,6 +424,51 @@ def run_b200(args):
                                          "FLOPs and TF32 runs at half the bf16 rate, so frac <= 1/6 by construction"}}
         del x5, y5, ld5, w5
 
+    # ---------------- the training step (value_and_grad(loss_fn_efficient) + Adam) on the same workload
+    train = None
+    if not args.no_sweep:
+        from waveflow_b200 import _train
+        opt_init, opt_update, get_params = _train.adam(1e-4, device=dev)
+        opt_state = opt_init(params)
+        tparams = get_params(opt_state)
+
+        def tstep(i):
+            return vqmc.train_step_efficient(i, psi, h_fn, opt_update, opt_state, tparams, x_dev, 0.0)
+        for i in range(3):
+            tstep(i)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        kt = 10
+        a.record()
+        for i in range(kt):
+            _, tl = tstep(3 + i)
+        b.record(); torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / kt
+        if world > 1:
+            tms = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+            ms = float(tms.item())
+        tfl = 3.0 * flops_per_walker(D) * n_local / (ms * 1e-3) / 1e12          # forward + ~2x for the reverse pass
+        train = {"api": "vqmc.train_step_efficient(epoch, psi, h_fn, opt_update, opt_state, params, batch, running_average)",
+                 "kernels": "wf_vqmc_loss_grad (layer-wise jets: linear / tanh / spline-head kernels, forward + reverse) + wf_adam_step",
+                 "walkers_total": wl["n_walkers"], "walkers_per_gpu": n_local, "ms_per_step": ms,
+                 "walkers_per_s": wl["n_walkers"] / (ms * 1e-3), "loss": float(tl),
+                 "exchange": "none" if world == 1 else f"all-reduce of the flat gradient ({opt_state.flat.numel()} floats) + 32-byte loss sums per step",
+                 "algorithmic_tflops_per_gpu": tfl, "frac_of_measured_fp32_fma": tfl / fp32_peak,
+                 "gpu_launches_per_step": 4 * (85 + 1) if n_local > 16384 else 86}
+        if world == 1 and not args.no_cpu_baseline:
+            from oracle import fixtures as fx
+            from oracle import grad as ograd
+            ns = 64
+            m32 = fx.waveflow_model(D, degree=wl["degree"], n_knots=wl["knots"], n_layers=wl["layers"], box=wl["box"], reg=wl["reg"])
+            p32 = fx.cast_params(params, np.float32)
+            t0 = time.perf_counter()
+            ograd.loss_and_grad(m32, p32, wl["walkers"][:ns], wl["protons"], 0.0, dtype=np.float32)
+            sec = time.perf_counter() - t0
+            train["cpu_baseline"] = {"value": ns / sec, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                                     "sample": f"first {ns} walkers, one pass", "seconds_per_pass": sec,
+                                     "note": "torch-CPU float32 autograd restatement (three reverse passes, oracle/grad.py); Adam not included"}
+
     # ---------------- CPU baseline (rank 0, N = 1): bounded sample of the same workload
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
@@ -448,7 +493,7 @@ def run_b200(args):
                     "ms_per_step": e2e_s / steps * 1e3},
             "gpu_launches": steps,
             "kernel_ms_per_step": kern_ms_mean, "wall_s_timed_region": t_wall,
-            "roofline": roofline, "cpu_baseline": cpu, "spline_sweep": sweep, "rqs_sweep": rqs_sweep, "coupling_flow_sweep": coupling, "tc_coupling_flow_sweep": tc_sweep,
+            "roofline": roofline, "cpu_baseline": cpu, "spline_sweep": sweep, "rqs_sweep": rqs_sweep, "coupling_flow_sweep": coupling, "tc_coupling_flow_sweep": tc_sweep, "train_step": train,
             "energy_estimate": {"mean": float(s[0] / s[2]), "n": int(s[2])}}
     print(json.dumps(line), flush=True)
     if world > 1:

@@ -36,60 +36,71 @@ __global__ void mask_weights_kernel(const float* __restrict__ W, float* __restri
 }
 
 // ---------------------------------------------------------------------------------------------- linear layers
+// Both GEMM kernels split the CTA into independent thread groups ("slices", 8 x BN/8 threads, one 8 x 8 register block per
+// thread) that stage their own row chunks in private shared memory and synchronise with named barriers only, so the
+// slices of a CTA drift out of phase and one slice's global loads overlap another's FMAs.
+__device__ __forceinline__ void slice_sync(int slice, int threads) {
+  // immediate barrier ids (a register id would make ptxas reserve all 16 barriers)
+  if (slice == 0) asm volatile("bar.sync 1, %0;" ::"r"(threads) : "memory");
+  else if (slice == 1) asm volatile("bar.sync 2, %0;" ::"r"(threads) : "memory");
+  else if (slice == 2) asm volatile("bar.sync 3, %0;" ::"r"(threads) : "memory");
+  else asm volatile("bar.sync 4, %0;" ::"r"(threads) : "memory");
+}
+
 // C[R][Nc] (+)= A[R][Kc] * B (+ bias on the value rows r % G == 0).  TRANS_B == false: B [Kc][Nc]; true: B given as [Nc][Kc].
-// CTA tile GM rows x BN (padded) columns, the whole K extent resident in shared memory; thread tile RM x 8 with 128-bit
-// shared loads (A row-major with k contiguous, B k-major).
-constexpr int GM = 128;
+// The whole K extent is resident in shared memory: B once per CTA (k-major), A per 64-row chunk (row-major, k contiguous).
+constexpr int LROWS = 64;   // rows per slice chunk
 template <int BN, bool TRANS_B, bool ACCUM>
 __global__ void __launch_bounds__(LIN_THREADS) linear_kernel(const float* __restrict__ A, const float* __restrict__ B,
                                                              const float* __restrict__ bias, float* __restrict__ C,
                                                              int64_t R, int Kc, int Nc, int G) {
   extern __shared__ __align__(16) float sm[];
-  constexpr int TX = BN / 8, TY = LIN_THREADS / TX, RM = GM / TY;
+  constexpr int TX = BN / 8, TS = 8 * TX, SL = LIN_THREADS / TS;
   const int KcP = (Kc + 3) & ~3, LDA = KcP + 4;
-  float* Bs = sm;                         // [KcP][BN]
-  float* As = sm + KcP * BN;              // [GM][LDA]
-  const int tid = threadIdx.x, tx = tid % TX, ty = tid / TX;
+  float* Bs = sm;                                         // [KcP][BN]
+  const int tid = threadIdx.x, slice = tid / TS, ts = tid % TS, tx = ts % TX, ty = ts / TX;
+  float* As = sm + KcP * BN + slice * LROWS * LDA;        // [LROWS][LDA], private to the slice
   for (int i = tid; i < KcP * BN; i += LIN_THREADS) {
     const int k = i / BN, n = i % BN;
     Bs[i] = (k < Kc && n < Nc) ? (TRANS_B ? B[(int64_t)n * Kc + k] : B[(int64_t)k * Nc + n]) : 0.f;
   }
-  const int64_t tiles = (R + GM - 1) / GM;
-  for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-    const int64_t r0 = tile * GM;
-    const int rows = (int)min((int64_t)GM, R - r0);
-    __syncthreads();
+  __syncthreads();
+  const int64_t chunks = (R + LROWS - 1) / LROWS;
+  for (int64_t ch = (int64_t)blockIdx.x * SL + slice; ch < chunks; ch += (int64_t)gridDim.x * SL) {
+    const int64_t r0 = ch * LROWS;
+    const int rows = (int)min((int64_t)LROWS, R - r0);
+    slice_sync(slice, TS);
     if ((Kc & 3) == 0) {
       const int k4n = Kc >> 2;
-      for (int i = tid; i < GM * k4n; i += LIN_THREADS) {
+      for (int i = ts; i < LROWS * k4n; i += TS) {
         const int row = i / k4n, k4 = i % k4n;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (row < rows) v = *reinterpret_cast<const float4*>(A + (r0 + row) * Kc + 4 * k4);
         *reinterpret_cast<float4*>(As + row * LDA + 4 * k4) = v;
       }
     } else {
-      for (int i = tid; i < GM * KcP; i += LIN_THREADS) {
+      for (int i = ts; i < LROWS * KcP; i += TS) {
         const int row = i / KcP, k = i % KcP;
         As[row * LDA + k] = (row < rows && k < Kc) ? A[(r0 + row) * Kc + k] : 0.f;
       }
     }
-    __syncthreads();
-    float acc[RM][8];
+    slice_sync(slice, TS);
+    float acc[8][8];
 #pragma unroll
-    for (int i = 0; i < RM; ++i)
+    for (int i = 0; i < 8; ++i)
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
 #pragma unroll 2
     for (int k = 0; k < KcP; k += 4) {
-      float4 a[RM];
+      float4 a[8];
 #pragma unroll
-      for (int i = 0; i < RM; ++i) a[i] = *reinterpret_cast<const float4*>(As + (ty * RM + i) * LDA + k);
+      for (int i = 0; i < 8; ++i) a[i] = *reinterpret_cast<const float4*>(As + (ty * 8 + i) * LDA + k);
 #pragma unroll
       for (int kk = 0; kk < 4; ++kk) {
         const float4 b0 = *reinterpret_cast<const float4*>(Bs + (k + kk) * BN + tx * 4);
         const float4 b1 = *reinterpret_cast<const float4*>(Bs + (k + kk) * BN + BN / 2 + tx * 4);
 #pragma unroll
-        for (int i = 0; i < RM; ++i) {
+        for (int i = 0; i < 8; ++i) {
           const float av = kk == 0 ? a[i].x : (kk == 1 ? a[i].y : (kk == 2 ? a[i].z : a[i].w));
           acc[i][0] = fmaf(av, b0.x, acc[i][0]); acc[i][1] = fmaf(av, b0.y, acc[i][1]);
           acc[i][2] = fmaf(av, b0.z, acc[i][2]); acc[i][3] = fmaf(av, b0.w, acc[i][3]);
@@ -99,8 +110,8 @@ __global__ void __launch_bounds__(LIN_THREADS) linear_kernel(const float* __rest
       }
     }
 #pragma unroll
-    for (int i = 0; i < RM; ++i) {
-      const int rl = ty * RM + i;
+    for (int i = 0; i < 8; ++i) {
+      const int rl = ty * 8 + i;
       if (rl >= rows) continue;
       const int64_t r = r0 + rl;
       const bool value_row = bias && (r % G) == 0;
@@ -123,76 +134,114 @@ __global__ void __launch_bounds__(LIN_THREADS) linear_kernel(const float* __rest
 }
 
 // partial[cta][Kc + 1][Nc] = sum over the CTA's rows of X[r][k] * dY[r][n]; row Kc = sum over the value rows (bias gradient).
-// Thread tile 4 (k) x BN/16 (n), 64-row tiles, 128-bit shared loads.
-constexpr int WG_ROWS = 64;
+// Each slice accumulates an 8 (k) x 8 (n) block per thread over its own 16-row chunks; the slices are summed through
+// shared memory in a fixed order at the end.
+constexpr int WROWS = 16;
 template <int BN>
 __global__ void __launch_bounds__(LIN_THREADS) wgrad_kernel(const float* __restrict__ X, const float* __restrict__ dY,
                                                             float* __restrict__ partial, int64_t R, int Kc, int Nc, int G) {
   extern __shared__ __align__(16) float sm[];
-  constexpr int NB = BN / 16;
-  const int KcP = (Kc + 3) & ~3, LDX = KcP + 4;
-  float* Xs = sm;                          // [WG_ROWS][LDX]
-  float* Ys = Xs + WG_ROWS * LDX;          // [WG_ROWS][BN]
-  float* Ind = Ys + WG_ROWS * BN;          // [WG_ROWS]
-  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-  const bool kact = ty * 4 < KcP;
-  float acc[4][NB], accb[NB];
+  constexpr int TXN = BN / 8, TS = 8 * TXN, SL = LIN_THREADS / TS;
+  constexpr int LDX = HID + 4;
+  constexpr int SLICE_FLOATS = WROWS * LDX + WROWS * BN + WROWS;
+  const int tid = threadIdx.x, slice = tid / TS, ts = tid % TS, tx = ts % TXN, ty = ts / TXN;
+  float* Xs = sm + slice * SLICE_FLOATS;         // [WROWS][LDX]   (k zero-padded to 64)
+  float* Ys = Xs + WROWS * LDX;                  // [WROWS][BN]
+  float* Ind = Ys + WROWS * BN;                  // [WROWS]
+  float* Acc = sm + SL * SLICE_FLOATS;           // [HID + 1][BN]
+  const bool kact = ty * 4 < Kc;
+  float acc[8][8], accb[8];
 #pragma unroll
-  for (int j = 0; j < NB; ++j) {
+  for (int j = 0; j < 8; ++j) {
     accb[j] = 0.f;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) acc[i][j] = 0.f;
+    for (int i = 0; i < 8; ++i) acc[i][j] = 0.f;
   }
-  const int64_t tiles = (R + WG_ROWS - 1) / WG_ROWS;
-  for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-    const int64_t r0 = tile * WG_ROWS;
-    const int rows = (int)min((int64_t)WG_ROWS, R - r0);
-    __syncthreads();
-    for (int i = tid; i < WG_ROWS * KcP; i += LIN_THREADS) {
-      const int rl = i / KcP, k = i % KcP;
-      Xs[rl * LDX + k] = (rl < rows && k < Kc) ? X[(r0 + rl) * Kc + k] : 0.f;
+  const bool xvec = Kc == HID, yvec = (Nc & 3) == 0;
+  const int64_t chunks = (R + WROWS - 1) / WROWS;
+  for (int64_t ch = (int64_t)blockIdx.x * SL + slice; ch < chunks; ch += (int64_t)gridDim.x * SL) {
+    const int64_t r0 = ch * WROWS;
+    const int rows = (int)min((int64_t)WROWS, R - r0);
+    slice_sync(slice, TS);
+    if (xvec) {
+      for (int i = ts; i < WROWS * (HID / 4); i += TS) {
+        const int rl = i / (HID / 4), k4 = i % (HID / 4);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (rl < rows) v = *reinterpret_cast<const float4*>(X + (r0 + rl) * HID + 4 * k4);
+        *reinterpret_cast<float4*>(Xs + rl * LDX + 4 * k4) = v;
+      }
+    } else {
+      for (int i = ts; i < WROWS * HID; i += TS) {
+        const int rl = i / HID, k = i % HID;
+        Xs[rl * LDX + k] = (rl < rows && k < Kc) ? X[(r0 + rl) * Kc + k] : 0.f;
+      }
     }
-    for (int i = tid; i < WG_ROWS * BN; i += LIN_THREADS) {
-      const int rl = i / BN, n = i % BN;
-      Ys[i] = (rl < rows && n < Nc) ? dY[(r0 + rl) * Nc + n] : 0.f;
+    if (yvec) {
+      const int n4n = Nc >> 2;
+      for (int i = ts; i < WROWS * (BN / 4); i += TS) {
+        const int rl = i / (BN / 4), n4 = i % (BN / 4);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (rl < rows && n4 < n4n) v = *reinterpret_cast<const float4*>(dY + (r0 + rl) * Nc + 4 * n4);
+        *reinterpret_cast<float4*>(Ys + rl * BN + 4 * n4) = v;
+      }
+    } else {
+      for (int i = ts; i < WROWS * BN; i += TS) {
+        const int rl = i / BN, n = i % BN;
+        Ys[i] = (rl < rows && n < Nc) ? dY[(r0 + rl) * Nc + n] : 0.f;
+      }
     }
-    if (tid < WG_ROWS) Ind[tid] = (tid < rows && ((r0 + tid) % G) == 0) ? 1.f : 0.f;
-    __syncthreads();
+    if (ts < WROWS) Ind[ts] = (ts < rows && ((r0 + ts) % G) == 0) ? 1.f : 0.f;
+    slice_sync(slice, TS);
 #pragma unroll 2
-    for (int r = 0; r < WG_ROWS; ++r) {
-      float y[NB];
-      {
-        const float4 y0 = *reinterpret_cast<const float4*>(Ys + r * BN + tx * 4);
-        y[0] = y0.x; y[1] = y0.y; y[2] = y0.z; y[3] = y0.w;
-        if (NB == 8) {
-          const float4 y1 = *reinterpret_cast<const float4*>(Ys + r * BN + BN / 2 + tx * 4);
-          y[NB - 4] = y1.x; y[NB - 3] = y1.y; y[NB - 2] = y1.z; y[NB - 1] = y1.w;
+    for (int r = 0; r < WROWS; ++r) {
+      const float4 y0 = *reinterpret_cast<const float4*>(Ys + r * BN + tx * 4);
+      const float4 y1 = *reinterpret_cast<const float4*>(Ys + r * BN + BN / 2 + tx * 4);
+      const float y[8] = {y0.x, y0.y, y0.z, y0.w, y1.x, y1.y, y1.z, y1.w};
+      if (ty == 0) {
+        const float ind = Ind[r];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) accb[j] = fmaf(ind, y[j], accb[j]);
+      }
+      if (kact) {
+        const float4 x0 = *reinterpret_cast<const float4*>(Xs + r * LDX + ty * 4);
+        const float4 x1 = *reinterpret_cast<const float4*>(Xs + r * LDX + HID / 2 + ty * 4);
+        const float x[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(x[i], y[j], acc[i][j]);
+      }
+    }
+  }
+  // thread block (i, j) <-> k = (i < 4 ? ty*4 + i : 32 + ty*4 + i - 4), n = (j < 4 ? tx*4 + j : BN/2 + tx*4 + j - 4)
+  for (int sl = 0; sl < SL; ++sl) {
+    __syncthreads();
+    if (slice == sl) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int k = i < 4 ? ty * 4 + i : HID / 2 + ty * 4 + (i - 4);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int n = j < 4 ? tx * 4 + j : BN / 2 + tx * 4 + (j - 4);
+          float* q = Acc + k * BN + n;
+          *q = sl == 0 ? acc[i][j] : *q + acc[i][j];
         }
       }
-      const float ind = Ind[r];
+      if (ty == 0) {
 #pragma unroll
-      for (int j = 0; j < NB; ++j) accb[j] = fmaf(ind, y[j], accb[j]);
-      if (kact) {
-        const float4 x4 = *reinterpret_cast<const float4*>(Xs + r * LDX + ty * 4);
-#pragma unroll
-        for (int j = 0; j < NB; ++j) {
-          acc[0][j] = fmaf(x4.x, y[j], acc[0][j]); acc[1][j] = fmaf(x4.y, y[j], acc[1][j]);
-          acc[2][j] = fmaf(x4.z, y[j], acc[2][j]); acc[3][j] = fmaf(x4.w, y[j], acc[3][j]);
+        for (int j = 0; j < 8; ++j) {
+          const int n = j < 4 ? tx * 4 + j : BN / 2 + tx * 4 + (j - 4);
+          float* q = Acc + HID * BN + n;
+          *q = sl == 0 ? accb[j] : *q + accb[j];
         }
       }
     }
   }
+  __syncthreads();
   float* out = partial + (int64_t)blockIdx.x * (Kc + 1) * Nc;
-#pragma unroll
-  for (int j = 0; j < NB; ++j) {
-    const int n = (NB == 8 && j >= 4) ? BN / 2 + tx * 4 + (j - 4) : tx * 4 + j;
-    if (n >= Nc) continue;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int k = ty * 4 + i;
-      if (k < Kc) out[(int64_t)k * Nc + n] = acc[i][j];
-    }
-    if (ty == 0) out[(int64_t)Kc * Nc + n] = accb[j];
+  for (int i = tid; i < (Kc + 1) * Nc; i += LIN_THREADS) {
+    const int k = i / Nc, n = i % Nc;
+    out[i] = Acc[(k < Kc ? k : HID) * BN + n];
   }
 }
 
@@ -713,8 +762,14 @@ int64_t per_row_floats(const wf_live_model* m) {
   return (int64_t)(nn + 1) * D + (int64_t)nn * (4 * HID + DPm) + 1 + (int64_t)m->n_layers * D + 2 * D + 1 + DPm + 2 * HID + 2 * D;
 }
 
-int smem_linear(int Kc, int BN) { const int KcP = (Kc + 3) & ~3; return (KcP * BN + GM * (KcP + 4)) * (int)sizeof(float); }
-int smem_wgrad(int Kc, int BN) { const int KcP = (Kc + 3) & ~3; return (WG_ROWS * (KcP + 4) + WG_ROWS * BN + WG_ROWS) * (int)sizeof(float); }
+int smem_linear(int Kc, int BN) {
+  const int KcP = (Kc + 3) & ~3, SL = LIN_THREADS / BN;
+  return (KcP * BN + SL * LROWS * (KcP + 4)) * (int)sizeof(float);
+}
+int smem_wgrad(int BN) {
+  const int SL = LIN_THREADS / BN;
+  return (SL * (WROWS * (HID + 4) + WROWS * BN + WROWS) + (HID + 1) * BN) * (int)sizeof(float);
+}
 
 template <int BN, bool T, bool A>
 int launch_linear_bn(const float* Ain, const float* B, const float* bias, float* C, int64_t R, int Kc, int Nc, int G, cudaStream_t s) {
@@ -723,7 +778,8 @@ int launch_linear_bn(const float* Ain, const float* B, const float* bias, float*
     WF_CUDA(cudaFuncSetAttribute(linear_kernel<BN, T, A>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     attr = true;
   }
-  const int64_t tiles = (R + GM - 1) / GM;
+  constexpr int SL = LIN_THREADS / BN;
+  const int64_t tiles = ((R + LROWS - 1) / LROWS + SL - 1) / SL;
   const int grid = (int)(tiles < 2 * num_sms() ? tiles : 2 * num_sms());
   linear_kernel<BN, T, A><<<grid, LIN_THREADS, smem_linear(Kc, BN), s>>>(Ain, B, bias, C, R, Kc, Nc, G);
   WF_LAUNCH_CHECK();
@@ -742,14 +798,14 @@ int launch_wgrad_bn(const float* X, const float* dY, float* partial, int grid, i
     WF_CUDA(cudaFuncSetAttribute(wgrad_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     attr = true;
   }
-  wgrad_kernel<BN><<<grid, LIN_THREADS, smem_wgrad(Kc, BN), s>>>(X, dY, partial, R, Kc, Nc, G);
+  wgrad_kernel<BN><<<grid, LIN_THREADS, smem_wgrad(BN), s>>>(X, dY, partial, R, Kc, Nc, G);
   WF_LAUNCH_CHECK();
   return WF_OK;
 }
 
 int launch_wgrad(const float* X, const float* dY, float* partial, float* gW, float* gb, int layer, int D, int64_t R, int Kc, int Nc,
                  int G, cudaStream_t s) {
-  const int64_t tiles = (R + WG_ROWS - 1) / WG_ROWS;
+  const int64_t tiles = (R + 4 * WROWS - 1) / (4 * WROWS);
   const int grid = (int)(tiles < WGRAD_CTAS ? tiles : WGRAD_CTAS);
   const int st = Nc <= 64 ? launch_wgrad_bn<64>(X, dY, partial, grid, R, Kc, Nc, G, s)
                           : launch_wgrad_bn<128>(X, dY, partial, grid, R, Kc, Nc, G, s);
