@@ -179,9 +179,12 @@ def run_b200(args):
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    # One JSON line on stdout and nothing else: libraries (NCCL prints its version banner to stdout) get stderr as
+    # their fd 1 for the whole run; the result line is written to the saved descriptor at the end.
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's version banner off stdout: one JSON line only
         dist.init_process_group("nccl", device_id=dev)
 
     from waveflow_b200 import _ffi, _live, model_factory, vqmc
@@ -274,6 +277,78 @@ def run_b200(args):
     ms_per_step = total_ms / steps
     value = wl["n_walkers"] / (ms_per_step * 1e-3)
     e2e_value = wl["n_walkers"] / (e2e_s / steps)
+
+    # ---------------- SURVEY 8(f) rank 1: the training step (value_and_grad(loss_fn_efficient) + Adam) on the same workload
+    train_ms = None
+    if not args.no_sweep:
+        from waveflow_b200 import _train
+        opt_init, opt_update, get_params = _train.adam(1e-4, device=dev)
+        opt_state = opt_init(params)
+        tparams = get_params(opt_state)
+
+        def tstep(i):
+            return vqmc.train_step_efficient(i, psi, h_fn, opt_update, opt_state, tparams, x_dev, 0.0)
+        for i in range(3):
+            tstep(i)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        kt = 10
+        a.record()
+        for i in range(kt):
+            _, tl = tstep(3 + i)
+        b.record(); torch.cuda.synchronize()
+        train_ms = a.elapsed_time(b) / kt
+        if world > 1:
+            tms = torch.tensor([train_ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+            train_ms = float(tms.item())
+        train_loss = float(tl)
+
+    # ---------------- BASELINE configs 3 and 5 over N GPUs: the fixed sample sets sharded by rows, no collective on the data
+    # path; whole-job samples/s = total samples / max over ranks of the device time
+    flow_scaling = None
+    if world > 1 and not args.no_sweep:
+        from waveflow_b200.flows.neural_splines import coupling_flow, coupling_flow_tc, pack_fcnn_tc
+        flow_scaling = {}
+
+        def rank_time(fn, reps):
+            fn(); torch.cuda.synchronize(); dist.barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(reps):
+                fn()
+            b.record(); torch.cuda.synchronize()
+            t = torch.tensor([a.elapsed_time(b) / reps], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        gW = lambda r_, a_, b_: torch.from_numpy((r_.standard_normal((a_, b_)) / np.sqrt(a_)).astype(np.float32)).to(dev)
+        zz = lambda n_: torch.zeros(n_, device=dev)
+        gsh = torch.Generator(device=dev); gsh.manual_seed(1000 + rank)
+        # config 3: D = 8, K = 32, hidden 8, 8 layers, 2^24 samples in total
+        crng = np.random.Generator(np.random.PCG64(0))
+        Dc, K3, h3, L3, M3 = 8, 32, 8, 8, (1 << 24) // world
+        od = (3 * K3 - 1) * Dc // 2
+        layers3 = [tuple([(gW(crng, Dc // 2, h3), zz(h3)), (), (gW(crng, h3, h3), zz(h3)), (), (gW(crng, h3, od), zz(od))] for _f in range(2))
+                   for _ in range(L3)]
+        x3 = torch.rand(M3, Dc, device=dev, generator=gsh) * 6 - 3
+        for inv in (False, True):
+            ms = rank_time(lambda: coupling_flow(layers3, x3, K3, 3.0, h3, inverse=inv), 3)
+            flow_scaling[f"c3_D8_{'inverse' if inv else 'density'}"] = {"samples_total": M3 * world, "ms": ms,
+                                                                        "samples_per_s": M3 * world / (ms * 1e-3)}
+        del x3, layers3
+        # config 5: D = 64, K = 64, hidden 512, 8 layers, 2^22 samples in total (tensor-core path)
+        crng = np.random.Generator(np.random.PCG64(0))
+        D5, K5, H5, L5, M5 = 64, 64, 512, 8, (1 << 22) // world
+        od = (3 * K5 - 1) * D5 // 2
+        w5 = torch.cat([pack_fcnn_tc([(gW(crng, D5 // 2, H5), zz(H5)), (), (gW(crng, H5, H5), zz(H5)), (), (gW(crng, H5, od), zz(od))], dev)
+                        for _ in range(2 * L5)]).contiguous()
+        x5 = torch.rand(M5, D5, device=dev, generator=gsh) * 6 - 3
+        coupling_flow_tc(w5, L5, x5[: 1 << 16], 3.0)
+        ms = rank_time(lambda: coupling_flow_tc(w5, L5, x5, 3.0), 1)
+        flow_scaling["c5_D64_logprob"] = {"samples_total": M5 * world, "ms": ms, "samples_per_s": M5 * world / (ms * 1e-3),
+                                          "algorithmic_tflops_total": 109051904.0 * M5 * world / (ms * 1e-3) / 1e12}
+        del x5, w5
+        torch.cuda.empty_cache()
 
     if rank != 0:
         if world > 1:
@@ -424,38 +499,17 @@ def run_b200(args):
                                          "FLOPs and TF32 runs at half the bf16 rate, so frac <= 1/6 by construction"}}
         del x5, y5, ld5, w5
 
-    # ---------------- SURVEY 8(f) rank 1: the training step (value_and_grad(loss_fn_efficient) + Adam) on the same workload
     train = None
-    if not args.no_sweep:
-        from waveflow_b200 import _train
-        opt_init, opt_update, get_params = _train.adam(1e-4, device=dev)
-        opt_state = opt_init(params)
-        tparams = get_params(opt_state)
-
-        def tstep(i):
-            return vqmc.train_step_efficient(i, psi, h_fn, opt_update, opt_state, tparams, x_dev, 0.0)
-        for i in range(3):
-            tstep(i)
-        torch.cuda.synchronize()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        kt = 10
-        a.record()
-        for i in range(kt):
-            _, tl = tstep(3 + i)
-        b.record(); torch.cuda.synchronize()
-        ms = a.elapsed_time(b) / kt
-        if world > 1:
-            tms = torch.tensor([ms], dtype=torch.float64, device=dev)
-            dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-            ms = float(tms.item())
+    if train_ms is not None:
+        ms = train_ms
         tfl = 3.0 * flops_per_walker(D) * n_local / (ms * 1e-3) / 1e12          # forward + ~2x for the reverse pass
         train = {"api": "vqmc.train_step_efficient(epoch, psi, h_fn, opt_update, opt_state, params, batch, running_average)",
                  "kernels": "wf_vqmc_loss_grad (layer-wise jets: linear / tanh / spline-head kernels, forward + reverse) + wf_adam_step",
                  "walkers_total": wl["n_walkers"], "walkers_per_gpu": n_local, "ms_per_step": ms,
-                 "walkers_per_s": wl["n_walkers"] / (ms * 1e-3), "loss": float(tl),
+                 "walkers_per_s": wl["n_walkers"] / (ms * 1e-3), "loss": train_loss,
                  "exchange": "none" if world == 1 else f"all-reduce of the flat gradient ({opt_state.flat.numel()} floats) + 32-byte loss sums per step",
                  "algorithmic_tflops_per_gpu": tfl, "frac_of_measured_fp32_fma": tfl / fp32_peak,
-                 "gpu_launches_per_step": 4 * (85 + 1) if n_local > 16384 else 86}
+                 "gpu_launches_per_step": 85 * ((n_local + 16383) // 16384) + 1}
         if world == 1 and not args.no_cpu_baseline:
             from oracle import fixtures as fx
             from oracle import grad as ograd
@@ -468,6 +522,7 @@ def run_b200(args):
             train["cpu_baseline"] = {"value": ns / sec, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
                                      "sample": f"first {ns} walkers, one pass", "seconds_per_pass": sec,
                                      "note": "torch-CPU float32 autograd restatement (three reverse passes, oracle/grad.py); Adam not included"}
+
 
     # ---------------- CPU baseline (rank 0, N = 1): bounded sample of the same workload
     cpu = None
@@ -493,9 +548,11 @@ def run_b200(args):
                     "ms_per_step": e2e_s / steps * 1e3},
             "gpu_launches": steps,
             "kernel_ms_per_step": kern_ms_mean, "wall_s_timed_region": t_wall,
-            "roofline": roofline, "cpu_baseline": cpu, "spline_sweep": sweep, "rqs_sweep": rqs_sweep, "coupling_flow_sweep": coupling, "tc_coupling_flow_sweep": tc_sweep, "train_step": train,
+            "roofline": roofline, "cpu_baseline": cpu, "spline_sweep": sweep, "rqs_sweep": rqs_sweep, "coupling_flow_sweep": coupling, "tc_coupling_flow_sweep": tc_sweep, "flow_scaling": flow_scaling, "train_step": train,
             "energy_estimate": {"mean": float(s[0] / s[2]), "n": int(s[2])}}
-    print(json.dumps(line), flush=True)
+    sys.stdout.flush()
+    os.write(json_fd, (json.dumps(line) + "\n").encode())
+    os.close(json_fd)
     if world > 1:
         dist.destroy_process_group()
 
@@ -511,6 +568,9 @@ def main():
     ap.add_argument("--no-sweep", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    if os.environ.get("WF_BENCH_WATCHDOG"):          # debugging aid: dump every thread's stack and exit after N seconds
+        import faulthandler
+        faulthandler.dump_traceback_later(int(os.environ["WF_BENCH_WATCHDOG"]), exit=True)
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
         run_reference(args)
