@@ -140,3 +140,43 @@ def test_training_lowers_the_energy(cuda):
             avg = float(np.mean(losses[-50:]))
     assert np.all(np.isfinite(losses))
     assert np.mean(losses[-20:]) < np.mean(losses[:20]) - 0.1, (np.mean(losses[:20]), np.mean(losses[-20:]))
+
+
+def test_checkpoint_writers_match_published_files(cuda, tmp_path):
+    """utils/helpers.create_checkpoint_wavefunc on the published He parameters reproduces the files the reference itself
+    wrote for that epoch (psi on the 100 x 100 plane, the on-proton cut), and the pickle round-trips (resume path)."""
+    from waveflow_b200 import model_factory
+    from waveflow_b200.utils import helpers
+    params, gold = fx.load_he_checkpoint()
+    init_fun = model_factory.get_waveflow_model(2, base_spline_degree=6, i_spline_degree=6, n_prior_internal_knots=23,
+                                                n_i_internal_knots=23, i_spline_reg=0.05, n_flow_layers=3, box_size=10,
+                                                cached_bases_root=None)
+    _, psi, log_pdf, sample = init_fun(0, 2)
+    tp = to_torch_tree(params, cuda)
+    sd = {"system_name": "He", "box_length": 10, "n_particle": 2, "n_space_dimension": 1}
+    helpers.create_checkpoint_wavefunc(3, str(tmp_path), psi, sample, tp, 100000, [0.0, -1.8], [[-1.8]], sd)
+    z = np.load(tmp_path / "outputs/wavefunctions_2d/values_epoch100000.npy")
+    assert z.shape == (10000,) and z.dtype == np.float32
+    assert np.abs(z - gold["psi_grid"]).max() < 3e-5
+    oc = np.load(tmp_path / "outputs/density_1e/onproton_coord_epoch100000.npy")
+    ov = np.load(tmp_path / "outputs/density_1e/onproton_values_epoch100000.npy")
+    assert np.allclose(oc, gold["onproton_coord"], atol=1e-6) and np.abs(ov - gold["onproton_values"]).max() < 3e-5
+    assert np.load(tmp_path / "outputs/sample_points/values_epoch100000.npy").shape == (250, 2)
+    assert np.load(tmp_path / "outputs/density_1e/random_values_epoch100000.npy").shape == (100,)
+    saved, epoch, loss, energies = helpers.load_checkpoint(str(tmp_path))
+    assert epoch == 100000 and loss == [0.0, -1.8]
+    for a, b in zip(_leaves(saved), _leaves(params)):
+        assert np.array_equal(np.asarray(a), np.asarray(b))
+
+
+def test_model_trainer_loop_and_resume(cuda, tmp_path):
+    from waveflow_b200 import vqmc
+    t = vqmc.ModelTrainer(system_name="He", learning_rate=1e-3, box_length=10, num_epochs=6, batch_size=128, log_every=5)
+    t.save_dir = str(tmp_path / "run")
+    params, loss = t.start_training(cached_bases_root=None)
+    assert len(loss) == 7 and np.all(np.isfinite(loss))
+    assert (tmp_path / "run/outputs/wavefunctions_2d/values_epoch5.npy").exists() and (tmp_path / "run/system_info.json").exists()
+    t2 = vqmc.ModelTrainer(system_name="He", learning_rate=1e-3, box_length=10, num_epochs=2, batch_size=128, log_every=5)
+    t2.save_dir = t.save_dir
+    params2, loss2 = t2.start_training(restart=True, cached_bases_root=None)
+    assert len(loss2) == len(np.load(tmp_path / "run/loss.npy")) + 2

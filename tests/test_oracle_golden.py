@@ -147,3 +147,12 @@ def test_gradient_oracle_against_finite_differences(he):
     # flow-layer gradients exist and are finite; zero_params get zeros
     for net in [n for n in g[0] if len(n)]:
         assert all(np.all(np.isfinite(a_)) for lay in net[0] for a_ in lay) and not np.any(net[1])
+
+
+def test_inversion_count_matches_definition():
+    from waveflow_b200.utils.coordinates import get_num_inversion_count
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal((50, 5))
+    brute = [sum(1 for i in range(5) for j in range(i + 1, 5) if r[i] > r[j]) for r in x]
+    assert get_num_inversion_count(x).tolist() == brute
+    assert get_num_inversion_count(np.array([[2.0, 1.0]])).tolist() == [1]

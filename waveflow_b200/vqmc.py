@@ -141,29 +141,40 @@ class ModelTrainer:
         self.opt_state, self.opt_update, self.get_params = opt_state, opt_update, get_params
         return psi, log_pdf, sample, get_params(opt_state), h_fn
 
-    def start_training(self, restart=False, num_epochs=None, rng=2, cached_bases_root='./cached_splines_bases', save=False,
+    def start_training(self, restart=False, num_epochs=None, rng=2, cached_bases_root='./cached_splines_bases', save=True,
                        callback=None):
-        """The optimisation loop of vqmc.py:53-117: sample a batch from |psi|^2, one train_step_efficient, running average
-        of the last 100 losses refreshed every 100 epochs.  -> (params, loss history).  Checkpoint / plot writers
-        (helpers.create_checkpoint_wavefunc) are not part of this path; save=True stores loss.npy / energies.npy only."""
+        """The optimisation loop of vqmc.py:53-117: checkpoint at epoch 1 and every log_every epochs
+        (helpers.create_checkpoint_wavefunc), sample a batch from |psi|^2, one train_step_efficient, running average of the last
+        100 losses refreshed every 100 epochs.  restart=True resumes from save_dir/checkpoints.  -> (params, loss history)."""
+        from pathlib import Path
+        from .utils import helpers
         psi, log_pdf, sample, params, h_fn = self.build(rng=rng, cached_bases_root=cached_bases_root)
         opt_state, opt_update, get_params = self.opt_state, self.opt_update, self.get_params
-        running_average = 0.0
-        loss = [0.0]
-        for epoch in range(1, (num_epochs or self.num_epochs) + 1):
+        system_dict = {"system_name": self.system_name, "box_length": self.box_length, "n_particle": self.n_particle,
+                       "n_space_dimension": self.n_space_dimension, "window": 100, "n_plotting": 200}
+        start_epoch, loss, energies = 0, [0.0], []
+        if restart and Path(f"{self.save_dir}/checkpoints").exists():
+            saved, start_epoch, loss, energies = helpers.load_checkpoint(self.save_dir)
+            opt_state.flat.copy_(_train.ravel(saved, opt_state.flat.device))        # Adam moments restart from zero
+        if save:
+            import json
+            helpers.make_result_dirs(self.save_dir)
+            with open(f"{self.save_dir}/system_info.json", "w") as f:
+                json.dump(system_dict, f, indent=4)
+        running_average = float(np.mean(loss[-100:])) if start_epoch >= 100 else 0.0
+        for epoch in range(start_epoch + 1, start_epoch + (num_epochs or self.num_epochs) + 1):
+            if save and (epoch % self.log_every == 0 or epoch == 1):
+                helpers.create_checkpoint_wavefunc(rng * 7919 + epoch, self.save_dir, psi, sample, params, epoch, loss, energies,
+                                                   system_dict)
             batch = sample(rng * 1000003 + epoch, params, self.batch_size)
             opt_state, new_loss = train_step_efficient(epoch, psi, h_fn, opt_update, opt_state, params, batch, running_average)
             if epoch % 100 == 0:
                 running_average = float(np.mean(loss[-100:]))
             params = get_params(opt_state)
             loss.append(float(new_loss))
+            energies.append([float(new_loss)])
             if callback is not None:
                 callback(epoch, loss[-1], params)
             if epoch % self.log_every == 0:
                 print(f"epoch {epoch} | Loss: {loss[-1]:.3f}")
-        if save:
-            from pathlib import Path
-            Path(self.save_dir).mkdir(parents=True, exist_ok=True)
-            np.save(f"{self.save_dir}/loss.npy", np.asarray(loss))
-            np.save(f"{self.save_dir}/energies.npy", np.asarray(loss[1:])[:, None])
         return params, loss
