@@ -510,6 +510,30 @@ def run_b200(args):
                  "exchange": "none" if world == 1 else f"all-reduce of the flat gradient ({opt_state.flat.numel()} floats) + 32-byte loss sums per step",
                  "algorithmic_tflops_per_gpu": tfl, "frac_of_measured_fp32_fma": tfl / fp32_peak,
                  "gpu_launches_per_step": 85 * ((n_local + 16383) // 16384) + 1}
+        if world == 1:
+            # the reference's own training configuration (BASELINE configs[1]): He, batch 256 -- launch-bound, CUDA-graph replay
+            from waveflow_b200 import _train
+            w2 = workload("vqmc_c2")
+            init2 = model_factory.get_waveflow_model(2, base_spline_degree=6, i_spline_degree=6, n_prior_internal_knots=23,
+                                                     n_i_internal_knots=23, i_spline_reg=0.05, i_spline_reverse_fun_tol=1e-6,
+                                                     n_flow_layers=3, box_size=10.0, xu_coord_type="mean", cached_bases_root=None)
+            _p2, psi2, _lp2, _s2 = init2(0, 2)
+            h2 = physics.construct_hamiltonian_function(psi2, protons=w2["protons"], n_space_dimensions=1, eps=0.0)
+            oi2, ou2, gp2 = _train.adam(1e-4, device=dev)
+            st2 = oi2(w2["params"])
+            xb = torch.from_numpy(w2["walkers"]).to(dev)
+            he = {}
+            for ug in (False, True):
+                for i in range(5):
+                    vqmc.train_step_efficient(i, psi2, h2, ou2, st2, gp2(st2), xb, -1.8, use_graph=ug)
+                torch.cuda.synchronize()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                for i in range(50):
+                    vqmc.train_step_efficient(5 + i, psi2, h2, ou2, st2, gp2(st2), xb, -1.8, use_graph=ug)
+                b.record(); torch.cuda.synchronize()
+                he["cuda_graph_ms_per_step" if ug else "eager_ms_per_step"] = a.elapsed_time(b) / 50
+            train["he_batch256"] = {"description": w2["desc"], **he}
         if world == 1 and not args.no_cpu_baseline:
             from oracle import fixtures as fx
             from oracle import grad as ograd

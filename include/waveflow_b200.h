@@ -247,15 +247,18 @@ int64_t wf_vqmc_grad_workspace_floats(const wf_live_model* model_host, int64_t w
  * evaluated by a reverse pass through the forward-mode Laplacian (table derivatives = next table; order 4 clamps to 3).
  * grad [wf_vqmc_param_floats] is ACCUMULATED into (zero it first; NULL = forward only; masked-out weights get 0);
  * inv_n_total = 1 / (number of walkers over all ranks).  psi, hpsi, eloc [N] nullable; sums (nullable, double[4]) +=
- * {sum E, sum E^2, count, sum psi^2}.  The call loops over chunks sized to the workspace; deterministic summation. */
+ * {sum E, sum E^2, count, sum psi^2}.  The call loops over chunks sized to the workspace; deterministic summation.
+ * running_average_dev (nullable, device float[1]) overrides running_average: the call then has no host-side inputs that
+ * change from step to step, so a captured CUDA graph of it can be replayed. */
 int wf_vqmc_loss_grad(const wf_live_model* model_host, const wf_live_tables* tables_host, const float* params,
                       const float* protons_host, int n_protons, const float* x, int64_t N, float running_average,
-                      float inv_n_total, float* grad, float* psi, float* hpsi, float* eloc, double* sums, float* workspace,
-                      int64_t workspace_floats, void* stream);
+                      const float* running_average_dev, float inv_n_total, float* grad, float* psi, float* hpsi, float* eloc,
+                      double* sums, float* workspace, int64_t workspace_floats, void* stream);
 
-/* One Adam update (optimizers.adam: m, v moment buffers, bias correction with exponent step + 1), in place. */
-int wf_adam_step(float* params, float* m, float* v, const float* grad, int64_t n, int64_t step, float lr, float b1, float b2,
-                 float eps, void* stream);
+/* One Adam update (optimizers.adam: m, v moment buffers, bias correction with exponent step + 1), in place.
+ * step_dev (nullable, device int64[1]) overrides step (graph replays). */
+int wf_adam_step(float* params, float* m, float* v, const float* grad, int64_t n, int64_t step, const int64_t* step_dev, float lr,
+                 float b1, float b2, float eps, void* stream);
 
 #ifdef __cplusplus
 }

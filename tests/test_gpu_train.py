@@ -180,3 +180,25 @@ def test_model_trainer_loop_and_resume(cuda, tmp_path):
     t2.save_dir = t.save_dir
     params2, loss2 = t2.start_training(restart=True, cached_bases_root=None)
     assert len(loss2) == len(np.load(tmp_path / "run/loss.npy")) + 2
+
+
+def test_graphed_step_equals_eager_step(cuda):
+    """The CUDA-graph replay of a training step gives the same parameters and loss as the eager step."""
+    from waveflow_b200 import vqmc
+    from waveflow_b200.utils import physics
+    res = []
+    for use_graph in (False, True):
+        psi, log_pdf, sample, opt_state, opt_update, get_params = vqmc.create_train_state(10, 1e-3, n_particle=2, rng=0,
+                                                                                          cached_bases_root=None)
+        h_fn = physics.construct_hamiltonian_function(psi, protons=np.array([[0.0], [0.0]]), n_space_dimensions=1)
+        params = get_params(opt_state)
+        losses = []
+        for epoch in range(1, 6):
+            batch = sample(epoch, params, 256)
+            opt_state, loss = vqmc.train_step_efficient(epoch, psi, h_fn, opt_update, opt_state, params, batch, -0.5 * epoch,
+                                                        use_graph=use_graph)
+            params = get_params(opt_state)
+            losses.append(float(loss))
+        res.append((opt_state.flat.clone(), losses))
+    assert np.allclose(res[0][1], res[1][1], rtol=1e-5, atol=1e-6), (res[0][1], res[1][1])
+    assert torch.allclose(res[0][0], res[1][0], rtol=1e-5, atol=1e-7)

@@ -29,3 +29,19 @@ for with_grad in (True, False):
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / K
     print(f'D={D} N={N} chunk={chunk} with_grad={with_grad}: {ms:.3f} ms  {N / ms * 1e3 / 1e6:.2f} M walkers/s')
+if N <= 4096:
+    from waveflow_b200 import vqmc
+    opt_init, opt_update, get_params = _train.adam(1e-4)
+    st = opt_init(fx.cast_params(params, np.float32))
+    class H: pass
+    h = H(); h.wf_spec = spec; h.protons = np.zeros(D, dtype=np.float32)
+    for ug in (False, True):
+        for i in range(5):
+            vqmc.train_step_efficient(i, None, h, opt_update, st, get_params(st), x, 0.0, use_graph=ug)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter(); e0.record()
+        for i in range(50):
+            vqmc.train_step_efficient(5 + i, None, h, opt_update, st, get_params(st), x, 0.0, use_graph=ug)
+        e1.record(); torch.cuda.synchronize()
+        print(f'train_step_efficient N={N} use_graph={ug}: {e0.elapsed_time(e1) / 50:.3f} ms/step (wall {(time.perf_counter() - t0) / 50 * 1e3:.3f} ms)')

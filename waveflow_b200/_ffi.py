@@ -79,9 +79,9 @@ _SIGS = {
     "wf_live_sample": (_i, [C.POINTER(LiveModelStruct), C.POINTER(LiveTablesStruct), _p, C.c_uint64, _l, _i, _p, _p, _p]),
     "wf_vqmc_param_floats": (_l, [C.POINTER(LiveModelStruct)]),
     "wf_vqmc_grad_workspace_floats": (_l, [C.POINTER(LiveModelStruct), _l]),
-    "wf_vqmc_loss_grad": (_i, [C.POINTER(LiveModelStruct), C.POINTER(LiveTablesStruct), _p, _p, _i, _p, _l, _f, _f, _p, _p, _p,
+    "wf_vqmc_loss_grad": (_i, [C.POINTER(LiveModelStruct), C.POINTER(LiveTablesStruct), _p, _p, _i, _p, _l, _f, _p, _f, _p, _p, _p,
                                _p, _p, _p, _l, _p]),
-    "wf_adam_step": (_i, [_p, _p, _p, _p, _l, _l, _f, _f, _f, _f, _p]),
+    "wf_adam_step": (_i, [_p, _p, _p, _p, _l, _l, _p, _f, _f, _f, _f, _p]),
     "wf_local_energy": (_i, [C.POINTER(LiveModelStruct), C.POINTER(LiveTablesStruct), _p, _p, _i, _p, _l, _p, _p, _p, _p, _p,
                              _p, _p]),
 }

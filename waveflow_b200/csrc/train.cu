@@ -28,11 +28,20 @@ __host__ __device__ inline bool made_mask(int layer, int D, int k, int n) {
   return ((n % D) - 1) >= (k % (D - 1));
 }
 
-__global__ void mask_weights_kernel(const float* __restrict__ W, float* __restrict__ Wm, int layer, int D, int K, int N) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= K * N) return;
-  const int k = i / N, n = i % N;
-  Wm[i] = made_mask(layer, D, k, n) ? W[i] : 0.f;
+// all layers of all conditioners in one launch: blockIdx.y = 3 * net + (layer - 1)
+struct MaskJobs {
+  int64_t src[3 * (WF_MAX_LAYERS + 1)], dst[3 * (WF_MAX_LAYERS + 1)];
+  int K[3 * (WF_MAX_LAYERS + 1)], N[3 * (WF_MAX_LAYERS + 1)];
+};
+__global__ void mask_weights_kernel(const float* __restrict__ params, float* __restrict__ Wm, const __grid_constant__ MaskJobs jobs, int D) {
+  const int j = blockIdx.y, layer = j % 3 + 1;
+  const int K = jobs.K[j], N = jobs.N[j];
+  const float* W = params + jobs.src[j];
+  float* out = Wm + jobs.dst[j];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < K * N; i += gridDim.x * blockDim.x) {
+    const int k = i / N, n = i % N;
+    out[i] = made_mask(layer, D, k, n) ? W[i] : 0.f;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------- linear layers
@@ -49,13 +58,13 @@ __device__ __forceinline__ void slice_sync(int slice, int threads) {
 
 // C[R][Nc] (+)= A[R][Kc] * B (+ bias on the value rows r % G == 0).  TRANS_B == false: B [Kc][Nc]; true: B given as [Nc][Kc].
 // The whole K extent is resident in shared memory: B once per CTA (k-major), A per 64-row chunk (row-major, k contiguous).
-constexpr int LROWS = 64;   // rows per slice chunk
-template <int BN, bool TRANS_B, bool ACCUM>
+// RM rows per thread: 8 (64-row chunks) for large batches, 2 (16-row chunks, 4x the CTAs) when the batch is small
+template <int BN, bool TRANS_B, bool ACCUM, int RM>
 __global__ void __launch_bounds__(LIN_THREADS) linear_kernel(const float* __restrict__ A, const float* __restrict__ B,
                                                              const float* __restrict__ bias, float* __restrict__ C,
                                                              int64_t R, int Kc, int Nc, int G) {
   extern __shared__ __align__(16) float sm[];
-  constexpr int TX = BN / 8, TS = 8 * TX, SL = LIN_THREADS / TS;
+  constexpr int TX = BN / 8, TS = 8 * TX, SL = LIN_THREADS / TS, LROWS = 8 * RM;
   const int KcP = (Kc + 3) & ~3, LDA = KcP + 4;
   float* Bs = sm;                                         // [KcP][BN]
   const int tid = threadIdx.x, slice = tid / TS, ts = tid % TS, tx = ts % TX, ty = ts / TX;
@@ -85,22 +94,22 @@ __global__ void __launch_bounds__(LIN_THREADS) linear_kernel(const float* __rest
       }
     }
     slice_sync(slice, TS);
-    float acc[8][8];
+    float acc[RM][8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+    for (int i = 0; i < RM; ++i)
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
 #pragma unroll 2
     for (int k = 0; k < KcP; k += 4) {
-      float4 a[8];
+      float4 a[RM];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) a[i] = *reinterpret_cast<const float4*>(As + (ty * 8 + i) * LDA + k);
+      for (int i = 0; i < RM; ++i) a[i] = *reinterpret_cast<const float4*>(As + (ty * RM + i) * LDA + k);
 #pragma unroll
       for (int kk = 0; kk < 4; ++kk) {
         const float4 b0 = *reinterpret_cast<const float4*>(Bs + (k + kk) * BN + tx * 4);
         const float4 b1 = *reinterpret_cast<const float4*>(Bs + (k + kk) * BN + BN / 2 + tx * 4);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < RM; ++i) {
           const float av = kk == 0 ? a[i].x : (kk == 1 ? a[i].y : (kk == 2 ? a[i].z : a[i].w));
           acc[i][0] = fmaf(av, b0.x, acc[i][0]); acc[i][1] = fmaf(av, b0.y, acc[i][1]);
           acc[i][2] = fmaf(av, b0.z, acc[i][2]); acc[i][3] = fmaf(av, b0.w, acc[i][3]);
@@ -110,8 +119,8 @@ __global__ void __launch_bounds__(LIN_THREADS) linear_kernel(const float* __rest
       }
     }
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int rl = ty * 8 + i;
+    for (int i = 0; i < RM; ++i) {
+      const int rl = ty * RM + i;
       if (rl >= rows) continue;
       const int64_t r = r0 + rl;
       const bool value_row = bias && (r % G) == 0;
@@ -624,6 +633,7 @@ struct FinalArgs {
   int n_layers, n_protons;
   float protons[WF_MAX_D];
   float running_average, inv_n;
+  const float* ra_dev;    // nullable: device-resident running average (CUDA-graph replays), overrides running_average
   float* PHIbar;          // [R][D]
   float* LDbar;           // [R]
   float* psi; float* hpsi; float* eloc;   // nullable [N]
@@ -674,7 +684,8 @@ __global__ void final_kernel(const __grid_constant__ FinalArgs a) {
     if (a.eloc) a.eloc[n] = eloc;
     if (isfinite(eloc)) { e = eloc; e2 = eloc * eloc; cnt = 1.f; p2 = psi.v * psi.v; }
     // custom_jvp of _loss_fn_efficient (vqmc.py:202-212)
-    const float ca = 2.f * (eloc - a.running_average) / psi.v - hpsi / (psi.v * psi.v);
+    const float ravg = a.ra_dev ? __ldg(a.ra_dev) : a.running_average;
+    const float ca = 2.f * (eloc - ravg) / psi.v - hpsi / (psi.v * psi.v);
     const float cb = 1.f / psi.v;
     Jet<D> psibar = jzero<D>();
     psibar.v = (ca + V * cb) * a.inv_n;
@@ -712,9 +723,14 @@ __global__ void final_kernel(const __grid_constant__ FinalArgs a) {
 
 // ---------------------------------------------------------------------------------------------- Adam (jax.example_libraries.optimizers.adam)
 __global__ void adam_kernel(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v, const float* __restrict__ g,
-                            int64_t n, float lr, float b1, float b2, float eps, float c1, float c2) {
+                            int64_t n, float lr, float b1, float b2, float eps, float c1, float c2, const int64_t* __restrict__ step_dev) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  if (step_dev) {   // device-resident step counter (CUDA-graph replays): bias corrections computed here
+    const float e = (float)(*step_dev + 1);
+    c1 = 1.f - powf(b1, e);
+    c2 = 1.f - powf(b2, e);
+  }
   const float gi = g[i];
   const float mi = (1.f - b1) * gi + b1 * m[i];
   const float vi = (1.f - b2) * gi * gi + b2 * v[i];
@@ -762,28 +778,35 @@ int64_t per_row_floats(const wf_live_model* m) {
   return (int64_t)(nn + 1) * D + (int64_t)nn * (4 * HID + DPm) + 1 + (int64_t)m->n_layers * D + 2 * D + 1 + DPm + 2 * HID + 2 * D;
 }
 
-int smem_linear(int Kc, int BN) {
+int smem_linear(int Kc, int BN, int lrows) {
   const int KcP = (Kc + 3) & ~3, SL = LIN_THREADS / BN;
-  return (KcP * BN + SL * LROWS * (KcP + 4)) * (int)sizeof(float);
+  return (KcP * BN + SL * lrows * (KcP + 4)) * (int)sizeof(float);
 }
 int smem_wgrad(int BN) {
   const int SL = LIN_THREADS / BN;
   return (SL * (WROWS * (HID + 4) + WROWS * BN + WROWS) + (HID + 1) * BN) * (int)sizeof(float);
 }
 
-template <int BN, bool T, bool A>
-int launch_linear_bn(const float* Ain, const float* B, const float* bias, float* C, int64_t R, int Kc, int Nc, int G, cudaStream_t s) {
+template <int BN, bool T, bool A, int RM>
+int launch_linear_rm(const float* Ain, const float* B, const float* bias, float* C, int64_t R, int Kc, int Nc, int G, cudaStream_t s) {
   static bool attr = false;
   if (!attr) {
-    WF_CUDA(cudaFuncSetAttribute(linear_kernel<BN, T, A>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    WF_CUDA(cudaFuncSetAttribute(linear_kernel<BN, T, A, RM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     attr = true;
   }
-  constexpr int SL = LIN_THREADS / BN;
+  constexpr int SL = LIN_THREADS / BN, LROWS = 8 * RM;
   const int64_t tiles = ((R + LROWS - 1) / LROWS + SL - 1) / SL;
   const int grid = (int)(tiles < 2 * num_sms() ? tiles : 2 * num_sms());
-  linear_kernel<BN, T, A><<<grid, LIN_THREADS, smem_linear(Kc, BN), s>>>(Ain, B, bias, C, R, Kc, Nc, G);
+  linear_kernel<BN, T, A, RM><<<grid, LIN_THREADS, smem_linear(Kc, BN, LROWS), s>>>(Ain, B, bias, C, R, Kc, Nc, G);
   WF_LAUNCH_CHECK();
   return WF_OK;
+}
+template <int BN, bool T, bool A>
+int launch_linear_bn(const float* Ain, const float* B, const float* bias, float* C, int64_t R, int Kc, int Nc, int G, cudaStream_t s) {
+  // small batches: 16-row chunks so that the rows spread over 4x as many CTAs
+  const bool small = (R + 63) / 64 < (int64_t)num_sms() * (LIN_THREADS / BN);
+  return small ? launch_linear_rm<BN, T, A, 2>(Ain, B, bias, C, R, Kc, Nc, G, s)
+               : launch_linear_rm<BN, T, A, 8>(Ain, B, bias, C, R, Kc, Nc, G, s);
 }
 template <bool T, bool A>
 int launch_linear(const float* Ain, const float* B, const float* bias, float* C, int64_t R, int Kc, int Nc, int G, cudaStream_t s) {
@@ -830,8 +853,8 @@ void fill_wq_I(const wf_live_model* m, float* w) {
 
 template <int D>
 int run_chunk(const wf_live_model* m, const wf_live_tables* t, const float* params, const float* protons, int n_protons,
-              const float* x, int64_t N, float running_average, float inv_n, float* grad, float* psi, float* hpsi, float* eloc,
-              double* sums, float* ws, cudaStream_t s) {
+              const float* x, int64_t N, float running_average, const float* ra_dev, float inv_n, float* grad, float* psi, float* hpsi,
+              float* eloc, double* sums, float* ws, cudaStream_t s) {
   constexpr int G = D + 2;
   const int nn = n_nets_of(m), L = m->n_layers, DPm = max_DP(m);
   const int64_t R = N * G;
@@ -860,6 +883,7 @@ int run_chunk(const wf_live_model* m, const wf_live_tables* t, const float* para
   {
     int64_t base = 0;
     float* w = Wm;
+    MaskJobs jobs;
     for (int i = 0; i < nn; ++i) {
       const int P = net_P(m, i), DP = D * P;
       off[i] = net_offsets(D, P, base);
@@ -867,10 +891,11 @@ int run_chunk(const wf_live_model* m, const wf_live_tables* t, const float* para
       W1m[i] = w; w += D * HID;
       W2m[i] = w; w += HID * HID;
       W3m[i] = w; w += HID * DP;
-      mask_weights_kernel<<<(D * HID + 127) / 128, 128, 0, s>>>(params + off[i].W1, W1m[i], 1, D, D, HID);
-      mask_weights_kernel<<<(HID * HID + 127) / 128, 128, 0, s>>>(params + off[i].W2, W2m[i], 2, D, HID, HID);
-      mask_weights_kernel<<<(HID * DP + 127) / 128, 128, 0, s>>>(params + off[i].W3, W3m[i], 3, D, HID, DP);
+      jobs.src[3 * i] = off[i].W1; jobs.dst[3 * i] = W1m[i] - Wm; jobs.K[3 * i] = D; jobs.N[3 * i] = HID;
+      jobs.src[3 * i + 1] = off[i].W2; jobs.dst[3 * i + 1] = W2m[i] - Wm; jobs.K[3 * i + 1] = HID; jobs.N[3 * i + 1] = HID;
+      jobs.src[3 * i + 2] = off[i].W3; jobs.dst[3 * i + 2] = W3m[i] - Wm; jobs.K[3 * i + 2] = HID; jobs.N[3 * i + 2] = DP;
     }
+    mask_weights_kernel<<<dim3(8, 3 * nn), 256, 0, s>>>(params, Wm, jobs, D);
     WF_LAUNCH_CHECK();
   }
 
@@ -911,7 +936,7 @@ int run_chunk(const wf_live_model* m, const wf_live_tables* t, const float* para
   fa.x = x; fa.PHI = PHI; fa.LDbox = LDbox; fa.LDC = LDC; fa.N = N; fa.ldc_stride = R * D; fa.n_layers = L;
   fa.n_protons = n_protons;
   for (int i = 0; i < WF_MAX_D; ++i) fa.protons[i] = i < n_protons ? protons[i] : 0.f;
-  fa.running_average = running_average; fa.inv_n = inv_n;
+  fa.running_average = running_average; fa.inv_n = inv_n; fa.ra_dev = ra_dev;
   fa.PHIbar = PHIbar; fa.LDbar = LDbar; fa.psi = psi; fa.hpsi = hpsi; fa.eloc = eloc; fa.sums = sums;
   final_kernel<D><<<(int)((N + 127) / 128), 128, 0, s>>>(fa);
   WF_LAUNCH_CHECK();
@@ -960,9 +985,9 @@ extern "C" int64_t wf_vqmc_grad_workspace_floats(const wf_live_model* m, int64_t
 }
 
 extern "C" int wf_vqmc_loss_grad(const wf_live_model* m, const wf_live_tables* t, const float* params, const float* protons_host,
-                                 int n_protons, const float* x, int64_t N, float running_average, float inv_n_total, float* grad,
-                                 float* psi, float* hpsi, float* eloc, double* sums, float* workspace, int64_t workspace_floats,
-                                 void* stream) {
+                                 int n_protons, const float* x, int64_t N, float running_average, const float* running_average_dev,
+                                 float inv_n_total, float* grad, float* psi, float* hpsi, float* eloc, double* sums, float* workspace,
+                                 int64_t workspace_floats, void* stream) {
   const int st = check_model(m);
   if (st != WF_OK) return st;
   if (N == 0) return WF_OK;
@@ -983,21 +1008,21 @@ extern "C" int wf_vqmc_loss_grad(const wf_live_model* m, const wf_live_tables* t
     float* ec = eloc ? eloc + lo : nullptr;
     int r;
     switch (m->D) {
-      case 2: r = run_chunk<2>(m, t, params, protons_host, n_protons, xc, n, running_average, inv_n_total, grad, pc, hc, ec, sums, workspace, s); break;
-      case 3: r = run_chunk<3>(m, t, params, protons_host, n_protons, xc, n, running_average, inv_n_total, grad, pc, hc, ec, sums, workspace, s); break;
-      default: r = run_chunk<4>(m, t, params, protons_host, n_protons, xc, n, running_average, inv_n_total, grad, pc, hc, ec, sums, workspace, s); break;
+      case 2: r = run_chunk<2>(m, t, params, protons_host, n_protons, xc, n, running_average, running_average_dev, inv_n_total, grad, pc, hc, ec, sums, workspace, s); break;
+      case 3: r = run_chunk<3>(m, t, params, protons_host, n_protons, xc, n, running_average, running_average_dev, inv_n_total, grad, pc, hc, ec, sums, workspace, s); break;
+      default: r = run_chunk<4>(m, t, params, protons_host, n_protons, xc, n, running_average, running_average_dev, inv_n_total, grad, pc, hc, ec, sums, workspace, s); break;
     }
     if (r != WF_OK) return r;
   }
   return WF_OK;
 }
 
-extern "C" int wf_adam_step(float* params, float* m, float* v, const float* grad, int64_t n, int64_t step, float lr, float b1,
-                            float b2, float eps, void* stream) {
+extern "C" int wf_adam_step(float* params, float* m, float* v, const float* grad, int64_t n, int64_t step, const int64_t* step_dev,
+                            float lr, float b1, float b2, float eps, void* stream) {
   if (n == 0) return WF_OK;
   if (!params || !m || !v || !grad || n < 0 || step < 0) return WF_ERR_INVALID_ARG;
   const float c1 = 1.f - powf(b1, (float)(step + 1)), c2 = 1.f - powf(b2, (float)(step + 1));
-  adam_kernel<<<(int)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(params, m, v, grad, n, lr, b1, b2, eps, c1, c2);
+  adam_kernel<<<(int)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(params, m, v, grad, n, lr, b1, b2, eps, c1, c2, step_dev);
   WF_LAUNCH_CHECK();
   return WF_OK;
 }

@@ -69,8 +69,28 @@ def value_and_grad_efficient(params, psi, h_fn, batch, running_average, group=No
     return loss, (grad if flat_grad else _train.unravel(params, grad))
 
 
-def train_step_efficient(epoch, psi, h_fn, opt_update, opt_state, params, batch, running_average, group=None):
-    """vqmc.py:214-221: -> (opt_update(epoch, gradients, opt_state), loss_val)."""
+GRAPH_MAX_BATCH = 4096      # at or below this many walkers the step is launch-bound and is replayed from a CUDA graph
+_GRAPHS: dict = {}
+
+
+def train_step_efficient(epoch, psi, h_fn, opt_update, opt_state, params, batch, running_average, group=None, use_graph=None):
+    """vqmc.py:214-221: -> (opt_update(epoch, gradients, opt_state), loss_val).
+
+    Single-process steps on small batches (the reference trains with 128 / 256 walkers) are captured once per
+    (optimiser state, batch shape) in a CUDA graph and replayed (use_graph=False disables, True forces)."""
+    dist = torch.distributed
+    world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+    x = _live._ffi.f32(batch)
+    graphable = (world == 1 and getattr(opt_update, "graphable", False) and params is opt_state.tree
+                 and h_fn.wf_spec is not None)
+    if use_graph is None:
+        use_graph = graphable and x.shape[0] <= GRAPH_MAX_BATCH
+    if use_graph and graphable:
+        key = (id(opt_state), tuple(x.shape), str(x.device))
+        g = _GRAPHS.get(key)
+        if g is None or g.state is not opt_state:
+            g = _GRAPHS[key] = _train.GraphedTrainStep(h_fn.wf_spec, opt_state, opt_update, h_fn.protons, tuple(x.shape), x.device)
+        return opt_state, g(epoch, x, float(running_average))
     loss_val, gradients = value_and_grad_efficient(params, psi, h_fn, batch, running_average, group=group, opt_state=opt_state,
                                                    flat_grad=True)
     return opt_update(epoch, gradients, opt_state), loss_val
