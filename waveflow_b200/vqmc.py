@@ -52,21 +52,35 @@ def value_and_grad_efficient(params, psi, h_fn, batch, running_average, group=No
     x = _live._ffi.f32(batch)
     dev = x.device
     flat = _flat_of(params, opt_state, dev)
-    dist = torch.distributed
-    world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
-    n_total = x.shape[0]
-    if world > 1:
-        cnt = torch.tensor([x.shape[0]], dtype=torch.int64, device=dev)
-        dist.all_reduce(cnt, group=group)
-        n_total = int(cnt.item())
+    n_total = total_walkers(x.shape[0], dev, group)
     sums = torch.zeros(4, dtype=torch.float64, device=dev)
     grad, _ = _train.loss_grad(spec, flat, x, h_fn.protons, float(running_average), n_total=n_total, sums=sums)
-    if world > 1:
-        dist.all_reduce(grad, group=group)
-        dist.all_reduce(sums, group=group)
-    # the mean is over ALL walkers, as jnp.mean does (non-finite E_loc are not dropped by the reference; sums[2] counts the finite ones)
-    loss = (sums[0] / float(n_total)).to(torch.float32)
+    loss = reduce_loss_and_grad(grad, sums, n_total, group)
     return loss, (grad if flat_grad else _train.unravel(params, grad))
+
+
+def _world(group=None):
+    dist = torch.distributed
+    return dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+
+
+def total_walkers(n_local: int, device, group=None) -> int:
+    """Number of walkers over all ranks (the 1/N of the loss mean and of the gradient; shards may be ragged)."""
+    if _world(group) == 1:
+        return int(n_local)
+    cnt = torch.tensor([n_local], dtype=torch.int64, device=device)
+    torch.distributed.all_reduce(cnt, group=group)
+    return int(cnt.item())
+
+
+def reduce_loss_and_grad(grad: torch.Tensor, sums: torch.Tensor, n_total: int, group=None) -> torch.Tensor:
+    """The exchange step of the sharded training step: every rank evaluated its shard with the global 1/N, so the
+    flat gradients simply add; the loss is the mean over ALL walkers, as jnp.mean does (non-finite E_loc are not dropped by
+    the reference; sums[2] counts the finite ones).  In place on grad / sums; backend-agnostic (NCCL, gloo in the CPU test)."""
+    if _world(group) > 1:
+        torch.distributed.all_reduce(grad, group=group)
+        torch.distributed.all_reduce(sums, group=group)
+    return (sums[0] / float(n_total)).to(torch.float32)
 
 
 GRAPH_MAX_BATCH = 4096      # at or below this many walkers the step is launch-bound and is replayed from a CUDA graph
