@@ -113,4 +113,15 @@ __device__ __forceinline__ float lerp_tab(float yl, float yr, float np_, float d
   return fmaf((yr - yl) * np_, dx, yl);
 }
 
+// tanh / sigmoid through ex2.approx + rcp.approx (about 1e-7 absolute error, measured in tests/test_gpu_live.py):
+// the accurate libdevice versions cost ~3x the issue slots
+__device__ __forceinline__ float fast_tanh(float x) {
+  const float xc = fminf(fmaxf(x, -15.f), 15.f);
+  const float e = __expf(2.f * xc);
+  return 1.f - __fdividef(2.f, e + 1.f);
+}
+__device__ __forceinline__ float fast_sigmoid(float x) {
+  return __fdividef(1.f, 1.f + __expf(-x));
+}
+
 }  // namespace wf

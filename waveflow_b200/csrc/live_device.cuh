@@ -124,14 +124,7 @@ struct Ctx {
 
 // tanh / sigmoid through ex2.approx + rcp.approx (about 1e-7 absolute error, measured in tests/test_gpu_live.py):
 // the accurate libdevice versions cost ~3x the issue slots and the glue around the MLPs is issue bound.
-__device__ __forceinline__ float fast_tanh(float x) {
-  const float xc = fminf(fmaxf(x, -15.f), 15.f);
-  const float e = __expf(2.f * xc);
-  return 1.f - __fdividef(2.f, e + 1.f);
-}
-__device__ __forceinline__ float fast_sigmoid(float x) {
-  return __fdividef(1.f, 1.f + __expf(-x));
-}
+// (fast_tanh / fast_sigmoid live in common.cuh)
 
 // tanh on a 1-register bundle (MLP hidden layers): needs |grad|^2 on the Laplacian lane.
 template <int D, bool LAP>

@@ -32,22 +32,31 @@ __device__ __forceinline__ void load_row(const float* __restrict__ row, int K, f
   }
 }
 
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 // In place: unnormalised -> right knots.  a[j] <- knot_{j+1} (neural_splines.py:98-107 / :111-120); knot_0 = lo.
 // Also returns count = #{j in 0..K : x >= knot_j (+eps on the last)} (neural_splines.py:11-13).
-template <int KMAX>
-__device__ __forceinline__ int knots_inplace(float (&a)[KMAX], int K, float lo, float hi, float x) {
-  float mx = -INFINITY;
-#pragma unroll
-  for (int j = 0; j < KMAX; ++j)
-    if (j < K) mx = fmaxf(mx, a[j]);
+// mx = max_j a[j] (callers that already know it pass it in).  FULL: K == KMAX, every bound check folds at compile time.
+template <int KMAX, bool FULL>
+__device__ __forceinline__ int knots_impl(float (&a)[KMAX], int K_in, float lo, float hi, float x, float mx) {
+  const int K = FULL ? KMAX : K_in;
   // softmax through ex2.approx on pre-scaled arguments and one reciprocal: ~1e-7 relative on the widths, far inside the
-  // 1e-5 parity budget, and 3x fewer issue slots than expf + IEEE division per bin (this loop is the kernel's hot spot)
+  // 1e-5 parity budget, and 3x fewer issue slots than expf + IEEE division per bin (this loop is the kernel's hot spot);
+  // two interleaved partial sums halve the dependent-add chain
   constexpr float LOG2E = 1.4426950408889634f;
   const float mxs = mx * LOG2E;
-  float sum = 0.f;
+  float s0 = 0.f, s1 = 0.f;
 #pragma unroll
   for (int j = 0; j < KMAX; ++j)
-    if (j < K) { a[j] = exp2f(fmaf(a[j], LOG2E, -mxs)); sum += a[j]; }
+    if (j < K) {
+      a[j] = ex2_approx(fmaf(a[j], LOG2E, -mxs));
+      if (j & 1) s1 += a[j]; else s0 += a[j];
+    }
+  const float sum = s0 + s1;
   const float scale = (1.f - RQS_MIN_BIN * (float)K) / sum;
   const float span = hi - lo;
   float c = 0.f;
@@ -64,6 +73,18 @@ __device__ __forceinline__ int knots_inplace(float (&a)[KMAX], int K, float lo, 
       count += (x >= cmp) ? 1 : 0;
     }
   return count;
+}
+template <int KMAX>
+__device__ __forceinline__ int knots_inplace(float (&a)[KMAX], int K, float lo, float hi, float x, float mx) {
+  return K == KMAX ? knots_impl<KMAX, true>(a, K, lo, hi, x, mx) : knots_impl<KMAX, false>(a, K, lo, hi, x, mx);
+}
+template <int KMAX>
+__device__ __forceinline__ int knots_inplace(float (&a)[KMAX], int K, float lo, float hi, float x) {
+  float mx = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < KMAX; ++j)
+    if (j < K) mx = fmaxf(mx, a[j]);
+  return knots_inplace<KMAX>(a, K, lo, hi, x, mx);
 }
 
 template <int KMAX>
@@ -82,9 +103,8 @@ struct RqsBin { int idx; float cwl, in_w, chl, in_h; };
 
 // a/b: unnormalised widths/heights (destroyed: they become the right knots).
 template <int KMAX>
-__device__ __forceinline__ RqsBin rqs_locate(float x, float (&a)[KMAX], float (&b)[KMAX], int K, float B, bool inverse) {
-  const int cnt_w = knots_inplace<KMAX>(a, K, -B, B, x);
-  const int cnt_h = knots_inplace<KMAX>(b, K, -B, B, x);
+__device__ __forceinline__ RqsBin rqs_locate_counts(float x, const float (&a)[KMAX], const float (&b)[KMAX], int K, float B, bool inverse,
+                                                    int cnt_w, int cnt_h) {
   RqsBin r;
   r.idx = min(max((inverse ? cnt_h : cnt_w) - 1, 0), K - 1);
   float cwr, chr;
@@ -92,6 +112,20 @@ __device__ __forceinline__ RqsBin rqs_locate(float x, float (&a)[KMAX], float (&
   knot_pair<KMAX>(b, K, -B, r.idx, r.chl, chr);
   r.in_w = cwr - r.cwl; r.in_h = chr - r.chl;
   return r;
+}
+template <int KMAX>
+__device__ __forceinline__ RqsBin rqs_locate(float x, float (&a)[KMAX], float (&b)[KMAX], int K, float B, bool inverse) {
+  const int cnt_w = knots_inplace<KMAX>(a, K, -B, B, x);
+  const int cnt_h = knots_inplace<KMAX>(b, K, -B, B, x);
+  return rqs_locate_counts<KMAX>(x, a, b, K, B, inverse, cnt_w, cnt_h);
+}
+// same, for rows whose maxima are already known (the coupling layer's own 2B * softmax puts the maximum at exactly 2B / sum)
+template <int KMAX>
+__device__ __forceinline__ RqsBin rqs_locate(float x, float (&a)[KMAX], float (&b)[KMAX], int K, float B, bool inverse, float mx_a,
+                                             float mx_b) {
+  const int cnt_w = knots_inplace<KMAX>(a, K, -B, B, x, mx_a);
+  const int cnt_h = knots_inplace<KMAX>(b, K, -B, B, x, mx_b);
+  return rqs_locate_counts<KMAX>(x, a, b, K, B, inverse, cnt_w, cnt_h);
 }
 
 // ud0 / ud1: unnormalised derivatives at the two knots of the bin (interior entries idx-1 / idx; ignored at the ends,
@@ -141,21 +175,41 @@ __device__ __forceinline__ void rqs_eval(float x, float (&a)[KMAX], float (&b)[K
   rqs_finish(x, r, K, ud0, ud1, inverse, out, lad);
 }
 
+template <int KMAX, class DGet>
+__device__ __forceinline__ void rqs_eval(float x, float (&a)[KMAX], float (&b)[KMAX], int K, float B, bool inverse, float mx_a,
+                                         float mx_b, DGet dget, float& out, float& lad, int& bin) {
+  const RqsBin r = rqs_locate<KMAX>(x, a, b, K, B, inverse, mx_a, mx_b);
+  bin = r.idx;
+  const float ud0 = (r.idx == 0) ? 0.f : dget(r.idx - 1);
+  const float ud1 = (r.idx == K - 1) ? 0.f : dget(r.idx);
+  rqs_finish(x, r, K, ud0, ud1, inverse, out, lad);
+}
+
 // 2B * softmax(raw[0..K))  (neural_splines.py:260-261: the coupling layer's own normalisation, before RQS repeats it), in place
-template <int KP>
-__device__ __forceinline__ void softmax_2b(float (&a)[KP], int K, float twoB) {
+// Returns the maximum of the result: the largest input maps to exp(0) = 1 exactly, so it is exactly 2B / sum.
+template <int KP, bool FULL>
+__device__ __forceinline__ float softmax_2b_impl(float (&a)[KP], int K_in, float twoB) {
+  const int K = FULL ? KP : K_in;
   float mx = -INFINITY;
 #pragma unroll
   for (int j = 0; j < KP; ++j)
     if (j < K) mx = fmaxf(mx, a[j]);
-  float sum = 0.f;
+  float s0 = 0.f, s1 = 0.f;
 #pragma unroll
   for (int j = 0; j < KP; ++j)
-    if (j < K) { a[j] = __expf(a[j] - mx); sum += a[j]; }
-  const float s = twoB / sum;
+    if (j < K) {
+      a[j] = __expf(a[j] - mx);
+      if (j & 1) s1 += a[j]; else s0 += a[j];
+    }
+  const float s = twoB / (s0 + s1);
 #pragma unroll
   for (int j = 0; j < KP; ++j)
     if (j < K) a[j] *= s;
+  return s;
+}
+template <int KP>
+__device__ __forceinline__ float softmax_2b(float (&a)[KP], int K, float twoB) {
+  return K == KP ? softmax_2b_impl<KP, true>(a, K, twoB) : softmax_2b_impl<KP, false>(a, K, twoB);
 }
 
 }  // namespace wf

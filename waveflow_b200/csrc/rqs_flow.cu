@@ -48,7 +48,7 @@ __device__ __forceinline__ void dense_tanh(const float* __restrict__ W, const fl
       acc[2] = fmaf(in[i], w.z, acc[2]); acc[3] = fmaf(in[i], w.w, acc[3]);
     }
 #pragma unroll
-    for (int t = 0; t < 4; ++t) out[j0 + t] = tanhf(acc[t]);
+    for (int t = 0; t < 4; ++t) out[j0 + t] = fast_tanh(acc[t]);
   }
 }
 
@@ -162,8 +162,8 @@ __global__ void __launch_bounds__(CF_THREADS) coupling_flow_kernel(const __grid_
           float a[KP], b[KP];
           dense_out<HD, KP>(W3, b3, 0, 3 * KP, h2, a);
           dense_out<HD, KP>(W3, b3, KP, 3 * KP, h2, b);
-          softmax_2b<KP>(a, K, 2.f * B);
-          softmax_2b<KP>(b, K, 2.f * B);
+          const float mx_a = softmax_2b<KP>(a, K, 2.f * B);
+          const float mx_b = softmax_2b<KP>(b, K, 2.f * B);
           int bin;
           auto dget = [&](int jd) {      // softplus(raw derivative jd): one dot product with a per-thread column
             float acc = b3[2 * KP + jd];
@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(CF_THREADS) coupling_flow_kernel(const __grid_
             for (int i = 0; i < HD; ++i) acc = fmaf(h2[i], W3[i * 3 * KP + 2 * KP + jd], acc);
             return softplus_f(acc);
           };
-          rqs_eval<KP>(tj, a, b, K, B, P.inverse != 0, dget, out, lad, bin);
+          rqs_eval<KP>(tj, a, b, K, B, P.inverse != 0, mx_a, mx_b, dget, out, lad, bin);
         }
         logdet += lad;
 #pragma unroll
