@@ -74,7 +74,7 @@ def _workspace(spec: _live.LiveSpec, n: int, device, max_chunk: int) -> torch.Te
 
 def loss_grad(spec: _live.LiveSpec, flat: torch.Tensor, x: torch.Tensor, protons, running_average: float,
               n_total: int | None = None, grad: torch.Tensor | None = None, want=(), sums: torch.Tensor | None = None,
-              with_grad: bool = True, max_chunk: int = 16384, running_average_dev: torch.Tensor | None = None):
+              with_grad: bool = True, max_chunk: int = 65536, running_average_dev: torch.Tensor | None = None):
     """wf_vqmc_loss_grad -> (grad flat [n_params] (accumulated into `grad` when given), dict of the `want`ed outputs)."""
     x = _ffi.f32(x)
     N, dev = x.shape[0], x.device
