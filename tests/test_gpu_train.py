@@ -202,3 +202,38 @@ def test_graphed_step_equals_eager_step(cuda):
         res.append((opt_state.flat.clone(), losses))
     assert np.allclose(res[0][1], res[1][1], rtol=1e-5, atol=1e-6), (res[0][1], res[1][1])
     assert torch.allclose(res[0][0], res[1][0], rtol=1e-5, atol=1e-7)
+
+
+def test_loss_grad_edge_cases(cuda):
+    """Empty and single-walker batches, forward-only mode, and a model outside the supported set."""
+    from waveflow_b200 import _train
+    from waveflow_b200._ffi import WaveflowB200Error
+    m = fx.waveflow_model(3)
+    rng = np.random.default_rng(7)
+    params = fx.random_params(rng, m)
+    spec = spec_from_live(m)
+    flat = _train.ravel(fx.cast_params(params, np.float32), cuda)
+    prot = np.zeros((3, 1))
+    # empty batch: nothing launched, zero gradient
+    g, out = _train.loss_grad(spec, flat, torch.zeros(0, 3, device=cuda), prot, 0.0, want=("eloc",))
+    assert g.abs().max().item() == 0 and out["eloc"].numel() == 0
+    # one walker
+    x = _walkers(rng, 1, 3, -5, 5, model=m, params=fx.cast_params(params, np.float64), protons=prot)
+    _, g_ref = ograd.loss_and_grad(m, fx.cast_params(params, np.float64), x.astype(np.float64), prot, 0.1)
+    g, _ = _train.loss_grad(spec, flat, torch.from_numpy(x).to(cuda), prot, 0.1)
+    _compare(_train.unravel(params, g), g_ref)
+    # forward only: same psi / eloc as the gradient call, gradient buffer untouched
+    xs = torch.from_numpy(_walkers(rng, 33, 3, -5, 5)).to(cuda)
+    _, a = _train.loss_grad(spec, flat, xs, prot, 0.1, want=("psi", "eloc"))
+    gz, b = _train.loss_grad(spec, flat, xs, prot, 0.1, want=("psi", "eloc"), with_grad=False)
+    assert gz is None and torch.equal(a["psi"], b["psi"]) and torch.equal(a["eloc"], b["eloc"])
+    # the fused local-energy kernel and the layer-wise training path agree on psi and E_loc
+    from waveflow_b200 import _live
+    w = _live.pack_params(spec, to_torch_tree(fx.cast_params(params, np.float32), cuda)[0],
+                          to_torch_tree(fx.cast_params(params, np.float32), cuda)[1], cuda)
+    le = _live.local_energy(spec, w, xs, prot, want=("psi", "hpsi"))
+    assert torch.allclose(le["psi"], a["psi"], rtol=2e-4, atol=1e-6 * float(a["psi"].abs().max()))
+    # MFlow (M prior, no box) is not a wavefunction model: the entry point refuses it
+    mm = fx.mflow_model()
+    with pytest.raises(WaveflowB200Error):
+        _train.loss_grad(spec_from_live(mm), flat, xs[:, :2].contiguous(), np.zeros((2, 1)), 0.0)

@@ -86,6 +86,8 @@ def loss_grad(spec: _live.LiveSpec, flat: torch.Tensor, x: torch.Tensor, protons
     if with_grad and grad is None:
         grad = torch.zeros(nparam, dtype=torch.float32, device=dev)
     out = {k: torch.empty(N, dtype=torch.float32, device=dev) for k in ("psi", "hpsi", "eloc") if k in want}
+    if N == 0:                                   # empty shard: nothing to launch (a rank may own no walkers)
+        return grad, out
     prot = _ffi.host_f32(np.asarray(protons, dtype=np.float32).reshape(-1))
     ws = _workspace(spec, N, dev, max_chunk)
     tabs = _live._tables(spec, dev)
