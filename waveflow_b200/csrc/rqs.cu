@@ -95,7 +95,7 @@ rqs_staged_kernel(const float* __restrict__ inputs, const float* __restrict__ uw
       int bin = -1;
       if (inside) {
         const float* udr = ud + m * (K - 1);
-        rqs_eval<K>(xv, a, b, K, B, inverse != 0, [&](int j) { return __ldg(udr + j); }, out, lad, bin);
+        rqs_eval<K, true>(xv, a, b, K, B, inverse != 0, [&](int j) { return __ldg(udr + j); }, out, lad, bin);
       }
       stg_stream(outputs + m, out);
       stg_stream(logabsdet + m, lad);

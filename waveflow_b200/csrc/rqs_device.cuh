@@ -74,17 +74,19 @@ __device__ __forceinline__ int knots_impl(float (&a)[KMAX], int K_in, float lo, 
     }
   return count;
 }
-template <int KMAX>
+// FULL = true asserts K == KMAX (every bound check folds at compile time); callers that know K statically say so.
+template <int KMAX, bool FULL = false>
 __device__ __forceinline__ int knots_inplace(float (&a)[KMAX], int K, float lo, float hi, float x, float mx) {
-  return K == KMAX ? knots_impl<KMAX, true>(a, K, lo, hi, x, mx) : knots_impl<KMAX, false>(a, K, lo, hi, x, mx);
+  return knots_impl<KMAX, FULL>(a, K, lo, hi, x, mx);
 }
-template <int KMAX>
-__device__ __forceinline__ int knots_inplace(float (&a)[KMAX], int K, float lo, float hi, float x) {
+template <int KMAX, bool FULL = false>
+__device__ __forceinline__ int knots_inplace(float (&a)[KMAX], int K_in, float lo, float hi, float x) {
+  const int K = FULL ? KMAX : K_in;
   float mx = -INFINITY;
 #pragma unroll
   for (int j = 0; j < KMAX; ++j)
     if (j < K) mx = fmaxf(mx, a[j]);
-  return knots_inplace<KMAX>(a, K, lo, hi, x, mx);
+  return knots_impl<KMAX, FULL>(a, K, lo, hi, x, mx);
 }
 
 template <int KMAX>
@@ -113,19 +115,19 @@ __device__ __forceinline__ RqsBin rqs_locate_counts(float x, const float (&a)[KM
   r.in_w = cwr - r.cwl; r.in_h = chr - r.chl;
   return r;
 }
-template <int KMAX>
+template <int KMAX, bool FULL = false>
 __device__ __forceinline__ RqsBin rqs_locate(float x, float (&a)[KMAX], float (&b)[KMAX], int K, float B, bool inverse) {
-  const int cnt_w = knots_inplace<KMAX>(a, K, -B, B, x);
-  const int cnt_h = knots_inplace<KMAX>(b, K, -B, B, x);
-  return rqs_locate_counts<KMAX>(x, a, b, K, B, inverse, cnt_w, cnt_h);
+  const int cnt_w = knots_inplace<KMAX, FULL>(a, K, -B, B, x);
+  const int cnt_h = knots_inplace<KMAX, FULL>(b, K, -B, B, x);
+  return rqs_locate_counts<KMAX>(x, a, b, FULL ? KMAX : K, B, inverse, cnt_w, cnt_h);
 }
 // same, for rows whose maxima are already known (the coupling layer's own 2B * softmax puts the maximum at exactly 2B / sum)
-template <int KMAX>
+template <int KMAX, bool FULL = false>
 __device__ __forceinline__ RqsBin rqs_locate(float x, float (&a)[KMAX], float (&b)[KMAX], int K, float B, bool inverse, float mx_a,
                                              float mx_b) {
-  const int cnt_w = knots_inplace<KMAX>(a, K, -B, B, x, mx_a);
-  const int cnt_h = knots_inplace<KMAX>(b, K, -B, B, x, mx_b);
-  return rqs_locate_counts<KMAX>(x, a, b, K, B, inverse, cnt_w, cnt_h);
+  const int cnt_w = knots_inplace<KMAX, FULL>(a, K, -B, B, x, mx_a);
+  const int cnt_h = knots_inplace<KMAX, FULL>(b, K, -B, B, x, mx_b);
+  return rqs_locate_counts<KMAX>(x, a, b, FULL ? KMAX : K, B, inverse, cnt_w, cnt_h);
 }
 
 // ud0 / ud1: unnormalised derivatives at the two knots of the bin (interior entries idx-1 / idx; ignored at the ends,
@@ -165,20 +167,20 @@ __device__ __forceinline__ void rqs_finish(float x, const RqsBin& r, int K, floa
 }
 
 // dget(j), j in [0, K-2]: unnormalised interior derivative j.
-template <int KMAX, class DGet>
+template <int KMAX, bool FULL = false, class DGet>
 __device__ __forceinline__ void rqs_eval(float x, float (&a)[KMAX], float (&b)[KMAX], int K, float B, bool inverse,
                                          DGet dget, float& out, float& lad, int& bin) {
-  const RqsBin r = rqs_locate<KMAX>(x, a, b, K, B, inverse);
+  const RqsBin r = rqs_locate<KMAX, FULL>(x, a, b, K, B, inverse);
   bin = r.idx;
   const float ud0 = (r.idx == 0) ? 0.f : dget(r.idx - 1);
   const float ud1 = (r.idx == K - 1) ? 0.f : dget(r.idx);
   rqs_finish(x, r, K, ud0, ud1, inverse, out, lad);
 }
 
-template <int KMAX, class DGet>
+template <int KMAX, bool FULL = false, class DGet>
 __device__ __forceinline__ void rqs_eval(float x, float (&a)[KMAX], float (&b)[KMAX], int K, float B, bool inverse, float mx_a,
                                          float mx_b, DGet dget, float& out, float& lad, int& bin) {
-  const RqsBin r = rqs_locate<KMAX>(x, a, b, K, B, inverse, mx_a, mx_b);
+  const RqsBin r = rqs_locate<KMAX, FULL>(x, a, b, K, B, inverse, mx_a, mx_b);
   bin = r.idx;
   const float ud0 = (r.idx == 0) ? 0.f : dget(r.idx - 1);
   const float ud1 = (r.idx == K - 1) ? 0.f : dget(r.idx);
@@ -207,9 +209,9 @@ __device__ __forceinline__ float softmax_2b_impl(float (&a)[KP], int K_in, float
     if (j < K) a[j] *= s;
   return s;
 }
-template <int KP>
+template <int KP, bool FULL = false>
 __device__ __forceinline__ float softmax_2b(float (&a)[KP], int K, float twoB) {
-  return K == KP ? softmax_2b_impl<KP, true>(a, K, twoB) : softmax_2b_impl<KP, false>(a, K, twoB);
+  return softmax_2b_impl<KP, FULL>(a, K, twoB);
 }
 
 }  // namespace wf

@@ -55,9 +55,9 @@ struct RqsEpi {
         for (int i = 0; i < 32; ++i) b[c * 32 + i] = v[i] + __ldg(bj + CK + c * 32 + i);
       }
     }
-    const float mx_a = softmax_2b<CK>(a, CK, 2.f * B);   // neural_splines.py:260-261 (RQS repeats the softmax, quirk Q7)
-    const float mx_b = softmax_2b<CK>(b, CK, 2.f * B);
-    const RqsBin bin = rqs_locate<CK>(tc_, a, b, CK, B, inverse != 0, mx_a, mx_b);
+    const float mx_a = softmax_2b<CK, true>(a, CK, 2.f * B);   // neural_splines.py:260-261 (RQS repeats the softmax, quirk Q7)
+    const float mx_b = softmax_2b<CK, true>(b, CK, 2.f * B);
+    const RqsBin bin = rqs_locate<CK, true>(tc_, a, b, CK, B, inverse != 0, mx_a, mx_b);
     // the two derivative parameters of the located bin: columns 128 + idx - 1 and 128 + idx of this row
     float ud0 = 0.f, ud1 = 0.f;
     {
