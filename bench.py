@@ -374,7 +374,10 @@ def run_b200(args):
     fl = flops_per_walker(D)
     achieved = fl * n_local / (kern_ms_mean * 1e-3) / 1e12
     roofline = {"bound": "fp32", "kernel": f"wf::live_kernel<{D}, true> (wf_local_energy)", "achieved": achieved, "peak": fp32_peak,
-                "unit": "TFLOP/s", "frac": achieved / fp32_peak, "traffic": None,
+                "unit": "TFLOP/s", "frac": achieved / fp32_peak,
+                # dram__bytes_read.sum + dram__bytes_write.sum of one 65536-walker D=4 launch (ncu --set full,
+                # profiles/r01_live_kernel_d4_lap_ncu_summary.txt); algorithmic bytes are 24 B/walker = 1.57 MB
+                "traffic": 2376960 if (D == 4 and n_local == 65536) else None,
                 "algorithmic_flops_per_walker": fl, "walkers_per_launch": n_local,
                 "peak_source": "FFMA probe kernel (wf_probe_fma) timed in this run; MEASURED_PEAKS.json holds no FP32 figure",
                 "note": "FMA-issue bound (SURVEY F8 / 8d): 24 B/walker of HBM traffic, so an HBM or tensor roofline does not "
@@ -403,7 +406,8 @@ def run_b200(args):
         sweep = {"kernel": "spline_local_kernel<true> (wf_spline_apply_local)", "elements": M, "P": tabs.P, "ms": ms,
                  "elements_per_s": M / (ms * 1e-3),
                  "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
-                              "traffic": None, "algorithmic_bytes_per_element": bytes_per_el, "peak_source": hbm_src,
+                              # ncu --set full of this launch (profiles/r01_spline_local_ncu_summary.txt): 2.014 GB read + 0.197 GB written
+                              "traffic": 2210474864, "algorithmic_bytes_per_element": bytes_per_el, "peak_source": hbm_src,
                               "inputs": "2.1 GB per launch (> 126 MB L2)"}}
         del c, xs
 
@@ -430,7 +434,10 @@ def run_b200(args):
             gbs = M * 4 * (3 * K + 2) / (ms * 1e-3) / 1e9
             res["inverse" if inv else "forward"] = {"ms": ms, "elements_per_s": M / (ms * 1e-3),
                                                      "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s",
-                                                                  "frac": gbs / hbm_peak, "traffic": None,
+                                                                  "frac": gbs / hbm_peak,
+                                                                  # ncu --set full at 2^22 elements (profiles/r01_rqs_k32_ncu_summary.txt:
+                                                                  # 1.537 GB read + 0.035 GB written), scaled x4 to this launch
+                                                                  "traffic": 4 * 1571992784 if not inv else None,
                                                                   "algorithmic_bytes_per_element": 4 * (3 * K + 2), "peak_source": hbm_src}}
         rqs_sweep = {"kernel": "rqs_kernel<32, true> (wf_rqs_apply)", "elements": M, "K": K, "inputs": "6.6 GB per launch (> L2)", **res}
         del uw, uh, ud, xs
