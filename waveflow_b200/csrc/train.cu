@@ -127,14 +127,29 @@ __global__ void __launch_bounds__(LIN_THREADS) linear_kernel(const float* __rest
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const int n0 = h * (BN / 2) + tx * 4;
+        if ((Nc & 3) == 0) {                 // 128-bit stores (rows are 16-byte aligned when Nc % 4 == 0)
+          if (n0 < Nc) {
+            float4 v = make_float4(acc[i][h * 4], acc[i][h * 4 + 1], acc[i][h * 4 + 2], acc[i][h * 4 + 3]);
+            if (value_row) {
+              v.x += bias[n0]; v.y += bias[n0 + 1]; v.z += bias[n0 + 2]; v.w += bias[n0 + 3];   // bias blocks are only 4-byte aligned
+            }
+            float4* dst = reinterpret_cast<float4*>(C + r * Nc + n0);
+            if (ACCUM) {
+              const float4 o = *dst;
+              v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+            }
+            *dst = v;
+          }
+        } else {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int n = n0 + j;
-          if (n < Nc) {
-            float v = acc[i][h * 4 + j];
-            if (value_row) v += bias[n];
-            if (ACCUM) v += C[r * Nc + n];
-            C[r * Nc + n] = v;
+          for (int j = 0; j < 4; ++j) {
+            const int n = n0 + j;
+            if (n < Nc) {
+              float v = acc[i][h * 4 + j];
+              if (value_row) v += bias[n];
+              if (ACCUM) v += C[r * Nc + n];
+              C[r * Nc + n] = v;
+            }
           }
         }
       }
@@ -806,7 +821,7 @@ int launch_linear_bn(const float* Ain, const float* B, const float* bias, float*
   // small batches: 16-row chunks so that the rows spread over 4x as many CTAs
   const bool small = (R + 63) / 64 < (int64_t)num_sms() * (LIN_THREADS / BN);
   return small ? launch_linear_rm<BN, T, A, 2>(Ain, B, bias, C, R, Kc, Nc, G, s)
-               : launch_linear_rm<BN, T, A, 8>(Ain, B, bias, C, R, Kc, Nc, G, s);
+               : launch_linear_rm<BN, T, A, 4>(Ain, B, bias, C, R, Kc, Nc, G, s);
 }
 template <bool T, bool A>
 int launch_linear(const float* Ain, const float* B, const float* bias, float* C, int64_t R, int Kc, int Nc, int G, cudaStream_t s) {
