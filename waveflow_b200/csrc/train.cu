@@ -160,8 +160,8 @@ __global__ void __launch_bounds__(LIN_THREADS) linear_kernel(const float* __rest
 // partial[cta][Kc + 1][Nc] = sum over the CTA's rows of X[r][k] * dY[r][n]; row Kc = sum over the value rows (bias gradient).
 // Each slice accumulates an 8 (k) x 8 (n) block per thread over its own 16-row chunks; the slices are summed through
 // shared memory in a fixed order at the end.
-constexpr int WROWS = 16;
-template <int BN>
+// WROWS rows per slice chunk: 32 for large batches (half the barrier / load phases per row), 16 when the batch is small
+template <int BN, int WROWS>
 __global__ void __launch_bounds__(LIN_THREADS) wgrad_kernel(const float* __restrict__ X, const float* __restrict__ dY,
                                                             float* __restrict__ partial, int64_t R, int Kc, int Nc, int G) {
   extern __shared__ __align__(16) float sm[];
@@ -797,9 +797,9 @@ int smem_linear(int Kc, int BN, int lrows) {
   const int KcP = (Kc + 3) & ~3, SL = LIN_THREADS / BN;
   return (KcP * BN + SL * lrows * (KcP + 4)) * (int)sizeof(float);
 }
-int smem_wgrad(int BN) {
+int smem_wgrad(int BN, int wrows) {
   const int SL = LIN_THREADS / BN;
-  return (SL * (WROWS * (HID + 4) + WROWS * BN + WROWS) + (HID + 1) * BN) * (int)sizeof(float);
+  return (SL * (wrows * (HID + 4) + wrows * BN + wrows) + (HID + 1) * BN) * (int)sizeof(float);
 }
 
 template <int BN, bool T, bool A, int RM>
@@ -829,24 +829,27 @@ int launch_linear(const float* Ain, const float* B, const float* bias, float* C,
                   : launch_linear_bn<128, T, A>(Ain, B, bias, C, R, Kc, Nc, G, s);
 }
 
-template <int BN>
+template <int BN, int WROWS>
 int launch_wgrad_bn(const float* X, const float* dY, float* partial, int grid, int64_t R, int Kc, int Nc, int G, cudaStream_t s) {
   static bool attr = false;
   if (!attr) {
-    WF_CUDA(cudaFuncSetAttribute(wgrad_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    WF_CUDA(cudaFuncSetAttribute(wgrad_kernel<BN, WROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     attr = true;
   }
-  wgrad_kernel<BN><<<grid, LIN_THREADS, smem_wgrad(BN), s>>>(X, dY, partial, R, Kc, Nc, G);
+  wgrad_kernel<BN, WROWS><<<grid, LIN_THREADS, smem_wgrad(BN, WROWS), s>>>(X, dY, partial, R, Kc, Nc, G);
   WF_LAUNCH_CHECK();
   return WF_OK;
 }
 
 int launch_wgrad(const float* X, const float* dY, float* partial, float* gW, float* gb, int layer, int D, int64_t R, int Kc, int Nc,
                  int G, cudaStream_t s) {
-  const int64_t tiles = (R + 4 * WROWS - 1) / (4 * WROWS);
+  const bool small = (R + 127) / 128 < (int64_t)num_sms();
+  const int wrows = small ? 16 : 32;
+  const int64_t tiles = (R + 4 * wrows - 1) / (4 * wrows);
   const int grid = (int)(tiles < WGRAD_CTAS ? tiles : WGRAD_CTAS);
-  const int st = Nc <= 64 ? launch_wgrad_bn<64>(X, dY, partial, grid, R, Kc, Nc, G, s)
-                          : launch_wgrad_bn<128>(X, dY, partial, grid, R, Kc, Nc, G, s);
+  int st;
+  if (Nc <= 64) st = small ? launch_wgrad_bn<64, 16>(X, dY, partial, grid, R, Kc, Nc, G, s) : launch_wgrad_bn<64, 32>(X, dY, partial, grid, R, Kc, Nc, G, s);
+  else st = small ? launch_wgrad_bn<128, 16>(X, dY, partial, grid, R, Kc, Nc, G, s) : launch_wgrad_bn<128, 32>(X, dY, partial, grid, R, Kc, Nc, G, s);
   if (st != WF_OK) return st;
   const int tot = (Kc + 1) * Nc;
   wgrad_reduce_kernel<<<(tot + 31) / 32, 256, 0, s>>>(partial, grid, gW, gb, layer, D, Kc, Nc);
