@@ -124,7 +124,7 @@ typedef struct wf_live_model {
   int32_t has_box;      /* 1: BoxTransformLayer first (made.py:108-204)                                            */
   int32_t coord_mean;   /* 1: xu_coord_type == 'mean', 0: 'first'                                                  */
   int32_t bc_I;         /* bit0: left {0:0}, bit1: right {0:1}   (other constraint sets: operator-level path only) */
-  int32_t bc_P;         /* bit0: left {0:0}, bit1: right {0:0}                                                     */
+  int32_t bc_P;         /* bit0: left {0:0}, bit1: right {0:0}; bit2: B prior third layer pre-multiplied, see below      */
   float box;            /* box_side L                                                                              */
   float reg;            /* spline_regularization (made.py:68)                                                      */
   float tol;            /* reverse_fun_tol (made.py:44)                                                            */
@@ -151,7 +151,11 @@ typedef struct wf_live_tables {
  *   W1m [D][64] | b1 [64] | W2m [64][64] | b2 [64] | W3p [64][D][32] | b3p [D][32]
  * W*m have the MADE masks already applied (model_factory.py:8-19,31-33); W3p/b3p are the third layer re-ordered so
  * that the P coefficients of dimension d are contiguous (p[n,d,q] = o[n, q*D + d], model_factory.py:59-60) and padded
- * with zeros to 32.  Size per net: wf_live_net_floats(D).  The buffer must be 16-byte aligned. */
+ * with zeros to 32.  Size per net: wf_live_net_floats(D).  The buffer must be 16-byte aligned.
+ * B prior with bit 2 of bc_P set (wf_live_forward / wf_local_energy only; P_P <= 31): the prior net's W3p / b3p hold the third
+ * layer already multiplied by diag(boundary mask) @ ob_to_b (bsplines_jax.py:132-134,173-198 are linear in the conditioner
+ * output), i.e. the kernel receives the un-normalised B-spline coefficients directly, and column 31 of every dimension
+ * holds the weights of sum_p o_p (whose sign survives the conditioner's own normalisation, model_factory.py:69-70). */
 int64_t wf_live_net_floats(int D);
 
 /* Outputs selector: any of the output pointers of wf_live_forward may be NULL.

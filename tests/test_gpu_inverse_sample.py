@@ -14,7 +14,7 @@ def _setup(m, seed, device, scale=3.0):
     from waveflow_b200 import _live
     params = fx.random_params(np.random.default_rng(seed), m, scale=scale)
     spec = spec_from_live(m)
-    return params, spec, _live.pack_params(spec, params[0], params[1], device)
+    return params, spec, _live.pack_params(spec, params[0], params[1], device, fold_prior=False)
 
 
 @pytest.mark.parametrize("kind", ["mflow", "waveflow"])

@@ -44,8 +44,13 @@ def net_arrays(net):
     return W1, b1, W2, b2, W3, b3
 
 
-def pack_net(net, D: int, P: int, device) -> torch.Tensor:
-    """One conditioner -> flat float32 [wf_live_net_floats(D)] in the kernel's layout."""
+def pack_net(net, D: int, P: int, device, fold: torch.Tensor | None = None) -> torch.Tensor:
+    """One conditioner -> flat float32 [wf_live_net_floats(D)] in the kernel's layout.
+
+    fold (B prior only): the [P, P] matrix  diag(boundary mask) @ ob_to_b.  Everything between the third layer and the
+    un-normalised B-spline coefficients is linear (bsplines_jax.py:132-134, 173-198), so it is multiplied into W3 / b3 here,
+    once per parameter set, instead of once per walker and dimension in the kernel; column 31 of every dimension carries
+    sum_p o_p, whose sign the conditioner's own normalisation leaves behind (model_factory.py:69-70)."""
     W1, b1, W2, b2, W3, b3 = [torch.as_tensor(a, dtype=torch.float32, device=device) for a in net_arrays(net)]
     if W1.shape != (D, HIDDEN) or W2.shape != (HIDDEN, HIDDEN) or W3.shape != (HIDDEN, D * P):
         raise _ffi.WaveflowB200Error(f"unexpected conditioner shapes {tuple(W1.shape)}, {tuple(W2.shape)}, {tuple(W3.shape)} "
@@ -57,10 +62,18 @@ def pack_net(net, D: int, P: int, device) -> torch.Tensor:
     W1m, b1p = (W1 * m1)[:, perm], b1[perm]
     W2m, b2p = (W2 * m2)[perm][:, perm], b2[perm]
     W3m = (W3 * m3.repeat(1, P))[perm].reshape(HIDDEN, P, D).permute(0, 2, 1)    # [64, D, P]
+    b3m = b3.reshape(P, D).t()                                                     # [D, P]
     W3p = torch.zeros(HIDDEN, D, MAXP, dtype=torch.float32, device=device)
-    W3p[:, :, :P] = W3m
     b3p = torch.zeros(D, MAXP, dtype=torch.float32, device=device)
-    b3p[:, :P] = b3.reshape(P, D).t()
+    if fold is not None:
+        F = fold.to(device=device, dtype=torch.float64)
+        W3p[:, :, :P] = (W3m.double() @ F).float()
+        b3p[:, :P] = (b3m.double() @ F).float()
+        W3p[:, :, MAXP - 1] = W3m.double().sum(-1).float()
+        b3p[:, MAXP - 1] = b3m.double().sum(-1).float()
+    else:
+        W3p[:, :, :P] = W3m
+        b3p[:, :P] = b3m
     return torch.cat([W1m.reshape(-1), b1p.reshape(-1), W2m.reshape(-1), b2p.reshape(-1), W3p.reshape(-1), b3p.reshape(-1)])
 
 
@@ -129,15 +142,40 @@ class LiveSpec:
         return s
 
 
-def pack_params(spec: LiveSpec, transform_params, sp_params, device) -> torch.Tensor:
-    """Reference pytrees -> one flat device buffer: IMADE nets in order, then the prior net."""
+def pack_params(spec: LiveSpec, transform_params, sp_params, device, fold_prior: bool = True) -> torch.Tensor:
+    """Reference pytrees -> one flat device buffer: IMADE nets in order, then the prior net.
+
+    fold_prior: pre-multiply the B prior's third layer by mask @ ob_to_b (see pack_net); the returned tensor is tagged
+    `wf_folded` and wf_live_forward / wf_local_energy are told through bit 2 of bc_P.  The sampler / inverse kernels need the
+    raw conditioner outputs: pack with fold_prior=False for them."""
     nets = [p for p in transform_params if len(p)]
     if len(nets) != spec.n_layers:
         raise _ffi.WaveflowB200Error(f"expected {spec.n_layers} IMADE parameter blocks, got {len(nets)}")
     parts = [pack_net(n, spec.D, spec.tab_I.P, device) for n in nets]
+    folded = False
     if spec.prior is not None:
-        parts.append(pack_net(sp_params, spec.D, spec.tab_P.P, device))
-    return torch.cat(parts).contiguous()
+        fold = None
+        if fold_prior and spec.prior == "B" and spec.tab_P.P <= MAXP - 1 and _bc_bits_P(spec.bc_P_left, spec.bc_P_right) is not None:
+            P = spec.tab_P.P
+            mask = np.ones(P)
+            bits = _bc_bits_P(spec.bc_P_left, spec.bc_P_right)
+            if bits & 1:
+                mask[0] = 0.0
+            if bits & 2:
+                mask[P - 1] = 0.0
+            fold = torch.from_numpy(mask[:, None] * np.asarray(spec.tab_P.ob_to_b64, dtype=np.float64))
+            folded = True
+        parts.append(pack_net(sp_params, spec.D, spec.tab_P.P, device, fold=fold))
+    out = torch.cat(parts).contiguous()
+    out.wf_folded = folded
+    return out
+
+
+def _struct_for(spec: LiveSpec, weights) -> LiveModelStruct:
+    st = spec.struct()
+    if getattr(weights, "wf_folded", False):
+        st.bc_P |= 4
+    return st
 
 
 def _tables(spec: LiveSpec, device) -> _ffi.LiveTablesStruct:
@@ -167,7 +205,7 @@ def forward(spec: LiveSpec, weights: torch.Tensor, x: torch.Tensor, want=("u", "
     for k in ("logdet", "logpdf", "psi"):
         if k in want:
             out[k] = torch.empty(N, dtype=torch.float32, device=dev)
-    st = lib.wf_live_forward(C.byref(spec.struct()), C.byref(tabs), ptr(weights), ptr(x), N, ptr(out.get("u")),
+    st = lib.wf_live_forward(C.byref(_struct_for(spec, weights)), C.byref(tabs), ptr(weights), ptr(x), N, ptr(out.get("u")),
                              ptr(out.get("logdet")), ptr(out.get("logpdf")), ptr(out.get("psi")), stream_ptr())
     check(st, "wf_live_forward")
     return out
@@ -189,7 +227,7 @@ def local_energy(spec: LiveSpec, weights: torch.Tensor, x: torch.Tensor, protons
         out["grad"] = torch.empty(N, spec.D, dtype=torch.float32, device=dev)
     if sums is not None and (sums.dtype != torch.float64 or sums.numel() != 4):
         raise _ffi.WaveflowB200Error("sums must be a float64 tensor with 4 elements")
-    st = lib.wf_local_energy(C.byref(spec.struct()), C.byref(tabs), ptr(weights), _ffi.np_ptr(prot), int(prot.size), ptr(x),
+    st = lib.wf_local_energy(C.byref(_struct_for(spec, weights)), C.byref(tabs), ptr(weights), _ffi.np_ptr(prot), int(prot.size), ptr(x),
                              N, ptr(out.get("psi")), ptr(out.get("hpsi")), ptr(out.get("eloc")), ptr(out.get("grad")),
                              ptr(out.get("lap")), ptr(sums), stream_ptr())
     check(st, "wf_local_energy")
@@ -202,7 +240,7 @@ def inverse(spec: LiveSpec, weights: torch.Tensor, u: torch.Tensor, exact: bool 
     N = u.shape[0]
     x = torch.empty_like(u)
     tabs = _tables(spec, u.device)
-    st = lib.wf_live_inverse(C.byref(spec.struct()), C.byref(tabs), ptr(weights), ptr(u), N, int(bool(exact)), ptr(x), stream_ptr())
+    st = lib.wf_live_inverse(C.byref(_struct_for(spec, weights)), C.byref(tabs), ptr(weights), ptr(u), N, int(bool(exact)), ptr(x), stream_ptr())
     check(st, "wf_live_inverse")
     return x
 
@@ -212,7 +250,7 @@ def sample(spec: LiveSpec, weights: torch.Tensor, seed: int, n: int, device, exa
     x = torch.empty(n, spec.D, dtype=torch.float32, device=device)
     u = torch.empty(n, spec.D, dtype=torch.float32, device=device)
     tabs = _tables(spec, device)
-    st = lib.wf_live_sample(C.byref(spec.struct()), C.byref(tabs), ptr(weights), C.c_uint64(int(seed) & (2 ** 64 - 1)), n,
+    st = lib.wf_live_sample(C.byref(_struct_for(spec, weights)), C.byref(tabs), ptr(weights), C.c_uint64(int(seed) & (2 ** 64 - 1)), n,
                             int(bool(exact)), ptr(x), ptr(u), stream_ptr())
     check(st, "wf_live_sample")
     return x, u

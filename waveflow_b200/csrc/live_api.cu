@@ -37,6 +37,7 @@ int fill_params(const wf_live_model* m, const wf_live_tables* t, const float* we
   if (m->prior_kind != -1 && !pnet) return WF_ERR_INVALID_ARG;
   if (pnet && (!t->dense_P || m->P_P < 2 || m->P_P > WF_MAX_P)) return WF_ERR_INVALID_ARG;
   if (m->prior_kind == WF_KIND_B && !t->ob_to_b) return WF_ERR_INVALID_ARG;
+  if ((m->bc_P & 4) && (m->prior_kind != WF_KIND_B || m->P_P > WF_MAX_P - 1)) return WF_ERR_INVALID_ARG;   // folded prior layer
   if (m->prior_kind == WF_KIND_M && (!t->rec_P || !t->lo_P)) return WF_ERR_INVALID_ARG;
   if (m->has_box && !(m->box > 0.f)) return WF_ERR_INVALID_ARG;
   if ((reinterpret_cast<uintptr_t>(weights) & 15) || (reinterpret_cast<uintptr_t>(t->dense_I) & 15) ||
@@ -102,6 +103,7 @@ int fill_inverse(const wf_live_model* m, const wf_live_tables* t, const float* w
   const int st = fill_params(m, t, weights, &dummy, N, L);
   if (st != WF_OK) return st;
   if (m->n_layers > 0 && !(m->tol > 0.f)) return WF_ERR_INVALID_ARG;
+  if (m->bc_P & 4) return WF_ERR_INVALID_ARG;     // the sampler / inverse need the raw conditioner outputs (unfolded weights)
   const bool pnet = m->prior_kind == WF_KIND_B || m->prior_kind == WF_KIND_M;
   if (sample && !pnet) return WF_ERR_INVALID_ARG;
   if (sample && m->prior_kind == WF_KIND_B && !t->b_to_ob) return WF_ERR_INVALID_ARG;

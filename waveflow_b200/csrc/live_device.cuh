@@ -377,19 +377,25 @@ __device__ __forceinline__ void sigmoid_spline(const Ctx<D, LAP>& cx, const Scra
 template <int D, bool LAP>
 __device__ __forceinline__ J bprior_factor(const Ctx<D, LAP>& cx, const Scratch& S, int P, const float* __restrict__ wq,
                                            const float* __restrict__ ob_s, const float* __restrict__ tab, int T,
-                                           float xd_in, float xv) {
+                                           float xd_in, float xv, bool folded) {
   constexpr int NK = LAP ? 3 : 1;
   // clip(u, 0, 1): derivative 1 strictly inside, 0 outside
   const float xc = fminf(fmaxf(xv, 0.f), 1.f);
   const float xd = ((xv > 0.f) && (xv < 1.f)) ? xd_in : 0.f;
   const float np_ = (float)(T - 1);
   const NodeIdx n = node_index(xc, T);
+  // folded (bit 2 of bc_P): the host multiplied mask @ ob_to_b into the third layer, S[q] already holds c'_q and S[31] the
+  // sum of the raw outputs (the per-walker 32 x 32 product below is skipped)
   float osum = 0.f;
+  if (folded) {
+    osum = S[WF_MAX_P - 1];
+  } else {
 #pragma unroll 4
-  for (int q = 0; q < WF_MAX_P; ++q) {
-    const float o = S[q];
-    if (q < P) osum += o;
-    S[q] = o * wq[q];                     // wq is 0 beyond P and on the constrained ends
+    for (int q = 0; q < WF_MAX_P; ++q) {
+      const float o = S[q];
+      if (q < P) osum += o;
+      S[q] = o * wq[q];                     // wq is 0 beyond P and on the constrained ends
+    }
   }
   const float sgn = cx.bv(osum) < 0.f ? -1.f : 1.f;
   J A[NK];
@@ -399,12 +405,17 @@ __device__ __forceinline__ J bprior_factor(const Ctx<D, LAP>& cx, const Scratch&
 #pragma unroll 1
   for (int j0 = 0; j0 < P; j0 += 4) {
     float c[4] = {0.f, 0.f, 0.f, 0.f};
+    if (folded) {
+#pragma unroll
+      for (int t = 0; t < 4; ++t) c[t] = (j0 + t < P) ? S[j0 + t] : 0.f;
+    } else {
 #pragma unroll 8
-    for (int i = 0; i < WF_MAX_P; ++i) {
-      const float ow = S[i];
-      const float4 w4 = lds4(ob_s + i * WF_MAX_P + j0);
-      c[0] = fmaf(ow, w4.x, c[0]); c[1] = fmaf(ow, w4.y, c[1]);
-      c[2] = fmaf(ow, w4.z, c[2]); c[3] = fmaf(ow, w4.w, c[3]);
+      for (int i = 0; i < WF_MAX_P; ++i) {
+        const float ow = S[i];
+        const float4 w4 = lds4(ob_s + i * WF_MAX_P + j0);
+        c[0] = fmaf(ow, w4.x, c[0]); c[1] = fmaf(ow, w4.y, c[1]);
+        c[2] = fmaf(ow, w4.z, c[2]); c[3] = fmaf(ow, w4.w, c[3]);
+      }
     }
     float f[NK][4];
 #pragma unroll

@@ -181,7 +181,7 @@ __global__ void __launch_bounds__(LIVE_THREADS, 1) live_kernel(const __grid_cons
           // constrained dimensions (model_factory.py:124-129): 'mean' -> 0..D-2, 'first' -> 1..D-1
           const bool cons = M.coord_mean ? (d < D - 1) : (d >= 1);
           if (M.prior_kind == WF_KIND_B) {
-            J phi = bprior_factor<D, LAP>(cx, S, M.P_P, P.wq_P, ob_s, P.tab_P, M.T, xd, xv);
+            J phi = bprior_factor<D, LAP>(cx, S, M.P_P, P.wq_P, ob_s, P.tab_P, M.T, xd, xv, (M.bc_P & 4) != 0);
             if (!LAP) {
               float pr = phi.v * phi.v;
               if (cons) pr = pr / 2.f;

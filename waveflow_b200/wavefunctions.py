@@ -80,7 +80,7 @@ def Waveflow(transformation, sp_transformation, spline_degree, n_internal_knots,
             from . import _sampler
             if spec is None:
                 raise WaveflowB200Error("Waveflow.sample needs the fused configuration built by get_waveflow_model")
-            w = _live.pack_params(spec, params[0], params[1], torch.device(device))
+            w = _live.pack_params(spec, params[0], params[1], torch.device(device), fold_prior=False)
             return _sampler.sample(spec, w, rng, num_samples, torch.device(device), exact=exact_inverse)[0]
 
         psi.wf_spec = spec
