@@ -213,10 +213,26 @@ def run_b200(args):
         if flush is not None:
             flush.fill_(1.0)
 
+    # estimator exchange: one-shot all-reduce over NVLink peer memory (wf_p2p_allreduce_sums), NCCL if unavailable
+    exchange_kind = "none"
+    if world > 1:
+        exchange_kind = "nccl all_reduce"
+        if not args.nccl_exchange:
+            try:
+                est.peer = vqmc.PeerExchange(dev)
+                exchange_kind = "peer-memory one-shot kernel (wf_p2p_allreduce_sums)"
+            except Exception as exc:                                      # noqa: BLE001 -- any failure: keep NCCL
+                print(f"[bench] peer-memory exchange unavailable ({type(exc).__name__}: {exc}); using NCCL", file=sys.stderr)
+                est.peer = None
+        flag = torch.tensor([1 if est.peer is not None else 0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)                       # all ranks or none
+        if int(flag.item()) == 0:
+            est.peer = None
+            exchange_kind = "nccl all_reduce"
+
     def step(sums):
         est.local_sums(x_dev, sums)
-        if world > 1:
-            dist.all_reduce(sums)
+        return est.exchange(sums)
 
     # ---------------- device-timed region: K steps, inputs resident in HBM
     all_sums = torch.zeros(warm + steps, 4, dtype=torch.float64, device=dev)
@@ -237,8 +253,7 @@ def run_b200(args):
         a.record()
         est.local_sums(x_dev, all_sums[warm + i])
         k.record()                                   # end of the dominant kernel
-        if world > 1:
-            dist.all_reduce(all_sums[warm + i])
+        est.exchange(all_sums[warm + i])
         b.record()
     torch.cuda.synchronize()
     if world > 1:
@@ -255,9 +270,7 @@ def run_b200(args):
         xd = x_host.to(dev, non_blocking=True)
         s = torch.zeros(4, dtype=torch.float64, device=dev)
         h_fn(params, xd, return_all=True, sums=s, packed=est.packed)
-        if world > 1:
-            dist.all_reduce(s)
-        return s.cpu()
+        return est.exchange(s).cpu()
     for _ in range(warm):
         e2e_step()
     torch.cuda.synchronize()
@@ -570,7 +583,7 @@ def run_b200(args):
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": wl["name"], "description": wl["desc"], "walkers_total": wl["n_walkers"],
-                       "walkers_per_gpu": n_local, "parallelism": f"walker-sharded x{world}, 32-byte estimator all-reduce per step",
+                       "walkers_per_gpu": n_local, "parallelism": f"walker-sharded x{world}, 32-byte estimator all-reduce per step", "exchange": exchange_kind,
                        "l2": "flushed between timed steps (256 MiB fill outside the event brackets)" if flush is not None else "not flushed",
                        "timing": "CUDA events per step on the launch stream, summed over K steps, max over ranks"},
             "clocks": clk,
@@ -598,6 +611,7 @@ def main():
     ap.add_argument("--no-l2-flush", action="store_true")
     ap.add_argument("--no-sweep", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--nccl-exchange", action="store_true", help="use the NCCL all-reduce for the estimator sums instead of the peer-memory kernel")
     args = ap.parse_args()
     if os.environ.get("WF_BENCH_WATCHDOG"):          # debugging aid: dump every thread's stack and exit after N seconds
         import faulthandler

@@ -264,6 +264,19 @@ int wf_vqmc_loss_grad(const wf_live_model* model_host, const wf_live_tables* tab
 int wf_adam_step(float* params, float* m, float* v, const float* grad, int64_t n, int64_t step, const int64_t* step_dev, float lr,
                  float b1, float b2, float eps, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * Estimator exchange over NVLink peer memory (the all-reduce of vqmc.py's energy sums)
+ * ------------------------------------------------------------------------------------------------------------------ */
+
+/* One-shot all-reduce (sum) of 4 doubles between `world` ranks of one node.  peer_bufs_dev: device array of `world`
+ * pointers, entry r = rank r's symmetric buffer of wf_p2p_allreduce_buffer_bytes(world) bytes (zero-initialised, peer
+ * mapped; e.g. torch.distributed._symmetric_memory).  step: sequence number, 1, 2, 3, ... identical on all ranks.  Every
+ * rank stores {local[4], step} into its slot of every peer's buffer and sums the slots of its own buffer in rank order
+ * (bit-identical results everywhere); out[0..3] = NaN if a peer did not show up within ~2 s.  One 32-thread kernel. */
+int64_t wf_p2p_allreduce_buffer_bytes(int world);
+int wf_p2p_allreduce_sums(const uint64_t* peer_bufs_dev, int rank, int world, uint64_t step, const double* local, double* out,
+                          void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -82,6 +82,8 @@ _SIGS = {
     "wf_vqmc_loss_grad": (_i, [C.POINTER(LiveModelStruct), C.POINTER(LiveTablesStruct), _p, _p, _i, _p, _l, _f, _p, _f, _p, _p, _p,
                                _p, _p, _p, _l, _p]),
     "wf_adam_step": (_i, [_p, _p, _p, _p, _l, _l, _p, _f, _f, _f, _f, _p]),
+    "wf_p2p_allreduce_buffer_bytes": (_l, [_i]),
+    "wf_p2p_allreduce_sums": (_i, [_p, _i, _i, C.c_uint64, _p, _p, _p]),
     "wf_local_energy": (_i, [C.POINTER(LiveModelStruct), C.POINTER(LiveTablesStruct), _p, _p, _i, _p, _l, _p, _p, _p, _p, _p,
                              _p, _p]),
 }
