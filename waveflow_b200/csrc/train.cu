@@ -23,6 +23,7 @@ constexpr int HEAD_THREADS = 128;
 // ---------------------------------------------------------------------------------------------- MADE masks
 // model_factory.py:8-19: degrees in = arange(D), hidden = h % (D-1), out = d - 1; mask[in][out] = deg_out >= deg_in.
 __host__ __device__ inline bool made_mask(int layer, int D, int k, int n) {
+  if (layer == 0) return true;                    // no mask (folded prior layer: the mask is applied when unfolding)
   if (layer == 1) return (n % (D - 1)) >= k;
   if (layer == 2) return (n % (D - 1)) >= (k % (D - 1));
   return ((n % D) - 1) >= (k % (D - 1));
@@ -41,6 +42,47 @@ __global__ void mask_weights_kernel(const float* __restrict__ params, float* __r
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < K * N; i += gridDim.x * blockDim.x) {
     const int k = i / N, n = i % N;
     out[i] = made_mask(layer, D, k, n) ? W[i] : 0.f;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- folded prior layer
+// Everything between the prior conditioner's third layer and the un-normalised B-spline coefficients is linear
+// (boundary mask, ob_to_b: bsplines_jax.py:132-134,173-198), so it is multiplied into the layer once per step:
+//   Wf[h][q*D + d] = sum_p W3m[h][p*D + d] * F[p][q],  F = diag(mask) @ ob_to_b;   Wf[h][D*P + d] = sum_p W3m[h][p*D + d]
+// (row h = 64 is the bias).  The last D columns carry sum_p o_p, whose sign the conditioner's normalisation leaves behind.
+__global__ void fold_prior_kernel(const float* __restrict__ W3m, const float* __restrict__ b3, const float* __restrict__ ob_to_b,
+                                  int D, int P, float* __restrict__ Wf, float* __restrict__ bf) {
+  const int NcF = D * P + D;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (HID + 1) * NcF) return;
+  const int h = i / NcF, c = i % NcF;
+  const float* src = h < HID ? W3m + (size_t)h * D * P : b3;
+  float acc = 0.f;
+  if (c < D * P) {
+    const int q = c / D, d = c % D;
+    for (int p = 1; p < P - 1; ++p) acc = fmaf(src[p * D + d], __ldg(ob_to_b + p * P + q), acc);
+  } else {
+    const int d = c - D * P;
+    for (int p = 0; p < P; ++p) acc += src[p * D + d];
+  }
+  if (h < HID) Wf[(size_t)h * NcF + c] = acc; else bf[c] = acc;
+}
+// gW3[h][p*D + d] += mask3 * sum_q gWf[h][q*D + d] * F[p][q]   (the sum columns have zero gradient: a sign is piecewise constant)
+__global__ void unfold_prior_grad_kernel(const float* __restrict__ gWf, const float* __restrict__ gbf, const float* __restrict__ ob_to_b,
+                                         int D, int P, float* __restrict__ gW3, float* __restrict__ gb3) {
+  const int NcF = D * P + D, DP = D * P;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (HID + 1) * DP) return;
+  const int h = i / DP, c = i % DP;
+  const int p = c / D, d = c % D;
+  if (p == 0 || p == P - 1) return;                                  // masked end coefficients: no gradient
+  const float* src = h < HID ? gWf + (size_t)h * NcF : gbf;
+  float acc = 0.f;
+  for (int q = 0; q < P; ++q) acc = fmaf(src[q * D + d], __ldg(ob_to_b + p * P + q), acc);
+  if (h < HID) {
+    if (made_mask(3, D, h, c)) gW3[(size_t)h * DP + c] += acc;
+  } else {
+    gb3[c] += acc;
   }
 }
 
@@ -521,16 +563,13 @@ __global__ void __launch_bounds__(HEAD_THREADS) imade_bwd_kernel(const __grid_co
 
 // ---- prior head (wavefunctions.py:54-71)
 struct PriorArgs {
-  const float* O;        // [R][D*P]
+  const float* O;        // [R][D*P + D]: folded third layer (see fold_prior_kernel)
   const float* U;        // [R][D]
   const float* tab;      // orthonormalised tables, dense [T][4][32]
-  const float* ob_to_b;  // [P][P]
   int64_t N;
   int P, T;
   int cons_lo, cons_hi;  // dimensions [cons_lo, cons_hi) carry the 1/sqrt(2) (model_factory.py:124-129)
-  float mb[WF_MAX_P];    // 0 at the constrained end coefficients (bsplines_jax.py:173-198 with {0: 0} | {0: 0})
 };
-constexpr int MS_LD = 33;   // ob_to_b in shared memory, row stride 33: conflict-free by row and by column
 
 template <int D>
 struct PriorLane {
@@ -541,19 +580,13 @@ struct PriorLane {
 };
 
 template <int D>
-__device__ __forceinline__ void prior_lane_fwd(const PriorArgs& a, const float* Ms, int64_t n, int d, int lane, PriorLane<D>& L) {
-  const int P = a.P, DP = D * P;
-  // The conditioner divides by sum_p o_p even when negative outputs are allowed (model_factory.py:69-70); the L2
-  // normalisations that follow cancel its magnitude and keep its sign.
-  float sv = lane < P ? a.O[n * (D + 2) * (int64_t)DP + lane * D + d] : 0.f;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) sv += __shfl_xor_sync(0xffffffffu, sv, o);
+__device__ __forceinline__ void prior_lane_fwd(const PriorArgs& a, int64_t n, int d, int lane, PriorLane<D>& L) {
+  const int P = a.P, NcF = D * P + D;
+  // O is the FOLDED third layer: column q*D + d = c'_q (un-normalised B coefficients), column D*P + d = sum_p o_p, whose sign
+  // the conditioner's own normalisation leaves behind (model_factory.py:69-70; the L2 normalisations cancel its magnitude)
+  const float sv = a.O[n * (D + 2) * (int64_t)NcF + D * P + d];
   L.sign = sv < 0.f ? -1.f : 1.f;
-  // c' = (mask o) @ ob_to_b: lane q accumulates column q
-  L.cpre = jzero<D>();
-#pragma unroll 1
-  for (int p = 1; p < P - 1; ++p) jaxpy(L.cpre, Ms[p * MS_LD + lane], jload<D>(a.O, n, DP, p * D + d));
-  if (lane >= P) L.cpre = jzero<D>();
+  L.cpre = lane < P ? jload<D>(a.O, n, NcF, lane * D + d) : jzero<D>();
   L.S = warp_sum(jmul(L.cpre, L.cpre));
   L.nrm = jrsqrt(L.S);
   L.c = jmul(L.cpre, L.nrm);
@@ -569,41 +602,29 @@ __device__ __forceinline__ void prior_lane_fwd(const PriorArgs& a, const float* 
   L.phi = jscale(warp_sum(jmul(L.c, L.B0)), L.scale);
 }
 
-__device__ __forceinline__ void load_ob_to_b(const PriorArgs& a, float* Ms) {
-  for (int i = threadIdx.x; i < WF_MAX_P * MS_LD; i += blockDim.x) {
-    const int p = i / MS_LD, q = i % MS_LD;
-    Ms[i] = (p < a.P && q < a.P) ? a.ob_to_b[p * a.P + q] : 0.f;
-  }
-  __syncthreads();
-}
-
 template <int D>
 __global__ void __launch_bounds__(HEAD_THREADS) prior_fwd_kernel(const __grid_constant__ PriorArgs a, float* __restrict__ PHI) {
-  __shared__ float Ms[WF_MAX_P * MS_LD];
-  load_ob_to_b(a, Ms);
   const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (w >= a.N * D) return;
   const int64_t n = w / D;
   const int d = (int)(w % D);
   PriorLane<D> L;
-  prior_lane_fwd<D>(a, Ms, n, d, lane, L);
+  prior_lane_fwd<D>(a, n, d, lane, L);
   if (lane == 0) jstore<D>(PHI, n, D, d, L.phi);
 }
 
 template <int D>
 __global__ void __launch_bounds__(HEAD_THREADS) prior_bwd_kernel(const __grid_constant__ PriorArgs a, const float* __restrict__ PHIbar,
                                                                  float* __restrict__ Obar, float* __restrict__ Ubar) {
-  __shared__ float Ms[WF_MAX_P * MS_LD];
-  load_ob_to_b(a, Ms);
   const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (w >= a.N * D) return;
   const int64_t n = w / D;
   const int d = (int)(w % D);
-  const int P = a.P;
+  const int P = a.P, NcF = D * P + D;
   PriorLane<D> L;
-  prior_lane_fwd<D>(a, Ms, n, d, lane, L);
+  prior_lane_fwd<D>(a, n, d, lane, L);
   const Jet<D> phibar = jscale(jload<D>(PHIbar, n, D, d), L.scale);
   Jet<D> cbar = jzero<D>(), B0bar = jzero<D>(), ub = jzero<D>();
   jmul_bwd(L.B0, phibar, cbar);
@@ -619,16 +640,9 @@ __global__ void __launch_bounds__(HEAD_THREADS) prior_bwd_kernel(const __grid_co
   Jet<D> t = jzero<D>();
   jmul_bwd(L.cpre, Sbar, t);            // d(c*c) = 2 * (one-sided adjoint)
   jaxpy(cb, 2.f, t);
-  if (lane >= P) cb = jzero<D>();
-  // o_bar_p = mask_p * sum_q ob_to_b[p][q] cb_q : lane p gathers the cb of every lane q
-  Jet<D> ob = jzero<D>();
-#pragma unroll 1
-  for (int q = 0; q < P; ++q) jaxpy(ob, Ms[lane * MS_LD + q], warp_bcast(cb, q));
-  if (lane < P) {
-    if (a.mb[lane] == 0.f) ob = jzero<D>();
-    jstore<D>(Obar, n, D * P, lane * D + d, ob);
-  }
+  if (lane < P) jstore<D>(Obar, n, NcF, lane * D + d, cb);                 // adjoint of c'_q
   if (lane == 0) {
+    jstore<D>(Obar, n, NcF, D * P + d, jzero<D>());                         // the sign column has no gradient
     if (!L.inside) {
       const float keep = (L.uraw == L.uc.v) ? ucbar.v : 0.f;   // clip passes the gradient only where it did not clamp
       ucbar = jzero<D>();
@@ -764,7 +778,8 @@ NetOff net_offsets(int D, int P, int64_t base) {
 }
 int n_nets_of(const wf_live_model* m) { return m->n_layers + 1; }
 int net_P(const wf_live_model* m, int i) { return i < m->n_layers ? m->P_I : m->P_P; }
-int max_DP(const wf_live_model* m) { return m->D * (m->P_I > m->P_P ? m->P_I : m->P_P); }
+int prior_cols(const wf_live_model* m) { return m->D * m->P_P + m->D; }     // folded prior layer: D*P coefficients + D sign sums
+int max_DP(const wf_live_model* m) { const int a = m->D * m->P_I, b = prior_cols(m); return a > b ? a : b; }
 
 int check_model(const wf_live_model* m) {
   if (!m) return WF_ERR_INVALID_ARG;
@@ -778,13 +793,14 @@ int check_model(const wf_live_model* m) {
 
 constexpr int WGRAD_CTAS = 296;
 
-struct Fixed { int64_t wm, partial, total; };
+struct Fixed { int64_t wm, fold, partial, total; };
 Fixed fixed_floats(const wf_live_model* m) {
   Fixed f;
   f.wm = 0;
   for (int i = 0; i < n_nets_of(m); ++i) f.wm += (int64_t)m->D * HID + HID * HID + (int64_t)HID * m->D * net_P(m, i);
+  f.fold = 2 * (int64_t)(HID + 1) * ((prior_cols(m) + 3) & ~3);       // folded prior layer (Wf | bf) and its gradient (gWf | gbf)
   f.partial = (int64_t)WGRAD_CTAS * (HID + 1) * MAX_W;
-  f.total = f.wm + f.partial;
+  f.total = f.wm + f.fold + f.partial;
   return f;
 }
 int64_t per_row_floats(const wf_live_model* m) {
@@ -878,7 +894,12 @@ int run_chunk(const wf_live_model* m, const wf_live_tables* t, const float* para
   const int64_t R = N * G;
   const Fixed fx = fixed_floats(m);
   float* Wm = ws;
-  float* partial = Wm + fx.wm;
+  const int NcF = prior_cols(m), NcFp = (NcF + 3) & ~3;
+  float* Wf = Wm + fx.wm;                        // [64][NcF] folded prior third layer
+  float* bf = Wf + (int64_t)HID * NcFp;          // [NcF]
+  float* gWf = bf + NcFp;                        // gradient of the folded layer, same shapes
+  float* gbf = gWf + (int64_t)HID * NcFp;
+  float* partial = Wm + fx.wm + fx.fold;
   float* p = partial + fx.partial;
   auto take = [&](int64_t n) { float* q = p; p += (n + 3) & ~(int64_t)3; return q; };   // keeps every array 16-byte aligned
   float* U[WF_MAX_LAYERS + 2];
@@ -914,6 +935,7 @@ int run_chunk(const wf_live_model* m, const wf_live_tables* t, const float* para
       jobs.src[3 * i + 2] = off[i].W3; jobs.dst[3 * i + 2] = W3m[i] - Wm; jobs.K[3 * i + 2] = HID; jobs.N[3 * i + 2] = DP;
     }
     mask_weights_kernel<<<dim3(8, 3 * nn), 256, 0, s>>>(params, Wm, jobs, D);
+    fold_prior_kernel<<<((HID + 1) * NcF + 127) / 128, 128, 0, s>>>(W3m[nn - 1], params + off[nn - 1].b3, t->ob_to_b, D, m->P_P, Wf, bf);
     WF_LAUNCH_CHECK();
   }
 
@@ -921,10 +943,9 @@ int run_chunk(const wf_live_model* m, const wf_live_tables* t, const float* para
   ha.tab = t->dense_I; ha.N = N; ha.P = m->P_I; ha.T = m->T; ha.reg = m->reg;
   fill_wq_I(m, ha.wq);
   PriorArgs pa;
-  pa.tab = t->dense_P; pa.ob_to_b = t->ob_to_b; pa.N = N; pa.P = m->P_P; pa.T = m->T;
+  pa.tab = t->dense_P; pa.N = N; pa.P = m->P_P; pa.T = m->T;
   pa.cons_lo = m->coord_mean ? 0 : 1;
   pa.cons_hi = m->coord_mean ? D - 1 : D;
-  for (int q = 0; q < WF_MAX_P; ++q) pa.mb[q] = (q > 0 && q < m->P_P - 1) ? 1.f : 0.f;
 
   const int eb = 256;
   const int64_t nh = N * HID, nd = N * D;
@@ -940,7 +961,9 @@ int run_chunk(const wf_live_model* m, const wf_live_tables* t, const float* para
     tanh_fwd_kernel<D><<<(int)((nh + eb - 1) / eb), eb, 0, s>>>(Z1[i], H1[i], N);
     if ((st = launch_linear<false, false>(H1[i], W2m[i], params + off[i].b2, Z2[i], R, HID, HID, G, s)) != WF_OK) return st;
     tanh_fwd_kernel<D><<<(int)((nh + eb - 1) / eb), eb, 0, s>>>(Z2[i], H2[i], N);
-    if ((st = launch_linear<false, false>(H2[i], W3m[i], params + off[i].b3, O[i], R, HID, DP, G, s)) != WF_OK) return st;
+    if (i < L) st = launch_linear<false, false>(H2[i], W3m[i], params + off[i].b3, O[i], R, HID, DP, G, s);
+    else st = launch_linear<false, false>(H2[i], Wf, bf, O[i], R, HID, NcF, G, s);          // folded prior layer
+    if (st != WF_OK) return st;
     if (i < L) {
       ha.O = O[i]; ha.U = U[i];
       imade_fwd_kernel<D><<<hb, HEAD_THREADS, 0, s>>>(ha, U[i + 1], LDC + (int64_t)i * R * D);
@@ -974,8 +997,17 @@ int run_chunk(const wf_live_model* m, const wf_live_tables* t, const float* para
     }
     WF_LAUNCH_CHECK();
     int st;
-    if ((st = launch_wgrad(H2[i], Obar, partial, grad + off[i].W3, grad + off[i].b3, 3, D, R, HID, DP, G, s)) != WF_OK) return st;
-    if ((st = launch_linear<true, false>(Obar, W3m[i], nullptr, HbA, R, DP, HID, G, s)) != WF_OK) return st;
+    if (i == L) {
+      // folded prior layer: gradient w.r.t. (Wf | bf) without a mask, then mapped back to (W3 | b3) through F^T and the MADE mask
+      WF_CUDA(cudaMemsetAsync(gWf, 0, sizeof(float) * (size_t)(HID + 1) * NcFp, s));   // gWf | gbf
+      if ((st = launch_wgrad(H2[i], Obar, partial, gWf, gbf, 0, D, R, HID, NcF, G, s)) != WF_OK) return st;
+      unfold_prior_grad_kernel<<<((HID + 1) * DP + 127) / 128, 128, 0, s>>>(gWf, gbf, t->ob_to_b, D, P, grad + off[i].W3, grad + off[i].b3);
+      WF_LAUNCH_CHECK();
+      if ((st = launch_linear<true, false>(Obar, Wf, nullptr, HbA, R, NcF, HID, G, s)) != WF_OK) return st;
+    } else {
+      if ((st = launch_wgrad(H2[i], Obar, partial, grad + off[i].W3, grad + off[i].b3, 3, D, R, HID, DP, G, s)) != WF_OK) return st;
+      if ((st = launch_linear<true, false>(Obar, W3m[i], nullptr, HbA, R, DP, HID, G, s)) != WF_OK) return st;
+    }
     tanh_bwd_kernel<D><<<(int)((nh + eb - 1) / eb), eb, 0, s>>>(Z2[i], HbA, N);
     if ((st = launch_wgrad(H1[i], HbA, partial, grad + off[i].W2, grad + off[i].b2, 2, D, R, HID, HID, G, s)) != WF_OK) return st;
     if ((st = launch_linear<true, false>(HbA, W2m[i], nullptr, HbB, R, HID, HID, G, s)) != WF_OK) return st;
