@@ -529,7 +529,7 @@ def run_b200(args):
                  "walkers_per_s": wl["n_walkers"] / (ms * 1e-3), "loss": train_loss,
                  "exchange": "none" if world == 1 else f"all-reduce of the flat gradient ({opt_state.flat.numel()} floats) + 32-byte loss sums per step",
                  "algorithmic_tflops_per_gpu": tfl, "frac_of_measured_fp32_fma": tfl / fp32_peak,
-                 "gpu_launches_per_step": 74 * ((n_local + 65535) // 65536) + 1}
+                 "gpu_launches_per_step": 76 * ((n_local + 65535) // 65536) + 1}
         if world == 1:
             # the reference's own training configuration (BASELINE configs[1]): He, batch 256 -- launch-bound, CUDA-graph replay
             from waveflow_b200 import _train
