@@ -22,8 +22,7 @@ ws = list(_train._WS.values())[0]
 G = D + 2
 R = N * G
 nn = 4
-wm = sum(D * 64 + 64 * 64 + 64 * D * P for P in (29, 29, 29, 28))
-fixed = wm + 296 * 65 * 128
+fixed = int(_ffi.lib.wf_vqmc_grad_workspace_floats(C.byref(spec.struct()), 0)) - 512      # masked weights | folded prior | partials
 U = [ws[fixed + i * R * D: fixed + (i + 1) * R * D].view(N, G, D)[:, 0, :].cpu().numpy() for i in range(nn)]
 p64 = fx.cast_params(params, np.float64); p32 = fx.cast_params(params, np.float32)
 m32 = m.cast(np.float32)
