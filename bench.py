@@ -300,7 +300,7 @@ def run_b200(args):
         tparams = get_params(opt_state)
 
         def tstep(i):
-            return vqmc.train_step_efficient(i, psi, h_fn, opt_update, opt_state, tparams, x_dev, 0.0)
+            return vqmc.train_step_efficient(i, psi, h_fn, opt_update, opt_state, tparams, x_dev, 0.0, n_total=wl["n_walkers"])
         for i in range(3):
             tstep(i)
         torch.cuda.synchronize()

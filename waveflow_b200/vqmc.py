@@ -40,11 +40,14 @@ def _flat_of(params, opt_state, device):
     return _train.ravel(params, device)
 
 
-def value_and_grad_efficient(params, psi, h_fn, batch, running_average, group=None, opt_state=None, flat_grad=False):
+def value_and_grad_efficient(params, psi, h_fn, batch, running_average, group=None, opt_state=None, flat_grad=False,
+                             n_total=None):
     """value_and_grad(loss_fn_efficient, argnums=0)(params, psi, h_fn, batch, running_average)  (vqmc.py:220).
 
     -> (loss, gradients in the structure of `params`).  With torch.distributed initialised, `batch` is this rank's shard of
     the walkers: the loss sums and the flat gradient are all-reduced, so every rank gets the global result.
+    n_total: number of walkers over all ranks when the caller knows it (saves the count all-reduce and its host
+    synchronisation every step; shards may be ragged, so it is not inferred).
     """
     spec = h_fn.wf_spec
     if spec is None:
@@ -52,7 +55,7 @@ def value_and_grad_efficient(params, psi, h_fn, batch, running_average, group=No
     x = _live._ffi.f32(batch)
     dev = x.device
     flat = _flat_of(params, opt_state, dev)
-    n_total = total_walkers(x.shape[0], dev, group)
+    n_total = int(n_total) if n_total is not None else total_walkers(x.shape[0], dev, group)
     sums = torch.zeros(4, dtype=torch.float64, device=dev)
     grad, _ = _train.loss_grad(spec, flat, x, h_fn.protons, float(running_average), n_total=n_total, sums=sums)
     loss = reduce_loss_and_grad(grad, sums, n_total, group)
@@ -87,7 +90,8 @@ GRAPH_MAX_BATCH = 4096      # at or below this many walkers the step is launch-b
 _GRAPHS: dict = {}
 
 
-def train_step_efficient(epoch, psi, h_fn, opt_update, opt_state, params, batch, running_average, group=None, use_graph=None):
+def train_step_efficient(epoch, psi, h_fn, opt_update, opt_state, params, batch, running_average, group=None, use_graph=None,
+                         n_total=None):
     """vqmc.py:214-221: -> (opt_update(epoch, gradients, opt_state), loss_val).
 
     Single-process steps on small batches (the reference trains with 128 / 256 walkers) are captured once per
@@ -106,7 +110,7 @@ def train_step_efficient(epoch, psi, h_fn, opt_update, opt_state, params, batch,
             g = _GRAPHS[key] = _train.GraphedTrainStep(h_fn.wf_spec, opt_state, opt_update, h_fn.protons, tuple(x.shape), x.device)
         return opt_state, g(epoch, x, float(running_average))
     loss_val, gradients = value_and_grad_efficient(params, psi, h_fn, batch, running_average, group=group, opt_state=opt_state,
-                                                   flat_grad=True)
+                                                   flat_grad=True, n_total=n_total)
     return opt_update(epoch, gradients, opt_state), loss_val
 
 
