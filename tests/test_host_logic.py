@@ -58,3 +58,22 @@ def test_pack_net_masks_sort_and_prior_fold():
     assert np.abs(folded[:, :, :P] - want).max() < 1e-4 * np.abs(want).max()
     assert np.abs(folded[:, :, 31] - o.sum(-1)).max() < 1e-4 * np.abs(o.sum(-1)).max()
     assert not _live.pack_params(spec, params[0], params[1], torch.device("cpu"), fold_prior=False).wf_folded
+
+
+def test_reference_arm_prints_one_json_line():
+    """bench.py --impl reference (the CPU arm the driver runs next to ours): one JSON line with the contract's keys."""
+    import json
+    import subprocess
+    import sys
+    from pathlib import Path
+    root = Path(__file__).resolve().parents[1]
+    r = subprocess.run([sys.executable, str(root / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=600, cwd=root)
+    assert r.returncode == 0, r.stderr[-500:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "vqmc_local_energy_walkers_per_s" and d["unit"] == "walkers/s"
+    assert d["value"] > 0 and d["higher_is_better"] is True and d["cpu_baseline"]["kind"] == "port"
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    assert d["config"]["workload"] == "vqmc_c4"
