@@ -239,7 +239,8 @@ int wf_rqs_coupling_flow_tc(const float* weights, int n_layers, float tail_bound
  * with P = P_I for the flow and P_P for the prior, i.e. the leaves of the reference's parameter pytree in traversal order
  * (zero_params, model_factory.py:83-84, is unused by this configuration: read by nothing, gradient 0).
  * Gradients use the same layout.  Returns the number of floats, or -1 for an unsupported model.
- * Supported: Waveflow models (B prior, BoxTransformLayer, constraints {0:0}|{0:1} / {0:0}|{0:0}), D in 2..4, D*P <= 128. */
+ * Supported: Waveflow models (B prior, BoxTransformLayer, constraints {0:0}|{0:1} / {0:0}|{0:0}), D in 2..4, D*P_I <= 128 and
+ * D*P_P + D <= 128 (the prior's third layer is evaluated pre-multiplied by mask @ ob_to_b plus D sign-sum columns). */
 int64_t wf_vqmc_param_floats(const wf_live_model* model_host);
 
 /* Floats of scratch needed to process `walkers` walkers in one chunk (activation jets of every layer). */
