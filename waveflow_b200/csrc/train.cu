@@ -224,6 +224,8 @@ __global__ void __launch_bounds__(LIN_THREADS) wgrad_kernel(const float* __restr
     for (int i = 0; i < 8; ++i) acc[i][j] = 0.f;
   }
   const bool xvec = Kc == HID, yvec = (Nc & 3) == 0;
+  if (!xvec)
+    for (int i = ts; i < WROWS * LDX; i += TS) Xs[i] = 0.f;      // zero padding of the narrow-input case (slice-private)
   const int64_t chunks = (R + WROWS - 1) / WROWS;
   for (int64_t ch = (int64_t)blockIdx.x * SL + slice; ch < chunks; ch += (int64_t)gridDim.x * SL) {
     const int64_t r0 = ch * WROWS;
@@ -237,9 +239,10 @@ __global__ void __launch_bounds__(LIN_THREADS) wgrad_kernel(const float* __restr
         *reinterpret_cast<float4*>(Xs + rl * LDX + 4 * k4) = v;
       }
     } else {
-      for (int i = ts; i < WROWS * HID; i += TS) {
-        const int rl = i / HID, k = i % HID;
-        Xs[rl * LDX + k] = (rl < rows && k < Kc) ? X[(r0 + rl) * Kc + k] : 0.f;
+      // narrow input (the first layer: Kc = D): only the Kc live columns are refreshed, the padding was zeroed once above
+      for (int i = ts; i < WROWS * Kc; i += TS) {
+        const int rl = i / Kc, k = i % Kc;
+        Xs[rl * LDX + k] = rl < rows ? X[(r0 + rl) * Kc + k] : 0.f;
       }
     }
     if (yvec) {
