@@ -77,3 +77,17 @@ def test_reference_arm_prints_one_json_line():
     assert d["value"] > 0 and d["higher_is_better"] is True and d["cpu_baseline"]["kind"] == "port"
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     assert d["config"]["workload"] == "vqmc_c4"
+
+
+def test_helpers_running_statistics():
+    """utils/helpers.py:122-135: moving_average and the edge-padded sliding mean."""
+    from waveflow_b200.utils import helpers
+    assert helpers.moving_average(2.0, 4.0, 0.25) == 2.5
+    x = np.arange(10, dtype=float) ** 2
+    w = 4
+    got = helpers.uniform_sliding_average(x, w)
+    padded = np.concatenate([np.full(w - 1, x[0]), x])
+    want = np.array([padded[i:i + w].mean() for i in range(len(x))])
+    assert got.shape == x.shape and np.allclose(got, want)
+    x2 = np.stack([x, 2 * x])
+    assert np.allclose(helpers.uniform_sliding_average(x2, w)[1], 2 * want)
