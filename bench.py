@@ -590,7 +590,7 @@ def run_b200(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(x_host.numel() * 4) * world,
                     "d2h_bytes_per_step": 32, "api": "utils.physics.construct_hamiltonian_function(psi, protons)(params, walkers)",
                     "ms_per_step": e2e_s / steps * 1e3},
-            "gpu_launches": steps,
+            "gpu_launches": steps * (2 if (world > 1 and est.peer is not None) else 1),     # live_kernel (+ p2p_allreduce_kernel)
             "kernel_ms_per_step": kern_ms_mean, "wall_s_timed_region": t_wall,
             "roofline": roofline, "cpu_baseline": cpu, "spline_sweep": sweep, "rqs_sweep": rqs_sweep, "coupling_flow_sweep": coupling, "tc_coupling_flow_sweep": tc_sweep, "flow_scaling": flow_scaling, "train_step": train,
             "energy_estimate": {"mean": float(s[0] / s[2]), "n": int(s[2])}}
