@@ -104,10 +104,18 @@ int wf_spline_reverse(const float* dense_t, int T, int P, const float* c, const 
                       float* out, int32_t* n_iter, void* stream);
 
 /* unconstrained_RQS (flows/bijections/neural_splines.py:16-71,74-184): rational-quadratic spline with K bins on
- * [-tail_bound, tail_bound], identity tails.  inputs [M], uw/uh [M][K], ud [M][K-1] (unnormalised); inverse != 0 runs
- * the inverse branch and returns -logabsdet.  bin_idx (nullable, int32 [M]) receives the located bin (-1 in the tails). */
+ * [-tail_bound, tail_bound], identity tails.  inputs [M], uw/uh [M][K], ud [M][K-1] (unnormalised).
+ * flags: WF_RQS_INVERSE runs the inverse branch and returns -logabsdet (the reference's `inverse=True`);
+ *        WF_RQS_EXACT_BINS evaluates the knot positions with exactly the float32 operation sequence of the reference's
+ *        arithmetic (neural_splines.py:98-107: softmax with a correctly rounded exp, sequential cumsum, no fused
+ *        multiply-adds), so bin_idx is bit-identical to it for every input; the default path computes the softmax with
+ *        ex2.approx and one reciprocal (knots within ~1e-7 relative: an input closer than that to a knot may be assigned
+ *        the neighbouring bin -- both are continuous there, outputs agree to float32 accuracy).
+ * bin_idx (nullable, int32 [M]) receives the located bin (-1 in the tails). */
+#define WF_RQS_INVERSE 1
+#define WF_RQS_EXACT_BINS 2
 int wf_rqs_apply(const float* inputs, const float* uw, const float* uh, const float* ud, int64_t M, int K,
-                 float tail_bound, int inverse, float* outputs, float* logabsdet, int32_t* bin_idx, void* stream);
+                 float tail_bound, int flags, float* outputs, float* logabsdet, int32_t* bin_idx, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Fused flows.
@@ -273,10 +281,19 @@ int wf_adam_step(float* params, float* m, float* v, const float* grad, int64_t n
  * pointers, entry r = rank r's symmetric buffer of wf_p2p_allreduce_buffer_bytes(world) bytes (zero-initialised, peer
  * mapped; e.g. torch.distributed._symmetric_memory).  step: sequence number, 1, 2, 3, ... identical on all ranks.  Every
  * rank stores {local[4], step} into its slot of every peer's buffer and sums the slots of its own buffer in rank order
- * (bit-identical results everywhere); out[0..3] = NaN if a peer did not show up within ~2 s.  One 32-thread kernel. */
+ * (bit-identical results everywhere).  If a peer does not show up within ~2 s the rank returns NaN in out[0..3], sets the
+ * sticky error word of its own buffer (the uint64 at byte offset 2 * world * 64: the step that timed out; the host may
+ * poll it) and contributes NaN to every later exchange, so the failure reaches all ranks.  One 32-thread kernel. */
 int64_t wf_p2p_allreduce_buffer_bytes(int world);
 int wf_p2p_allreduce_sums(const uint64_t* peer_bufs_dev, int rank, int world, uint64_t step, const double* local, double* out,
                           void* stream);
+
+/* Single-GPU self-test of the same protocol: ALL `world` ranks are emulated by the warps of one CTA (one launch, so the
+ * mutual flag waits cannot dead-lock on a device that serialises kernels).  peer_bufs_dev: `world` buffers on this
+ * device; locals / outs: [world][4] doubles.  skip_rank >= 0: that rank never arrives (exercises the time-out path; pass a
+ * short timeout_cycles, <= 0 selects the production ~2 s). */
+int wf_p2p_allreduce_emulated(const uint64_t* peer_bufs_dev, int world, uint64_t step, const double* locals, double* outs,
+                              int skip_rank, int64_t timeout_cycles, void* stream);
 
 #ifdef __cplusplus
 }

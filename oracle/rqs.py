@@ -18,9 +18,16 @@ MIN_DERIVATIVE = 1e-3
 
 
 def softmax(x):
-    """jax.nn.softmax(axis=-1): exp(x - max) / sum."""
-    e = np.exp(x - x.max(-1, keepdims=True))
-    return e / e.sum(-1, keepdims=True)
+    """jax.nn.softmax(axis=-1): exp(x - max) / sum, in the working precision of `x`.
+
+    JAX leaves two things to XLA that decide the last bit of a float32 knot: the exp implementation and the order of the
+    reduction.  This restatement pins both so that the float32 arithmetic is a SPECIFICATION the CUDA exact-bin path
+    (WF_RQS_EXACT_BINS, csrc/rqs_device.cuh: knots_exact) reproduces operation by operation: exp is correctly rounded
+    (evaluated in float64, rounded once to the working precision) and the sum runs sequentially left to right."""
+    d = x - x.max(-1, keepdims=True)
+    e = np.exp(d.astype(np.float64)).astype(x.dtype)
+    s = np.cumsum(e, axis=-1, dtype=x.dtype)[..., -1:]
+    return e / s
 
 
 def softplus(x):

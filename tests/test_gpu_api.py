@@ -119,31 +119,46 @@ def test_mflow_get_model_and_energy_estimator(cuda):
     assert abs(float(loss) - full["energy"]) <= 1e-4 * abs(full["energy"])
 
 
-def test_peer_memory_exchange_protocol_on_one_device(cuda):
-    """wf_p2p_allreduce_sums with the `peers` emulated on ONE device: two symmetric buffers, the two ranks' kernels on two
-    streams.  Checks the slot / flag / parity protocol over several steps (the real multi-GPU run is tools/p2p_test.py and
-    bench.py --gpus N)."""
+def test_peer_memory_exchange_protocol_emulated_ranks(cuda):
+    """The slot / flag / parity protocol of wf_p2p_allreduce_sums with ALL ranks emulated by the warps of one CTA in ONE launch
+    (wf_p2p_allreduce_emulated): kernels that wait on one another must never be separate launches on one GPU
+    (B200_PROFILING.md).  The real multi-GPU run is tools/p2p_test.py and bench.py --gpus N."""
     import ctypes as C
     from waveflow_b200._ffi import check, lib, ptr
+    assert lib.wf_p2p_allreduce_buffer_bytes(0) == -1 and lib.wf_p2p_allreduce_buffer_bytes(17) == -1
+    rng = np.random.default_rng(0)
+    for world in (1, 2, 4, 8):
+        nbytes = int(lib.wf_p2p_allreduce_buffer_bytes(world))
+        assert nbytes == (2 * world * 8 + 8) * 8
+        bufs = [torch.zeros(nbytes // 8, dtype=torch.float64, device=cuda) for _ in range(world)]
+        ptrs = torch.tensor([b.data_ptr() for b in bufs], dtype=torch.int64, device=cuda)
+        outs = torch.zeros(world, 4, dtype=torch.float64, device=cuda)
+        for step in range(1, 8):
+            vals = torch.from_numpy(rng.standard_normal((world, 4)) * 1e3).to(cuda)
+            check(lib.wf_p2p_allreduce_emulated(ptr(ptrs), world, C.c_uint64(step), ptr(vals), ptr(outs), -1, 0, C.c_void_p(0)),
+                  "wf_p2p_allreduce_emulated")
+            torch.cuda.synchronize()
+            want = torch.zeros(4, dtype=torch.float64, device=cuda)
+            for r in range(world):
+                want = want + vals[r]                       # rank order, as the kernel adds
+            for r in range(world):
+                assert torch.equal(outs[r], want), (world, step, r)
+        assert all(int(b.view(torch.int64)[2 * world * 8].item()) == 0 for b in bufs)
+    # a peer that never arrives: the waiting rank times out (short timeout here), returns NaN, sets its sticky error word,
+    # and poisons the NEXT exchange so the failure reaches the ranks that did not time out themselves
     world = 2
     nbytes = int(lib.wf_p2p_allreduce_buffer_bytes(world))
-    assert nbytes == 2 * world * 8 * 8 and lib.wf_p2p_allreduce_buffer_bytes(0) == -1
     bufs = [torch.zeros(nbytes // 8, dtype=torch.float64, device=cuda) for _ in range(world)]
     ptrs = torch.tensor([b.data_ptr() for b in bufs], dtype=torch.int64, device=cuda)
-    outs = [torch.zeros(4, dtype=torch.float64, device=cuda) for _ in range(world)]
-    streams = [torch.cuda.Stream(device=cuda) for _ in range(world)]
-    rng = np.random.default_rng(0)
+    outs = torch.zeros(world, 4, dtype=torch.float64, device=cuda)
+    vals = torch.ones(world, 4, dtype=torch.float64, device=cuda)
+    check(lib.wf_p2p_allreduce_emulated(ptr(ptrs), world, C.c_uint64(1), ptr(vals), ptr(outs), 1, 2_000_000, C.c_void_p(0)))
     torch.cuda.synchronize()
-    for step in range(1, 8):
-        vals = [torch.from_numpy(rng.standard_normal(4) * 1e3).to(cuda) for _ in range(world)]
-        torch.cuda.synchronize()
-        for r in range(world):
-            check(lib.wf_p2p_allreduce_sums(ptr(ptrs), r, world, C.c_uint64(step), ptr(vals[r]), ptr(outs[r]),
-                                            C.c_void_p(streams[r].cuda_stream)), "wf_p2p_allreduce_sums")
-        torch.cuda.synchronize()
-        want = vals[0] + vals[1]
-        assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], want), step
-    # single rank: the sum is the local block
+    assert bool(torch.isnan(outs[0]).all()) and int(bufs[0].view(torch.int64)[2 * world * 8].item()) == 1
+    check(lib.wf_p2p_allreduce_emulated(ptr(ptrs), world, C.c_uint64(2), ptr(vals), ptr(outs), -1, 2_000_000, C.c_void_p(0)))
+    torch.cuda.synchronize()
+    assert bool(torch.isnan(outs).all())                   # rank 0 is poisoned -> NaN everywhere
+    # the production entry point, single rank: the sum is the local block; step 0 is reserved
     one = torch.zeros(int(lib.wf_p2p_allreduce_buffer_bytes(1)) // 8, dtype=torch.float64, device=cuda)
     p1 = torch.tensor([one.data_ptr()], dtype=torch.int64, device=cuda)
     v = torch.tensor([1.5, -2.0, 3.0, 4.25], dtype=torch.float64, device=cuda)
@@ -151,4 +166,4 @@ def test_peer_memory_exchange_protocol_on_one_device(cuda):
     check(lib.wf_p2p_allreduce_sums(ptr(p1), 0, 1, C.c_uint64(1), ptr(v), ptr(o), C.c_void_p(0)), "wf_p2p_allreduce_sums")
     torch.cuda.synchronize()
     assert torch.equal(o, v)
-    assert lib.wf_p2p_allreduce_sums(ptr(p1), 0, 1, C.c_uint64(0), ptr(v), ptr(o), C.c_void_p(0)) == -1      # step 0 is reserved
+    assert lib.wf_p2p_allreduce_sums(ptr(p1), 0, 1, C.c_uint64(0), ptr(v), ptr(o), C.c_void_p(0)) == -1

@@ -3,10 +3,11 @@ import numpy as np
 import pytest
 import torch
 
+from oracle import fast_cpu
 from oracle import fixtures as fx
 from oracle import laplacian as olap
 from oracle import live
-from tests.util import assert_fp32_grade, relerr, spec_from_live
+from tests.util import assert_fp32_grade, record_flat, relerr, spec_from_live
 
 pytestmark = pytest.mark.gpu
 
@@ -83,8 +84,11 @@ def test_mflow_log_pdf(cuda, bc):
     assert np.abs(np.clip(out["u"].cpu().numpy(), 0, 1) - u64).max() < 2e-5
 
 
-def _check_energy(out, ref, psi32, tol_e=1e-4):
+def _check_energy(out, ref, psi32, tol_e=1e-4, ref32=None):
     psi, hpsi, eloc = [out[k].cpu().numpy() for k in ("psi", "hpsi", "eloc")]
+    # north_star: local energies within 1e-4 relative -- recorded per walker (written to gpurun_out/parity_fractions.json)
+    record_flat("E_loc (pointwise relative)", eloc, ref["eloc"], tol_e, None if ref32 is None else ref32["eloc"])
+    record_flat("H psi (pointwise relative)", hpsi, ref["hpsi"], tol_e, None if ref32 is None else ref32["hpsi"])
     assert_fp32_grade(psi, ref["psi"], psi32, 1e-5, name="psi")
     assert relerr(out["grad"].cpu().numpy(), ref["grad"]) < tol_e
     assert relerr(out["lap"].cpu().numpy(), ref["lap"]) < tol_e
@@ -113,7 +117,8 @@ def test_local_energy_he_checkpoint(cuda):
     out = _live.local_energy(spec, w, torch.from_numpy(x).to(cuda), prot, want=("psi", "hpsi", "eloc", "grad", "lap"), sums=sums)
     ref = olap.local_energy_bundle(m, params, x.astype(np.float64), prot)
     psi32 = live.psi(fx.waveflow_model(2, dtype=np.float32), fx.cast_params(params, np.float32), x)
-    psi, eloc = _check_energy(out, ref, psi32)
+    ref32 = fast_cpu.FastLocalEnergy(fx.waveflow_model(2, dtype=np.float32), params, prot, dtype=torch.float32)(x)
+    psi, eloc = _check_energy(out, ref, psi32, ref32=ref32)
     s = sums.cpu().numpy()
     assert s[2] == len(x)
     assert abs(s[0] - eloc.astype(np.float64).sum()) <= 1e-6 * np.abs(eloc).sum()
@@ -135,7 +140,8 @@ def test_local_energy_random_params(cuda, D, coord, N):
     x = np.sort(np.random.default_rng(2).uniform(-10, 10, (N, D)), -1).astype(np.float32)
     out = _live.local_energy(spec, w, torch.from_numpy(x).to(cuda), prot, want=("psi", "hpsi", "eloc", "grad", "lap"))
     ref = olap.local_energy_bundle(m, params, x.astype(np.float64), prot)
-    _check_energy(out, ref, live.psi(m.cast(np.float32), fx.cast_params(params, np.float32), x))
+    ref32 = fast_cpu.FastLocalEnergy(m.cast(np.float32), params, prot, dtype=torch.float32)(x)
+    _check_energy(out, ref, live.psi(m.cast(np.float32), fx.cast_params(params, np.float32), x), ref32=ref32)
 
 
 def test_local_energy_shard_equality(cuda):

@@ -9,11 +9,45 @@ from tests.util import assert_fp32_grade, relerr
 pytestmark = pytest.mark.gpu
 
 
-def _run(cuda, x, uw, uh, ud, inverse, B):
+def _run(cuda, x, uw, uh, ud, inverse, B, exact_bins=False):
     from waveflow_b200.flows.neural_splines import unconstrained_RQS
     t = lambda a: torch.from_numpy(a).to(cuda)
-    out, lad, bins = unconstrained_RQS(t(x), t(uw), t(uh), t(ud), inverse=inverse, tail_bound=B, return_bin_idx=True)
+    out, lad, bins = unconstrained_RQS(t(x), t(uw), t(uh), t(ud), inverse=inverse, tail_bound=B, return_bin_idx=True,
+                                       exact_bins=exact_bins)
     return out.cpu().numpy(), lad.cpu().numpy(), bins.cpu().numpy()
+
+
+@pytest.mark.parametrize("K", [32, 64])
+def test_rqs_exact_bins_bit_identical_to_float32_reference_arithmetic(cuda, K):
+    """north_star: bit-exact spline bin indices.  WF_RQS_EXACT_BINS against the float32 restatement of
+    neural_splines.py:11-13,98-125 on 2^20 random-parameter elements, forward and inverse, EVERY element (no mask around the
+    knots), plus inputs placed exactly on / one ulp beside the oracle's float32 knots."""
+    rng = np.random.default_rng(100 + K)
+    N, B = 1 << 20, 3.0
+    uw, uh = rng.standard_normal((2, N, K)).astype(np.float32)
+    ud = rng.standard_normal((N, K - 1)).astype(np.float32)
+    for inverse in (False, True):
+        x = rng.uniform(-B, B, N).astype(np.float32)
+        # adversarial inputs: on the float32 knots of their own row and one ulp to either side
+        cw, _ = orqs._knots(uh[: 3 * 4096] if inverse else uw[: 3 * 4096], -B, B, orqs.MIN_BIN_WIDTH)
+        pick = rng.integers(0, K + 1, 3 * 4096)
+        kn = cw[np.arange(3 * 4096), pick]
+        x[:4096] = kn[:4096]
+        x[4096:8192] = np.nextafter(kn[4096:8192], np.float32(-10))
+        x[8192:12288] = np.nextafter(kn[8192:12288], np.float32(10))
+        x = np.clip(x, -B, B)
+        out, lad, bins = _run(cuda, x, uw, uh, ud, inverse, B, exact_bins=True)
+        o32, l32, b32 = orqs.unconstrained_rqs(x, uw, uh, ud, inverse, B, return_bin=True)
+        assert np.array_equal(bins, b32), (K, inverse, int((bins != b32).sum()))
+        # same bins and the same float32 knots: outputs agree to float32 rounding of the final rational map
+        assert np.abs(out - o32).max() <= 4e-6 * B
+        # the default (ex2.approx) path may only differ for inputs within float32 rounding of a knot
+        _, _, fast = _run(cuda, x, uw, uh, ud, inverse, B)
+        diff = fast != b32
+        assert diff.mean() < 2e-3 and np.all(np.abs(fast[diff] - b32[diff]) == 1)
+        if diff.any():
+            knots = orqs._knots((uh if inverse else uw)[diff], -B, B, orqs.MIN_BIN_WIDTH)[0]
+            assert np.min(np.abs(knots - x[diff][:, None]), axis=-1).max() < 2e-6
 
 
 @pytest.mark.parametrize("K", [5, 8, 32, 64])

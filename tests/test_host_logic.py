@@ -91,3 +91,27 @@ def test_helpers_running_statistics():
     assert got.shape == x.shape and np.allclose(got, want)
     x2 = np.stack([x, 2 * x])
     assert np.allclose(helpers.uniform_sliding_average(x2, w)[1], 2 * want)
+
+
+def test_pack_cache_keys_on_leaf_identity_and_version():
+    """The reference signature carries the raw pytree on every call; the packed layout is rebuilt only when a leaf changed
+    (new tensor, in-place torch update, or a raw-pointer update announced through bump_version)."""
+    import torch
+    from waveflow_b200 import _ffi
+    a, b = torch.zeros(4), torch.ones(3)
+    tree = ([(a, b), ()], (np.zeros(2),))
+    k0 = _ffi.params_key(tree)
+    assert _ffi.params_key(([(a, b), ()], tree[1])) == k0                  # same leaves, new containers
+    cache, made = _ffi.PackCache(size=2), []
+    make = lambda: made.append(1) or len(made)
+    assert cache.get(k0, tree, make) == 1 and cache.get(_ffi.params_key(tree), tree, make) == 1
+    a.add_(1.0)                                                             # in-place update through torch
+    k1 = _ffi.params_key(tree)
+    assert k1 != k0 and cache.get(k1, tree, make) == 2
+    view = a[1:3]
+    _ffi.bump_version(a)                                                    # raw-pointer update (wf_adam_step) announced by hand
+    assert _ffi.params_key(tree) != k1 and view._version == a._version
+    assert _ffi.params_key(([(a.clone(), b), ()], tree[1])) != _ffi.params_key(tree)
+    for i in range(3):                                                      # LRU keeps `size` entries
+        cache.get(("k", i), None, make)
+    assert len(cache.items) == 2

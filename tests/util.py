@@ -36,6 +36,9 @@ def spec_from_live(m):
                     bc_P_right=m.bc_p_right, box=m.box, coord=m.coord)
 
 
+PARITY_LOG: list = []      # one record per assert_fp32_grade call; tests/conftest.py writes it out at the end of the session
+
+
 def assert_fp32_grade(got, ref64, ref32, rtol, scale=None, name="", max_slack=4.0):
     """The GPU result must agree with the float64 oracle to `rtol` (relative to |ref| + scale) -- or, where float32
     arithmetic itself cannot (ill-conditioned points: log(p + 1e-7) next to a node of psi, log-dets of tiny bins), be as
@@ -46,6 +49,28 @@ def assert_fp32_grade(got, ref64, ref32, rtol, scale=None, name="", max_slack=4.
     eg = np.abs(got - ref64) / (np.abs(ref64) + s)
     eo = np.abs(ref32 - ref64) / (np.abs(ref64) + s)
     assert np.all(np.isfinite(got)), name
+    # north_star states FLAT tolerances (1e-5 log-prob / inverse, 1e-4 local energy): record the fraction of elements that
+    # meet `rtol` outright, for this implementation and for the reference's own float32 arithmetic, next to the error statistics
+    PARITY_LOG.append({"name": name, "n": int(eg.size), "flat_tol": float(rtol), "frac_within_flat_tol": float(np.mean(eg <= rtol)),
+                       "frac_within_flat_tol_float32_restatement": float(np.mean(eo <= rtol)),
+                       "median": float(np.median(eg)), "p99": float(np.quantile(eg, 0.99)), "max": float(eg.max()),
+                       "median_float32_restatement": float(np.median(eo)), "max_float32_restatement": float(eo.max())})
     assert np.median(eg) <= max(rtol / 10, 2 * np.median(eo)), (name, "median", np.median(eg), np.median(eo))
     assert np.quantile(eg, 0.99) <= max(rtol, 2 * np.quantile(eo, 0.99)), (name, "p99", np.quantile(eg, 0.99), np.quantile(eo, 0.99))
     assert eg.max() <= max(rtol, max_slack * eo.max()), (name, "max", eg.max(), eo.max())
+
+
+def record_flat(name, got, ref64, tol, ref32=None):
+    """Record (no assertion) the fraction of elements with |got - ref| <= tol * |ref| -- north_star's flat relative tolerance --
+    and, when given, the same fraction for the reference's own float32 arithmetic."""
+    got, ref64 = np.asarray(got, dtype=np.float64), np.asarray(ref64, dtype=np.float64)
+    eg = np.abs(got - ref64) / (np.abs(ref64) + 1e-300)
+    rec = {"name": name, "n": int(eg.size), "flat_tol": float(tol), "frac_within_flat_tol": float(np.mean(eg <= tol)),
+           "frac_within_flat_tol_float32_restatement": float("nan"), "median": float(np.median(eg)),
+           "p99": float(np.quantile(eg, 0.99)), "max": float(eg.max())}
+    if ref32 is not None:
+        eo = np.abs(np.asarray(ref32, dtype=np.float64) - ref64) / (np.abs(ref64) + 1e-300)
+        rec["frac_within_flat_tol_float32_restatement"] = float(np.mean(eo <= tol))
+        rec["median_float32_restatement"] = float(np.median(eo)); rec["max_float32_restatement"] = float(eo.max())
+    PARITY_LOG.append(rec)
+    return rec

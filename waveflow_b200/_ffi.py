@@ -44,7 +44,7 @@ def _load() -> C.CDLL:
         if os.environ.get("WAVEFLOW_B200_NO_AUTOBUILD"):
             raise WaveflowB200Error(f"{LIB_PATH} is missing: run `python -m waveflow_b200.build` (needs nvcc)")
         from . import build as _build
-        _build.build()
+        _build.build()           # serialised across processes by a file lock; the library appears atomically (os.replace)
     return C.CDLL(str(LIB_PATH))
 
 
@@ -84,13 +84,63 @@ _SIGS = {
     "wf_adam_step": (_i, [_p, _p, _p, _p, _l, _l, _p, _f, _f, _f, _f, _p]),
     "wf_p2p_allreduce_buffer_bytes": (_l, [_i]),
     "wf_p2p_allreduce_sums": (_i, [_p, _i, _i, C.c_uint64, _p, _p, _p]),
+    "wf_p2p_allreduce_emulated": (_i, [_p, _i, C.c_uint64, _p, _p, _i, _l, _p]),
     "wf_local_energy": (_i, [C.POINTER(LiveModelStruct), C.POINTER(LiveTablesStruct), _p, _p, _i, _p, _l, _p, _p, _p, _p, _p,
                              _p, _p]),
 }
+class _DeviceGuardedLib:
+    """The C ABI launches on the CURRENT device and stream.  Every call through this proxy first makes the device that holds
+    the tensors of the call current (set by `ptr` / `f32` while the arguments are marshalled, see `_touch`), so tensors on
+    cuda:1 are never launched on cuda:0 when one process drives several GPUs."""
+
+    def __init__(self, cdll):
+        object.__setattr__(self, "_cdll", cdll)
+
+    def __getattr__(self, name):
+        fn = getattr(self._cdll, name)
+        if not name.startswith("wf_") or name in _HOST_ONLY:
+            return fn
+
+        def call(*args):
+            dev = _pending_device()
+            if dev is None:
+                return fn(*args)
+            with torch.cuda.device(dev):
+                return fn(*args)
+
+        call.__name__ = name
+        object.__setattr__(self, name, call)
+        return call
+
+
+_HOST_ONLY = {"wf_abi_version", "wf_status_string", "wf_table_layout_host", "wf_live_net_floats", "wf_vqmc_param_floats",
+              "wf_vqmc_grad_workspace_floats", "wf_p2p_allreduce_buffer_bytes", "wf_rqs_coupling_net_floats",
+              "wf_rqs_coupling_tc_net_floats", "wf_rqs_coupling_tc_workspace_floats"}
+_CALL_DEVICE = {"dev": None}
+
+
+def _touch(t: torch.Tensor):
+    """Remember the device of the tensors marshalled for the next call; mixing devices in one call is an error."""
+    d = t.device
+    cur = _CALL_DEVICE["dev"]
+    if cur is not None and cur != d:
+        _CALL_DEVICE["dev"] = None
+        raise WaveflowB200Error(f"tensors of one call live on different devices ({cur} and {d})")
+    _CALL_DEVICE["dev"] = d
+
+
+def _pending_device():
+    d = _CALL_DEVICE["dev"]
+    _CALL_DEVICE["dev"] = None
+    return d
+
+
 for _name, (_res, _args) in _SIGS.items():
     _fn = getattr(lib, _name)
     _fn.restype = _res
     _fn.argtypes = _args
+_cdll = lib
+lib = _DeviceGuardedLib(_cdll)
 
 if lib.wf_abi_version(None) != 1:
     raise WaveflowB200Error("libwaveflow_b200.so ABI version mismatch: rebuild with `python -m waveflow_b200.build --force`")
@@ -110,6 +160,7 @@ def ptr(t) -> C.c_void_p:
         raise WaveflowB200Error("waveflow_b200 ops take CUDA tensors only (there is no CPU path)")
     if not t.is_contiguous():
         raise WaveflowB200Error("tensor must be contiguous")
+    _touch(t)
     return C.c_void_p(t.data_ptr())
 
 
@@ -122,7 +173,9 @@ def f32(t: torch.Tensor) -> torch.Tensor:
 
 
 def stream_ptr() -> C.c_void_p:
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    """Current stream of the device that holds the tensors marshalled so far for this call (see `_touch`)."""
+    d = _CALL_DEVICE["dev"]
+    return C.c_void_p(torch.cuda.current_stream(d).cuda_stream)
 
 
 def host_f32(a) -> np.ndarray:
@@ -146,3 +199,53 @@ def table_layouts(tab: np.ndarray, kind: str):
         return dense, None, None
     check(st, "wf_table_layout_host")
     return dense, rec, lo
+
+
+# ---------------------------------------------------------------------------------------------- parameter identity
+def bump_version(t: torch.Tensor):
+    """Tell torch that `t` was modified in place by a kernel launched through the C ABI (a raw-pointer write does not touch
+    the tensor's version counter, which `params_key` uses to detect changed parameters)."""
+    try:
+        torch._C._autograd._unsafe_set_version_counter((t,), (t._version + 1,))
+    except Exception:            # noqa: BLE001 -- older / newer torch without the hook: a real (tiny) in-place op
+        t.add_(0)
+
+
+def params_key(tree) -> tuple:
+    """Identity of a parameter pytree: (storage address, version counter, size) per torch leaf -- in-place updates bump
+    the version (optimisers through torch, wf_adam_step through `bump_version`), new tensors have new addresses that are
+    kept alive by the cache entry holding them.  numpy leaves are keyed by object identity and buffer address: like the
+    reference's immutable JAX arrays they are expected not to be mutated in place."""
+    key = []
+
+    def walk(t):
+        if isinstance(t, (tuple, list)):
+            for c in t:
+                walk(c)
+        elif isinstance(t, torch.Tensor):
+            key.append((t.data_ptr(), t._version, t.numel(), t.device.index))
+        elif isinstance(t, np.ndarray):
+            key.append((id(t), t.__array_interface__["data"][0], t.size))
+        else:
+            key.append(("py", id(t)))
+    walk(tree)
+    return tuple(key)
+
+
+class PackCache:
+    """Small LRU of packed device buffers keyed by params_key: packing (masks, regrouping, the prior fold -- dozens of small
+    launches) runs once per parameter set instead of once per psi / log_pdf / h_fn call."""
+
+    def __init__(self, size: int = 4):
+        self.size, self.items = size, []
+
+    def get(self, key, tree, make):
+        for i, (k, _keep, val) in enumerate(self.items):
+            if k == key:
+                if i:
+                    self.items.insert(0, self.items.pop(i))
+                return val
+        val = make()
+        self.items.insert(0, (key, tree, val))      # `tree` keeps the leaves (and thus their addresses) alive
+        del self.items[self.size:]
+        return val

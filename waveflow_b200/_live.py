@@ -171,6 +171,16 @@ def pack_params(spec: LiveSpec, transform_params, sp_params, device, fold_prior:
     return out
 
 
+def packed_for(spec: LiveSpec, transform_params, sp_params, device, fold_prior: bool = True) -> torch.Tensor:
+    """pack_params through a per-model cache keyed on the identity / version of the parameter leaves (_ffi.params_key): the
+    reference's call signature h_fn(params, x) / psi(params, x) / log_pdf(params, x) carries the raw pytree on every call,
+    the packed kernel layout is rebuilt only when the parameters changed."""
+    cache = spec.__dict__.setdefault("_pack_cache", _ffi.PackCache())
+    tree = (transform_params, sp_params)
+    key = (str(device), bool(fold_prior), _ffi.params_key(tree))
+    return cache.get(key, tree, lambda: pack_params(spec, transform_params, sp_params, device, fold_prior=fold_prior))
+
+
 def _struct_for(spec: LiveSpec, weights) -> LiveModelStruct:
     st = spec.struct()
     if getattr(weights, "wf_folded", False):

@@ -59,11 +59,18 @@ def unravel(like, flat: torch.Tensor):
 _WS: dict = {}
 
 
-def _workspace(spec: _live.LiveSpec, n: int, device, max_chunk: int) -> torch.Tensor:
+def workspace_floats(spec: _live.LiveSpec, n: int, max_chunk: int) -> int:
     chunk = max(1, min(n, max_chunk))
     need = int(lib.wf_vqmc_grad_workspace_floats(C.byref(spec.struct()), chunk))
     if need < 0:
         raise _ffi.WaveflowB200Error("wf_vqmc_loss_grad does not support this model (Waveflow, D in 2..4, D*P <= 128)")
+    return need
+
+
+def _workspace(spec: _live.LiveSpec, n: int, device, max_chunk: int) -> torch.Tensor:
+    """Process-wide scratch of the EAGER calls (grown on demand, stream-ordered reuse).  Captured CUDA graphs must not use
+    it -- a later, larger call would replace the tensor under the graph's recorded pointer: GraphedTrainStep owns its own."""
+    need = workspace_floats(spec, n, max_chunk)
     key = str(device)
     ws = _WS.get(key)
     if ws is None or ws.numel() < need:
@@ -74,8 +81,10 @@ def _workspace(spec: _live.LiveSpec, n: int, device, max_chunk: int) -> torch.Te
 
 def loss_grad(spec: _live.LiveSpec, flat: torch.Tensor, x: torch.Tensor, protons, running_average: float,
               n_total: int | None = None, grad: torch.Tensor | None = None, want=(), sums: torch.Tensor | None = None,
-              with_grad: bool = True, max_chunk: int = 65536, running_average_dev: torch.Tensor | None = None):
-    """wf_vqmc_loss_grad -> (grad flat [n_params] (accumulated into `grad` when given), dict of the `want`ed outputs)."""
+              with_grad: bool = True, max_chunk: int = 65536, running_average_dev: torch.Tensor | None = None,
+              ws: torch.Tensor | None = None):
+    """wf_vqmc_loss_grad -> (grad flat [n_params] (accumulated into `grad` when given), dict of the `want`ed outputs).
+    ws: caller-owned workspace (>= workspace_floats(spec, N, max_chunk) floats); default: the shared eager scratch."""
     x = _ffi.f32(x)
     N, dev = x.shape[0], x.device
     nparam = int(lib.wf_vqmc_param_floats(C.byref(spec.struct())))
@@ -89,7 +98,10 @@ def loss_grad(spec: _live.LiveSpec, flat: torch.Tensor, x: torch.Tensor, protons
     if N == 0:                                   # empty shard: nothing to launch (a rank may own no walkers)
         return grad, out
     prot = _ffi.host_f32(np.asarray(protons, dtype=np.float32).reshape(-1))
-    ws = _workspace(spec, N, dev, max_chunk)
+    if ws is None:
+        ws = _workspace(spec, N, dev, max_chunk)
+    elif ws.numel() < workspace_floats(spec, N, max_chunk) or ws.device != dev or ws.dtype != torch.float32:
+        raise _ffi.WaveflowB200Error("workspace too small / wrong device or dtype for this batch")
     tabs = _live._tables(spec, dev)
     st = lib.wf_vqmc_loss_grad(C.byref(spec.struct()), C.byref(tabs), ptr(flat), _ffi.np_ptr(prot), int(prot.size), ptr(x), N,
                                float(running_average), ptr(running_average_dev), 1.0 / float(n_total or N),
@@ -123,6 +135,7 @@ def adam(step_size, b1=0.9, b2=0.999, eps=1e-8, device="cuda"):
                               0 if step_dev is not None else int(i), ptr(step_dev), float(lr), float(b1), float(b2), float(eps),
                               stream_ptr())
         check(st, "wf_adam_step")
+        _ffi.bump_version(state.flat)        # the views handed out by get_params share this counter (pack caches key on it)
         return state
 
     opt_update.graphable = not callable(step_size)      # a schedule is evaluated on the host, per step
@@ -141,7 +154,8 @@ class GraphedTrainStep:
     (static buffer), the running average (float32[1]) and the Adam step index (int64[1])."""
 
     def __init__(self, spec, opt_state: AdamState, opt_update, protons, batch_shape, device):
-        self.spec, self.state = spec, opt_state
+        import weakref
+        self.spec, self.state = spec, weakref.ref(opt_state)     # no strong reference: the cache entry must not keep it alive
         self.x = torch.zeros(batch_shape, dtype=torch.float32, device=device)
         self.ra = torch.zeros(1, dtype=torch.float32, device=device)
         self.step = torch.zeros(1, dtype=torch.int64, device=device)
@@ -149,12 +163,14 @@ class GraphedTrainStep:
         self.sums = torch.zeros(4, dtype=torch.float64, device=device)
         self.loss = torch.zeros((), dtype=torch.float32, device=device)
         n = batch_shape[0]
+        # the graph records raw pointers: it owns every buffer it touches, including the activation workspace
+        self.ws = torch.empty(workspace_floats(spec, n, n), dtype=torch.float32, device=device)
 
         def body():
             self.grad.zero_()
             self.sums.zero_()
             loss_grad(spec, opt_state.flat, self.x, protons, 0.0, grad=self.grad, sums=self.sums, running_average_dev=self.ra,
-                      max_chunk=n)
+                      max_chunk=n, ws=self.ws)
             opt_update(0, self.grad, opt_state, step_dev=self.step)
             self.loss.copy_((self.sums[0] / float(n)).to(torch.float32))
 
@@ -177,4 +193,7 @@ class GraphedTrainStep:
         self.ra.fill_(float(running_average))
         self.step.fill_(int(epoch))
         self.graph.replay()
+        state = self.state()
+        if state is not None:
+            _ffi.bump_version(state.flat)
         return self.loss.clone()

@@ -47,7 +47,20 @@ def _compile(src: Path, obj: Path):
 
 
 def build(force: bool = False, verbose: bool = False, jobs: int | None = None) -> Path:
+    """Compile + link under an exclusive file lock: when N ranks import the package at the same time (torchrun) exactly one
+    of them builds, the others wait on the lock and then find everything up to date.  The library is linked to a temporary
+    name and moved into place with os.replace, so no process can ever load a half-written file."""
+    import fcntl
     OBJ.mkdir(exist_ok=True)
+    with open(OBJ / ".build.lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            return _build_locked(force, verbose, jobs)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(force: bool, verbose: bool, jobs: int | None) -> Path:
     hm = _headers_mtime()
     todo = [(s, OBJ / (s.stem + ".o")) for s in sources() if force or _stale(s, OBJ / (s.stem + ".o"), hm)]
     if not todo and LIB.exists() and not needs_build():
@@ -60,10 +73,13 @@ def build(force: bool = False, verbose: bool = False, jobs: int | None = None) -
             if r.returncode != 0:
                 raise RuntimeError(f"nvcc failed for {src.name}:\n{r.stderr}\n{r.stdout}")
     objs = [str(OBJ / (s.stem + ".o")) for s in sources()]
-    r = subprocess.run([NVCC, "-shared", "-o", str(LIB), *objs, "-lcudart"], capture_output=True, text=True)
+    tmp = LIB.with_name(LIB.name + f".tmp{os.getpid()}")
+    r = subprocess.run([NVCC, "-shared", "-o", str(tmp), *objs, "-lcudart"], capture_output=True, text=True)
     if r.returncode != 0:
+        tmp.unlink(missing_ok=True)
         raise RuntimeError(f"link failed:\n{r.stderr}")
-    with open(CSRC / "ptxas.log", "a") as f:
+    os.replace(tmp, LIB)
+    with open(CSRC / "ptxas.log", "w") as f:           # the log of the LAST build only (it used to grow without bound)
         f.write("\n".join(logs))
     if verbose:
         print("\n".join(logs))

@@ -24,14 +24,24 @@ namespace wf {
 
 constexpr float LOG_TOL = 1e-7f;   // made.py:79, wavefunctions.py:34, distributions.py:140
 
+constexpr int WF_MAX_DEVICES = 64;
+
+// ordinal of the current device, clamped into the per-device caches below
+inline int current_device() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0) dev = 0;
+  return dev < WF_MAX_DEVICES ? dev : WF_MAX_DEVICES - 1;
+}
+
 inline int num_sms() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
-    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  static int n[WF_MAX_DEVICES] = {};     // per device: one process may drive several GPUs
+  const int dev = current_device();
+  if (n[dev] == 0) {
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+    n[dev] = v;
   }
-  return n;
+  return n[dev];
 }
 
 // ---------------------------------------------------------------------------------------------- mbarrier + bulk copy (TMA)

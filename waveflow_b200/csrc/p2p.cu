@@ -4,72 +4,60 @@
 // 8 GPUs the local-energy kernel takes 0.24 ms and an NCCL all-reduce of 32 bytes ~0.025 ms: pure latency.  Here every rank
 // stores its four values plus a sequence flag straight into a slot of every peer's buffer (P2P stores over NVLink /
 // NVSwitch into symmetric memory), then waits for the flags of all slots of its OWN buffer and adds the slots in rank
-// order -- one small kernel, no ring, and bit-identical results on all ranks.
+// order -- one small kernel (or the tail of the local-energy kernel itself, see wf_local_energy_p2p), no ring, and
+// bit-identical results on all ranks.
 //
-// Buffer of one rank (symmetric: same layout everywhere): slot[parity][src_rank] = { double v[4]; uint64 flag; pad[3] }.
-// The parity alternates with the step: a rank can only be a whole step ahead of a peer (it needs the peer's flag to finish),
-// so two generations of slots are enough.
-#include "common.cuh"
+// Buffer of one rank (symmetric: same layout everywhere): slot[parity][src_rank] = { double v[4]; uint64 flag; pad[3] },
+// followed by a header { uint64 sticky_error; pad[7] }.  The parity alternates with the step: a rank can only be a whole
+// step ahead of a peer (it needs the peer's flag to finish), so two generations of slots are enough.
+#include "p2p_device.cuh"
+
+using namespace wf;
 
 namespace {
 
-constexpr int SLOT_DOUBLES = 8;
-
-__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
-  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
-  unsigned long long v;
-  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
+__global__ void __launch_bounds__(32) p2p_allreduce_kernel(p2p::Args a, const double* __restrict__ local, long long timeout_cycles) {
+  __shared__ double vals[p2p::MAX_WORLD * 4];
+  p2p::allreduce_warp(a, local, vals, timeout_cycles);
 }
 
-__global__ void __launch_bounds__(32) p2p_allreduce_kernel(const unsigned long long* __restrict__ peer_bufs, int rank, int world,
-                                                           unsigned long long step, const double* __restrict__ local,
-                                                           double* __restrict__ out, long long timeout_cycles) {
-  __shared__ double vals[WF_MAX_D * 2][4];
-  __shared__ int failed;
-  const int p = threadIdx.x;
-  if (p == 0) failed = 0;
-  __syncwarp();
-  const int parity = (int)(step & 1ull);
-  if (p < world) {
-    // 1. my values -> slot [parity][rank] of peer p (plain stores, then the flag with release semantics at system scope)
-    double* dst = reinterpret_cast<double*>(peer_bufs[p]) + ((size_t)parity * world + rank) * SLOT_DOUBLES;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) dst[k] = local[k];
-    __threadfence_system();
-    st_release_sys(reinterpret_cast<unsigned long long*>(dst + 4), step);
-    // 2. wait for rank p's values in MY buffer
-    const double* src = reinterpret_cast<const double*>(peer_bufs[rank]) + ((size_t)parity * world + p) * SLOT_DOUBLES;
-    const long long t0 = clock64();
-    while (ld_acquire_sys(reinterpret_cast<const unsigned long long*>(src + 4)) != step) {
-      if (clock64() - t0 > timeout_cycles) { atomicExch(&failed, 1); break; }   // never hang the GPU on a lost peer
-    }
-#pragma unroll
-    for (int k = 0; k < 4; ++k) vals[p][k] = src[k];
-  }
-  __syncwarp();
-  if (p < 4) {
-    double s = 0.0;
-    for (int r = 0; r < world; ++r) s += vals[r][p];       // fixed order: identical bits on every rank
-    out[p] = failed ? __longlong_as_double(0x7ff8000000000000ll) : s;
-  }
+// All `world` ranks emulated by the warps of ONE CTA (co-resident by construction, so the mutual flag waits are safe on a
+// single GPU): warp r runs rank r's side of the protocol on buffer r.  skip_rank >= 0: that rank never shows up.
+__global__ void __launch_bounds__(32 * p2p::MAX_WORLD) p2p_emulated_kernel(const unsigned long long* __restrict__ peer_bufs, int world,
+                                                                            unsigned long long step, const double* __restrict__ locals,
+                                                                            double* __restrict__ outs, int skip_rank,
+                                                                            long long timeout_cycles) {
+  __shared__ double vals[p2p::MAX_WORLD][p2p::MAX_WORLD * 4];
+  const int r = threadIdx.x >> 5;
+  if (r >= world || r == skip_rank) return;
+  p2p::Args a{peer_bufs, r, world, step, outs + 4 * r};
+  p2p::allreduce_warp(a, locals + 4 * r, vals[r], timeout_cycles);
 }
 
 }  // namespace
 
 extern "C" int64_t wf_p2p_allreduce_buffer_bytes(int world) {
-  return world >= 1 && world <= 2 * WF_MAX_D ? (int64_t)2 * world * SLOT_DOUBLES * (int64_t)sizeof(double) : -1;
+  return world >= 1 && world <= p2p::MAX_WORLD ? p2p::buffer_doubles(world) * (int64_t)sizeof(double) : -1;
 }
 
 extern "C" int wf_p2p_allreduce_sums(const uint64_t* peer_bufs_dev, int rank, int world, uint64_t step, const double* local,
                                      double* out, void* stream) {
-  if (!peer_bufs_dev || !local || !out || world < 1 || world > 2 * WF_MAX_D || rank < 0 || rank >= world || step == 0)
+  if (!peer_bufs_dev || !local || !out || world < 1 || world > p2p::MAX_WORLD || rank < 0 || rank >= world || step == 0)
     return WF_ERR_INVALID_ARG;
-  // ~2 s at 2 GHz: far beyond any legitimate skew between ranks, short enough not to look like a hung device
-  p2p_allreduce_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(reinterpret_cast<const unsigned long long*>(peer_bufs_dev), rank, world,
-                                                          (unsigned long long)step, local, out, 4000000000ll);
+  p2p::Args a{reinterpret_cast<const unsigned long long*>(peer_bufs_dev), rank, world, (unsigned long long)step, out};
+  p2p_allreduce_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(a, local, p2p::TIMEOUT_CYCLES);
+  WF_LAUNCH_CHECK();
+  return WF_OK;
+}
+
+extern "C" int wf_p2p_allreduce_emulated(const uint64_t* peer_bufs_dev, int world, uint64_t step, const double* locals,
+                                         double* outs, int skip_rank, int64_t timeout_cycles, void* stream) {
+  if (!peer_bufs_dev || !locals || !outs || world < 1 || world > p2p::MAX_WORLD || step == 0 || skip_rank >= world)
+    return WF_ERR_INVALID_ARG;
+  if (timeout_cycles <= 0) timeout_cycles = p2p::TIMEOUT_CYCLES;
+  p2p_emulated_kernel<<<1, 32 * world, 0, (cudaStream_t)stream>>>(reinterpret_cast<const unsigned long long*>(peer_bufs_dev), world,
+                                                                  (unsigned long long)step, locals, outs, skip_rank,
+                                                                  (long long)timeout_cycles);
   WF_LAUNCH_CHECK();
   return WF_OK;
 }

@@ -8,7 +8,7 @@ using namespace wf;
 // One thread per element.  Each thread streams its own K-float rows of unnormalised widths / heights with 128-bit
 // loads (a row is one 128-byte line at K = 32), keeps them in registers for the softmax + left-to-right knot scan,
 // and touches only the two derivative entries of the located bin.
-template <int KMAX, bool VEC>
+template <int KMAX, bool VEC, bool EXACT = false>
 __global__ void __launch_bounds__(256)
 rqs_kernel(const float* __restrict__ inputs, const float* __restrict__ uw, const float* __restrict__ uh,
            const float* __restrict__ ud, int64_t M, int K, float B, int inverse, float* __restrict__ outputs,
@@ -23,7 +23,8 @@ rqs_kernel(const float* __restrict__ inputs, const float* __restrict__ uw, const
       load_row<KMAX, VEC>(uw + m * K, K, a);
       load_row<KMAX, VEC>(uh + m * K, K, b);
       const float* udr = ud + m * (K - 1);
-      rqs_eval<KMAX>(xv, a, b, K, B, inverse != 0, [&](int j) { return __ldg(udr + j); }, out, lad, bin);
+      if (EXACT) rqs_eval_exact<KMAX>(xv, a, b, K, B, inverse != 0, [&](int j) { return __ldg(udr + j); }, out, lad, bin);
+      else rqs_eval<KMAX>(xv, a, b, K, B, inverse != 0, [&](int j) { return __ldg(udr + j); }, out, lad, bin);
     }
     stg_stream(outputs + m, out);
     stg_stream(logabsdet + m, lad);
@@ -119,7 +120,7 @@ static int launch_rqs_staged(const float* inputs, const float* uw, const float* 
   return WF_OK;
 }
 
-template <int KMAX>
+template <int KMAX, bool EXACT = false>
 static int launch_rqs(const float* inputs, const float* uw, const float* uh, const float* ud, int64_t M, int K,
                       float B, int inverse, float* outputs, float* logabsdet, int32_t* bin_idx, cudaStream_t s) {
   const int threads = 256;
@@ -128,16 +129,18 @@ static int launch_rqs(const float* inputs, const float* uw, const float* uh, con
   const int blocks = (int)(want < cap ? want : cap);
   const bool vec = (K % 4 == 0) && !(reinterpret_cast<uintptr_t>(uw) & 15) && !(reinterpret_cast<uintptr_t>(uh) & 15);
   if (vec)
-    rqs_kernel<KMAX, true><<<blocks, threads, 0, s>>>(inputs, uw, uh, ud, M, K, B, inverse, outputs, logabsdet, bin_idx);
+    rqs_kernel<KMAX, true, EXACT><<<blocks, threads, 0, s>>>(inputs, uw, uh, ud, M, K, B, inverse, outputs, logabsdet, bin_idx);
   else
-    rqs_kernel<KMAX, false><<<blocks, threads, 0, s>>>(inputs, uw, uh, ud, M, K, B, inverse, outputs, logabsdet, bin_idx);
+    rqs_kernel<KMAX, false, EXACT><<<blocks, threads, 0, s>>>(inputs, uw, uh, ud, M, K, B, inverse, outputs, logabsdet, bin_idx);
   WF_LAUNCH_CHECK();
   return WF_OK;
 }
 
 extern "C" int wf_rqs_apply(const float* inputs, const float* uw, const float* uh, const float* ud, int64_t M, int K,
-                            float tail_bound, int inverse, float* outputs, float* logabsdet, int32_t* bin_idx,
+                            float tail_bound, int flags, float* outputs, float* logabsdet, int32_t* bin_idx,
                             void* stream) {
+  if (flags & ~(WF_RQS_INVERSE | WF_RQS_EXACT_BINS)) return WF_ERR_INVALID_ARG;
+  const int inverse = (flags & WF_RQS_INVERSE) ? 1 : 0;
   if (M == 0) return WF_OK;   // empty batch: nothing to do (pointers of empty buffers may be NULL)
   if (!inputs || !uw || !uh || !ud || !outputs || !logabsdet || M < 0 || K < 2 || !(tail_bound > 0.f)) return WF_ERR_INVALID_ARG;
   if (K > 64) return WF_ERR_UNSUPPORTED;
@@ -145,6 +148,12 @@ extern "C" int wf_rqs_apply(const float* inputs, const float* uw, const float* u
   if (1e-3 * K > 1.0) return WF_ERR_INVALID_ARG;
   if (M == 0) return WF_OK;
   cudaStream_t s = (cudaStream_t)stream;
+  if (flags & WF_RQS_EXACT_BINS) {
+    if (K <= 8) return launch_rqs<8, true>(inputs, uw, uh, ud, M, K, tail_bound, inverse, outputs, logabsdet, bin_idx, s);
+    if (K <= 16) return launch_rqs<16, true>(inputs, uw, uh, ud, M, K, tail_bound, inverse, outputs, logabsdet, bin_idx, s);
+    if (K <= 32) return launch_rqs<32, true>(inputs, uw, uh, ud, M, K, tail_bound, inverse, outputs, logabsdet, bin_idx, s);
+    return launch_rqs<64, true>(inputs, uw, uh, ud, M, K, tail_bound, inverse, outputs, logabsdet, bin_idx, s);
+  }
   const bool aligned = !(reinterpret_cast<uintptr_t>(uw) & 15) && !(reinterpret_cast<uintptr_t>(uh) & 15);
   if (aligned && K == 32 && M >= 4 * RQS_TILE) return launch_rqs_staged<32>(inputs, uw, uh, ud, M, tail_bound, inverse, outputs, logabsdet, bin_idx, s);
   if (aligned && K == 64 && M >= 4 * RQS_TILE) return launch_rqs_staged<64>(inputs, uw, uh, ud, M, tail_bound, inverse, outputs, logabsdet, bin_idx, s);

@@ -74,6 +74,42 @@ __device__ __forceinline__ int knots_impl(float (&a)[KMAX], int K_in, float lo, 
     }
   return count;
 }
+// Exact-bin variant (WF_RQS_EXACT_BINS): the knot positions are computed with exactly the float32 operation sequence of the
+// float32 restatement of neural_splines.py:98-107 (oracle/rqs.py: correctly rounded exp, SEQUENTIAL sums, one IEEE division
+// per bin, no fused multiply-adds), so the located bin is bit-identical to that arithmetic for every input -- including
+// inputs within an ulp of a knot, where the ex2.approx softmax above may land in the neighbouring bin.
+//   e_j = fl32(exp(a_j - max))  [exp evaluated in float64 and rounded once],  s = ((e_0 + e_1) + e_2) + ...,
+//   w_j = min + (1 - min K) * (e_j / s),  c_j = c_{j-1} + w_j,  knot_{j+1} = (hi - lo) * c_j + lo,  knot_K = hi.
+template <int KMAX>
+__device__ __forceinline__ int knots_exact(float (&a)[KMAX], int K, float lo, float hi, float x) {
+  float mx = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < KMAX; ++j)
+    if (j < K) mx = fmaxf(mx, a[j]);
+  float sum = 0.f;
+#pragma unroll
+  for (int j = 0; j < KMAX; ++j)
+    if (j < K) {
+      a[j] = (float)exp((double)__fsub_rn(a[j], mx));
+      sum = __fadd_rn(sum, a[j]);
+    }
+  const float c1 = __fsub_rn(1.f, __fmul_rn(RQS_MIN_BIN, (float)K));
+  const float span = (float)((double)hi - (double)lo);
+  float c = 0.f;
+  int count = (x >= lo) ? 1 : 0;
+#pragma unroll
+  for (int j = 0; j < KMAX; ++j)
+    if (j < K) {
+      const float w = __fadd_rn(RQS_MIN_BIN, __fmul_rn(c1, __fdiv_rn(a[j], sum)));
+      c = __fadd_rn(c, w);
+      float kn = __fadd_rn(__fmul_rn(span, c), lo);
+      if (j == K - 1) kn = hi;
+      a[j] = kn;
+      const float cmp = (j == K - 1) ? __fadd_rn(kn, RQS_EPS) : kn;
+      count += (x >= cmp) ? 1 : 0;
+    }
+  return count;
+}
 // FULL = true asserts K == KMAX (every bound check folds at compile time); callers that know K statically say so.
 template <int KMAX, bool FULL = false>
 __device__ __forceinline__ int knots_inplace(float (&a)[KMAX], int K, float lo, float hi, float x, float mx) {
@@ -114,6 +150,12 @@ __device__ __forceinline__ RqsBin rqs_locate_counts(float x, const float (&a)[KM
   knot_pair<KMAX>(b, K, -B, r.idx, r.chl, chr);
   r.in_w = cwr - r.cwl; r.in_h = chr - r.chl;
   return r;
+}
+template <int KMAX>
+__device__ __forceinline__ RqsBin rqs_locate_exact(float x, float (&a)[KMAX], float (&b)[KMAX], int K, float B, bool inverse) {
+  const int cnt_w = knots_exact<KMAX>(a, K, -B, B, x);
+  const int cnt_h = knots_exact<KMAX>(b, K, -B, B, x);
+  return rqs_locate_counts<KMAX>(x, a, b, K, B, inverse, cnt_w, cnt_h);
 }
 template <int KMAX, bool FULL = false>
 __device__ __forceinline__ RqsBin rqs_locate(float x, float (&a)[KMAX], float (&b)[KMAX], int K, float B, bool inverse) {
@@ -171,6 +213,16 @@ template <int KMAX, bool FULL = false, class DGet>
 __device__ __forceinline__ void rqs_eval(float x, float (&a)[KMAX], float (&b)[KMAX], int K, float B, bool inverse,
                                          DGet dget, float& out, float& lad, int& bin) {
   const RqsBin r = rqs_locate<KMAX, FULL>(x, a, b, K, B, inverse);
+  bin = r.idx;
+  const float ud0 = (r.idx == 0) ? 0.f : dget(r.idx - 1);
+  const float ud1 = (r.idx == K - 1) ? 0.f : dget(r.idx);
+  rqs_finish(x, r, K, ud0, ud1, inverse, out, lad);
+}
+
+template <int KMAX, class DGet>
+__device__ __forceinline__ void rqs_eval_exact(float x, float (&a)[KMAX], float (&b)[KMAX], int K, float B, bool inverse,
+                                               DGet dget, float& out, float& lad, int& bin) {
+  const RqsBin r = rqs_locate_exact<KMAX>(x, a, b, K, B, inverse);
   bin = r.idx;
   const float ud0 = (r.idx == 0) ? 0.f : dget(r.idx - 1);
   const float ud1 = (r.idx == K - 1) ? 0.f : dget(r.idx);

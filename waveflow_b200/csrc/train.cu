@@ -714,7 +714,9 @@ __global__ void final_kernel(const __grid_constant__ FinalArgs a) {
     if (a.psi) a.psi[n] = psi.v;
     if (a.hpsi) a.hpsi[n] = hpsi;
     if (a.eloc) a.eloc[n] = eloc;
-    if (isfinite(eloc)) { e = eloc; e2 = eloc * eloc; cnt = 1.f; p2 = psi.v * psi.v; }
+    // every walker enters the sums, as jnp.mean does (vqmc.py:200): a non-finite E_loc makes the loss non-finite, visibly,
+    // exactly as it makes the adjoint seeds below -- and hence the gradient -- non-finite (same policy as wf_local_energy)
+    e = eloc; e2 = eloc * eloc; cnt = 1.f; p2 = psi.v * psi.v;
     // custom_jvp of _loss_fn_efficient (vqmc.py:202-212)
     const float ravg = a.ra_dev ? __ldg(a.ra_dev) : a.running_average;
     const float ca = 2.f * (eloc - ravg) / psi.v - hpsi / (psi.v * psi.v);
@@ -823,10 +825,11 @@ int smem_wgrad(int BN, int wrows) {
 
 template <int BN, bool T, bool A, int RM>
 int launch_linear_rm(const float* Ain, const float* B, const float* bias, float* C, int64_t R, int Kc, int Nc, int G, cudaStream_t s) {
-  static bool attr = false;
-  if (!attr) {
+  static bool attr[WF_MAX_DEVICES] = {};                  // the opt-in is per device, not per process
+  const int dev = current_device();
+  if (!attr[dev]) {
     WF_CUDA(cudaFuncSetAttribute(linear_kernel<BN, T, A, RM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    attr = true;
+    attr[dev] = true;
   }
   constexpr int SL = LIN_THREADS / BN, LROWS = 8 * RM;
   const int64_t tiles = ((R + LROWS - 1) / LROWS + SL - 1) / SL;
@@ -850,10 +853,11 @@ int launch_linear(const float* Ain, const float* B, const float* bias, float* C,
 
 template <int BN, int WROWS>
 int launch_wgrad_bn(const float* X, const float* dY, float* partial, int grid, int64_t R, int Kc, int Nc, int G, cudaStream_t s) {
-  static bool attr = false;
-  if (!attr) {
+  static bool attr[WF_MAX_DEVICES] = {};
+  const int dev = current_device();
+  if (!attr[dev]) {
     WF_CUDA(cudaFuncSetAttribute(wgrad_kernel<BN, WROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    attr = true;
+    attr[dev] = true;
   }
   wgrad_kernel<BN, WROWS><<<grid, LIN_THREADS, smem_wgrad(BN, WROWS), s>>>(X, dY, partial, R, Kc, Nc, G);
   WF_LAUNCH_CHECK();

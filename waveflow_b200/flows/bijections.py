@@ -89,7 +89,7 @@ def Serial(*init_funs):
             if spec is None:
                 return feed_forward(params, direct_funs, inputs)
             x = f32(inputs)
-            w = _live.pack_params(spec, params, None, x.device)
+            w = _live.packed_for(spec, params, None, x.device)
             out = _live.forward(spec, w, x, want=("u", "logdet"))
             return out["u"], out["logdet"]
 
@@ -98,7 +98,7 @@ def Serial(*init_funs):
                 return feed_forward(list(reversed(list(params))), list(reversed(inverse_funs)), inputs)
             from .. import _inverse
             x = f32(inputs)
-            w = _live.pack_params(spec, params, None, x.device)
+            w = _live.packed_for(spec, params, None, x.device)
             return _inverse.flow_inverse(spec, w, x), 0
 
         direct_fun.wf_spec = spec

@@ -109,7 +109,7 @@ def MFlow(transformation, sp_transformation, spline_degree, n_internal_knots, co
                 x = x[None]
             tp, sp = params
             if spec is not None:
-                w = _live.pack_params(spec, tp, sp, x.device)
+                w = _live.packed_for(spec, tp, sp, x.device)
                 out = _live.forward(spec, w, x, want=("u", "logpdf") if return_sample else ("logpdf",))
                 if return_sample:
                     return out["logpdf"], torch.clamp(out["u"], 0.0, 1.0)
@@ -128,7 +128,7 @@ def MFlow(transformation, sp_transformation, spline_degree, n_internal_knots, co
             if spec is None:
                 raise WaveflowB200Error("MFlow.sample needs the fused configuration built by model_factory.get_model")
             tp, sp = params
-            w = _live.pack_params(spec, tp, sp, torch.device(device))
+            w = _live.packed_for(spec, tp, sp, torch.device(device))
             x, u = _sampler.sample(spec, w, rng, num_samples, torch.device(device), exact=exact_inverse)
             if return_original_samples:
                 return x, u

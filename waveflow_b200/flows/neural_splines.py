@@ -16,8 +16,11 @@ DEFAULT_MIN_DERIVATIVE = 1e-3
 
 def unconstrained_RQS(inputs, unnormalized_widths, unnormalized_heights, unnormalized_derivatives, inverse=False,
                       tail_bound=1.0, min_bin_width=DEFAULT_MIN_BIN_WIDTH, min_bin_height=DEFAULT_MIN_BIN_HEIGHT,
-                      min_derivative=DEFAULT_MIN_DERIVATIVE, return_bin_idx=False):
-    """inputs [...], widths/heights [..., K], derivatives [..., K-1] -> (outputs, logabsdet) (+ int32 bin index)."""
+                      min_derivative=DEFAULT_MIN_DERIVATIVE, return_bin_idx=False, exact_bins=False):
+    """inputs [...], widths/heights [..., K], derivatives [..., K-1] -> (outputs, logabsdet) (+ int32 bin index).
+
+    exact_bins=True (WF_RQS_EXACT_BINS): knot positions in exactly the reference's float32 operation sequence
+    (neural_splines.py:98-107), bin indices bit-identical to it; the default is the fast ex2.approx softmax."""
     if (min_bin_width, min_bin_height, min_derivative) != (1e-3, 1e-3, 1e-3):
         raise _ffi.WaveflowB200Error("only the reference's default minimum bin width/height/derivative (1e-3) are compiled in")
     x = f32(inputs)
@@ -35,7 +38,7 @@ def unconstrained_RQS(inputs, unnormalized_widths, unnormalized_heights, unnorma
     out = torch.empty_like(xf)
     lad = torch.empty_like(xf)
     bins = torch.empty(M, dtype=torch.int32, device=xf.device) if return_bin_idx else None
-    st = lib.wf_rqs_apply(ptr(xf), ptr(uw), ptr(uh), ptr(ud), M, K, float(tail_bound), int(bool(inverse)), ptr(out),
+    st = lib.wf_rqs_apply(ptr(xf), ptr(uw), ptr(uh), ptr(ud), M, K, float(tail_bound), int(bool(inverse)) | (2 if exact_bins else 0), ptr(out),
                           ptr(lad), ptr(bins), stream_ptr())
     check(st, "wf_rqs_apply")
     if return_bin_idx:
@@ -67,12 +70,22 @@ def _pack_fcnn(net, half: int, K: int, Hd: int, device) -> torch.Tensor:
     return torch.cat(parts)
 
 
+_COUPLING_PACKS = _ffi.PackCache(size=8)
+
+
+def pack_coupling(layers, D: int, K: int, hidden_dim: int, device) -> torch.Tensor:
+    """All 2L conditioners of Serial(NeuralSplineCoupling * L) in the layout of wf_rqs_coupling_flow, cached on the identity /
+    version of the parameter leaves (the ~40 small torch ops per conditioner run once per parameter set, not per call)."""
+    key = (D, K, hidden_dim, str(device), _ffi.params_key(layers))
+    return _COUPLING_PACKS.get(key, layers, lambda: torch.cat(
+        [_pack_fcnn(f, D // 2, K, hidden_dim, device) for pair in layers for f in pair]).contiguous())
+
+
 def coupling_flow(layers, x, K: int, B: float, hidden_dim: int, inverse: bool = False):
     """Serial(NeuralSplineCoupling * L) in one launch.  layers = [(f1_params, f2_params), ...] -> (y, log_det)."""
     x = f32(x)
     N, D = x.shape
-    half = D // 2
-    w = torch.cat([_pack_fcnn(f, half, K, hidden_dim, x.device) for pair in layers for f in pair]).contiguous()
+    w = pack_coupling(layers, D, K, hidden_dim, x.device)
     expect = lib.wf_rqs_coupling_net_floats(D, K, hidden_dim) * 2 * len(layers)
     if w.numel() != expect:
         raise _ffi.WaveflowB200Error("packed coupling weights have the wrong size")

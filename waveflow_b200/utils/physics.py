@@ -54,7 +54,7 @@ def construct_hamiltonian_function(fn, protons=np.array([[0, 0]]), n_space_dimen
 
     def _construct(weight_dict, x, return_all=False, sums=None, packed=None):
         xx = f32(x)
-        w = packed if packed is not None else _live.pack_params(spec, weight_dict[0], weight_dict[1], xx.device)
+        w = packed if packed is not None else _live.packed_for(spec, weight_dict[0], weight_dict[1], xx.device)
         out = _live.local_energy(spec, w, xx, prot, want=("psi", "hpsi", "eloc"), sums=sums)
         if return_all:
             return out

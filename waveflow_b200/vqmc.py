@@ -78,8 +78,9 @@ def total_walkers(n_local: int, device, group=None) -> int:
 
 def reduce_loss_and_grad(grad: torch.Tensor, sums: torch.Tensor, n_total: int, group=None) -> torch.Tensor:
     """The exchange step of the sharded training step: every rank evaluated its shard with the global 1/N, so the
-    flat gradients simply add; the loss is the mean over ALL walkers, as jnp.mean does (non-finite E_loc are not dropped by
-    the reference; sums[2] counts the finite ones).  In place on grad / sums; backend-agnostic (NCCL, gloo in the CPU test)."""
+    flat gradients simply add; the loss is the mean over ALL walkers, as jnp.mean does: a non-finite E_loc is not dropped, it makes
+    the loss (and the gradient) non-finite on every path -- kernels, eager loss_fn_efficient and the graph replay agree;
+    sums[2] counts all walkers.  In place on grad / sums; backend-agnostic (NCCL, gloo in the CPU test)."""
     if _world(group) > 1:
         torch.distributed.all_reduce(grad, group=group)
         torch.distributed.all_reduce(sums, group=group)
@@ -106,8 +107,10 @@ def train_step_efficient(epoch, psi, h_fn, opt_update, opt_state, params, batch,
     if use_graph and graphable:
         key = (id(opt_state), tuple(x.shape), str(x.device))
         g = _GRAPHS.get(key)
-        if g is None or g.state is not opt_state:
+        if g is None or g.state() is not opt_state:
+            import weakref
             g = _GRAPHS[key] = _train.GraphedTrainStep(h_fn.wf_spec, opt_state, opt_update, h_fn.protons, tuple(x.shape), x.device)
+            weakref.finalize(opt_state, _GRAPHS.pop, key, None)      # the graph (and its buffers) die with the optimiser state
         return opt_state, g(epoch, x, float(running_average))
     loss_val, gradients = value_and_grad_efficient(params, psi, h_fn, batch, running_average, group=group, opt_state=opt_state,
                                                    flat_grad=True, n_total=n_total)
@@ -144,6 +147,17 @@ class PeerExchange:
         check(lib.wf_p2p_allreduce_sums(ptr(self.ptrs), self.rank, self.world, C.c_uint64(self.step), ptr(sums), ptr(self.out),
                                         stream_ptr()), "wf_p2p_allreduce_sums")
         return self.out
+
+    def failed_step(self) -> int:
+        """Sticky error word of this rank's buffer: 0, or the step at which a peer did not show up within ~2 s (from then
+        on every exchange returns NaN on ALL ranks, see include/waveflow_b200.h).  Synchronises the device."""
+        return int(self.buf.view(torch.int64)[2 * self.world * 8].item())
+
+    def check(self):
+        step = self.failed_step()
+        if step:
+            raise RuntimeError(f"peer-memory estimator exchange timed out at step {step} on rank {self.rank}: a peer rank is "
+                               "missing or more than ~2 s behind")
 
 
 class EnergyEstimator:
@@ -188,15 +202,23 @@ class EnergyEstimator:
             torch.distributed.all_reduce(sums, group=group)
         return EnergyEstimator.finish(sums)
 
+    def finish_checked(self, sums: torch.Tensor):
+        """finish() that turns a failed peer exchange (NaN sums + sticky error word) into an exception on every rank."""
+        out = self.finish(sums)
+        if self.peer is not None and not np.isfinite(float(out["n"])):      # the walker count is NaN only after a time-out
+            self.peer.check()
+        return out
+
     @staticmethod
     def finish(sums: torch.Tensor):
         s = sums.detach().cpu().numpy()
         mean = s[0] / s[2]
-        return dict(energy=float(mean), variance=float(s[1] / s[2] - mean * mean), n=int(s[2]), psi2=float(s[3]))
+        n = int(s[2]) if np.isfinite(s[2]) else float("nan")
+        return dict(energy=float(mean), variance=float(s[1] / s[2] - mean * mean), n=n, psi2=float(s[3]))
 
     def estimate(self, walkers: torch.Tensor):
         """-> dict(energy, variance, n) over all ranks."""
-        return self.finish(self.exchange(self.local_sums(walkers)))
+        return self.finish_checked(self.exchange(self.local_sums(walkers)))
 
 
 class ModelTrainer:

@@ -54,7 +54,7 @@ def Waveflow(transformation, sp_transformation, spline_degree, n_internal_knots,
             if x.dim() == 1:
                 x = x[None]
             if spec is not None:
-                w = _live.pack_params(spec, params[0], params[1], x.device)
+                w = _live.packed_for(spec, params[0], params[1], x.device)
                 out = _live.forward(spec, w, x, want=("u", "logpdf") if return_sample else ("logpdf",))
                 if return_sample:
                     return out["logpdf"], torch.clamp(out["u"], 0.0, 1.0)
@@ -70,7 +70,7 @@ def Waveflow(transformation, sp_transformation, spline_degree, n_internal_knots,
             if x.dim() == 1:
                 x = x[None]
             if spec is not None:
-                w = _live.pack_params(spec, params[0], params[1], x.device)
+                w = _live.packed_for(spec, params[0], params[1], x.device)
                 return _live.forward(spec, w, x, want=("psi",))["psi"]
             phi, log_det, _ = _factors(params, x)
             phi[:, cons] = phi[:, cons] / (2.0 ** 0.5)
@@ -80,7 +80,7 @@ def Waveflow(transformation, sp_transformation, spline_degree, n_internal_knots,
             from . import _sampler
             if spec is None:
                 raise WaveflowB200Error("Waveflow.sample needs the fused configuration built by get_waveflow_model")
-            w = _live.pack_params(spec, params[0], params[1], torch.device(device), fold_prior=False)
+            w = _live.packed_for(spec, params[0], params[1], torch.device(device), fold_prior=False)
             return _sampler.sample(spec, w, rng, num_samples, torch.device(device), exact=exact_inverse)[0]
 
         psi.wf_spec = spec
