@@ -30,7 +30,8 @@ extern "C" {
 #define WF_MAX_P 32        /* max number of spline bases per element handled by the fused kernels            */
 #define WF_HIDDEN 64       /* conditioner width, fixed by the reference (model_factory.py:38,72)              */
 #define WF_WIN 8           /* local-support window of the compact node records                                */
-#define WF_MAX_D 8         /* max flow dimension of the fused kernels                                         */
+#define WF_MAX_D 8         /* capacity of the per-model arrays (protons, peer ranks = 2 * WF_MAX_D)                    */
+#define WF_MAX_FUSED_D 4   /* max flow dimension of the fused live kernels (wf_live_*, wf_local_energy, wf_vqmc_*)      */
 #define WF_MAX_LAYERS 16
 
 /* spline kinds */
@@ -39,7 +40,7 @@ extern "C" {
 #define WF_KIND_B 2
 
 /* ABI / build info: returns WF_ABI_VERSION; writes the compiled SM arch (e.g. 100) to *sm_arch if non-null. */
-#define WF_ABI_VERSION 1
+#define WF_ABI_VERSION 2
 int wf_abi_version(int* sm_arch);
 /* Human-readable text for a status code returned by any wf_* call (static storage). */
 const char* wf_status_string(int status);
@@ -123,7 +124,7 @@ int wf_rqs_apply(const float* inputs, const float* uw, const float* uh, const fl
 
 /* Static description of a model built by model_factory.get_model / get_waveflow_model (model_factory.py:96-146). */
 typedef struct wf_live_model {
-  int32_t D;            /* flow dimension (2..WF_MAX_D)                                                           */
+  int32_t D;            /* flow dimension (2..WF_MAX_FUSED_D)                                                     */
   int32_t n_layers;     /* number of (IMADE, Reverse) pairs                                                        */
   int32_t T;            /* mesh points of the tables (2000)                                                        */
   int32_t P_I, k_I;     /* I-spline bases / degree                                                                 */
@@ -137,7 +138,12 @@ typedef struct wf_live_model {
   float reg;            /* spline_regularization (made.py:68)                                                      */
   float tol;            /* reverse_fun_tol (made.py:44)                                                            */
   int32_t n_knots_P;    /* length of the prior's knot vector (M prior sampling bound, msplines_jax.py:145-148)     */
+  int32_t weight_layout; /* WF_WEIGHTS_SIMT: packed weights as described below (CUDA-core kernels; required by the inverse /
+                          * sampler); WF_WEIGHTS_TC: the tensor-core image made by wf_live_pack_tc (wf_live_forward,
+                          * wf_local_energy, wf_local_energy_exchange: conditioner layers 2 and 3 on tcgen05, 3xTF32)      */
 } wf_live_model;
+#define WF_WEIGHTS_SIMT 0
+#define WF_WEIGHTS_TC 1
 
 /* Device-resident basis tables of a model (a HOST struct of DEVICE pointers), all produced by wf_table_layout_host:
  *   dense_* [T][4][32]  transposed tables zero-padded to WF_MAX_P bases; rec_* [T][4][8] / lo_* [T] the compact
@@ -166,6 +172,17 @@ typedef struct wf_live_tables {
  * holds the weights of sum_p o_p (whose sign survives the conditioner's own normalisation, model_factory.py:69-70). */
 int64_t wf_live_net_floats(int D);
 
+/* Tensor-core weight image (WF_WEIGHTS_TC) of `n_nets` conditioners packed as above (device -> device, one launch; run it
+ * once per parameter set).  Per net, wf_live_net_floats_tc(D) floats:
+ *   W2 hi | W2 lo  [2 k-blocks][64 rows = output unit][32 floats]   TF32-exact planes (w = hi + lo) of the masked second
+ *   W3 hi | W3 lo  [2 k-blocks][32 D rows = (dim, coefficient)][32]  and third layer, K-major with the 128-byte swizzle of
+ *                                                                    the tcgen05 shared-memory descriptors (16-byte chunk
+ *                                                                    c of row n stored at c ^ (n % 8))
+ *   W1 [D][64] | b1 [64] | b2 [64] | b3 [D][32]                      float32 (first layer and biases stay on CUDA cores)
+ * Supported: D in 2..4; a B prior must be packed with the pre-multiplied third layer (bit 2 of bc_P). */
+int64_t wf_live_net_floats_tc(int D);
+int wf_live_pack_tc(int D, int n_nets, const float* weights, float* weights_tc, void* stream);
+
 /* Outputs selector: any of the output pointers of wf_live_forward may be NULL.
  *   u [N][D]     flow output in the unit cube (Serial.direct_fun, bijections.py:452-460)
  *   logdet [N]   log|det J|
@@ -184,6 +201,15 @@ int wf_live_forward(const wf_live_model* model_host, const wf_live_tables* table
 int wf_local_energy(const wf_live_model* model_host, const wf_live_tables* tables_host, const float* weights,
                     const float* protons_host, int n_protons, const float* x, int64_t N, float* psi, float* hpsi,
                     float* eloc, float* grad, float* lap, double* sums, void* stream);
+
+/* wf_local_energy followed by the estimator exchange of SURVEY 8e (see wf_p2p_allreduce_sums for the protocol and the
+ * buffers): sums_out[0..3] = sum over ranks of this rank's `sums` after the launch.  With WF_WEIGHTS_TC the exchange runs in
+ * the TAIL of the local-energy kernel (the last CTA to retire publishes the block sums to the peers and waits for theirs):
+ * one launch per VQMC step.  done_counter: device uint32, zero-initialised, private to this stream. */
+int wf_local_energy_exchange(const wf_live_model* model_host, const wf_live_tables* tables_host, const float* weights,
+                             const float* protons_host, int n_protons, const float* x, int64_t N, float* psi, float* hpsi,
+                             float* eloc, float* grad, float* lap, double* sums, const uint64_t* peer_bufs_dev, int rank, int world,
+                             uint64_t step, double* sums_out, uint32_t* done_counter, void* stream);
 
 /* Serial.inverse_fun for the live flow (bijections.py:462-463): (Reverse, IMADE.inverse) x L then the box inverse.
  * exact == 0 reproduces the reference (made.py:85-100: coefficients conditioned on the layer INPUT, quirk Q1; bisection

@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     lib = ctypes.CDLL(str(_ffi.LIB_PATH))
     missing = [s for s in declared_symbols() if not hasattr(lib, s)]
     assert not missing, missing
-    assert _ffi.lib.wf_abi_version(None) == 1
+    assert _ffi.lib.wf_abi_version(None) == _ffi.ABI_VERSION == 2
     arch = ctypes.c_int(0)
     _ffi.lib.wf_abi_version(ctypes.byref(arch))
     assert arch.value == 100

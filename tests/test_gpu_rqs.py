@@ -44,7 +44,7 @@ def test_rqs_exact_bins_bit_identical_to_float32_reference_arithmetic(cuda, K):
         # the default (ex2.approx) path may only differ for inputs within float32 rounding of a knot
         _, _, fast = _run(cuda, x, uw, uh, ud, inverse, B)
         diff = fast != b32
-        assert diff.mean() < 2e-3 and np.all(np.abs(fast[diff] - b32[diff]) == 1)
+        assert diff[12288:].mean() < 1e-4 and np.all(np.abs(fast[diff] - b32[diff]) == 1)     # [12288:] = the random inputs
         if diff.any():
             knots = orqs._knots((uh if inverse else uw)[diff], -B, B, orqs.MIN_BIN_WIDTH)[0]
             assert np.min(np.abs(knots - x[diff][:, None]), axis=-1).max() < 2e-6

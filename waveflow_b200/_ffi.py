@@ -16,6 +16,7 @@ _HERE = Path(__file__).resolve().parent
 LIB_PATH = _HERE / "libwaveflow_b200.so"
 
 WF_MAX_P = 32
+WEIGHTS_SIMT, WEIGHTS_TC = 0, 1
 WF_HIDDEN = 64
 WF_WIN = 8
 KIND_I, KIND_M, KIND_B = 0, 1, 2
@@ -31,7 +32,7 @@ class LiveModelStruct(C.Structure):
     _fields_ = [("D", C.c_int32), ("n_layers", C.c_int32), ("T", C.c_int32), ("P_I", C.c_int32), ("k_I", C.c_int32),
                 ("prior_kind", C.c_int32), ("P_P", C.c_int32), ("k_P", C.c_int32), ("has_box", C.c_int32),
                 ("coord_mean", C.c_int32), ("bc_I", C.c_int32), ("bc_P", C.c_int32), ("box", C.c_float),
-                ("reg", C.c_float), ("tol", C.c_float), ("n_knots_P", C.c_int32)]
+                ("reg", C.c_float), ("tol", C.c_float), ("n_knots_P", C.c_int32), ("weight_layout", C.c_int32)]
 
 
 class LiveTablesStruct(C.Structure):
@@ -67,6 +68,10 @@ _SIGS = {
     "wf_spline_reverse": (_i, [_p, _i, _i, _p, _p, _l, _f, _p, _p, _p]),
     "wf_rqs_apply": (_i, [_p, _p, _p, _p, _l, _i, _f, _i, _p, _p, _p, _p]),
     "wf_live_net_floats": (_l, [_i]),
+    "wf_live_net_floats_tc": (_l, [_i]),
+    "wf_live_pack_tc": (_i, [_i, _i, _p, _p, _p]),
+    "wf_local_energy_exchange": (_i, [C.POINTER(LiveModelStruct), C.POINTER(LiveTablesStruct), _p, _p, _i, _p, _l, _p, _p, _p, _p, _p,
+                                      _p, _p, _i, _i, C.c_uint64, _p, _p, _p]),
     "wf_tf32_split": (_i, [_p, _l, _p, _p, _p]),
     "wf_rqs_coupling_tc_net_floats": (_l, []),
     "wf_rqs_coupling_tc_workspace_floats": (_l, [_l]),
@@ -113,7 +118,8 @@ class _DeviceGuardedLib:
         return call
 
 
-_HOST_ONLY = {"wf_abi_version", "wf_status_string", "wf_table_layout_host", "wf_live_net_floats", "wf_vqmc_param_floats",
+_HOST_ONLY = {"wf_abi_version", "wf_status_string", "wf_table_layout_host", "wf_live_net_floats", "wf_live_net_floats_tc",
+              "wf_vqmc_param_floats",
               "wf_vqmc_grad_workspace_floats", "wf_p2p_allreduce_buffer_bytes", "wf_rqs_coupling_net_floats",
               "wf_rqs_coupling_tc_net_floats", "wf_rqs_coupling_tc_workspace_floats"}
 _CALL_DEVICE = {"dev": None}
@@ -142,7 +148,8 @@ for _name, (_res, _args) in _SIGS.items():
 _cdll = lib
 lib = _DeviceGuardedLib(_cdll)
 
-if lib.wf_abi_version(None) != 1:
+ABI_VERSION = 2
+if lib.wf_abi_version(None) != ABI_VERSION:
     raise WaveflowB200Error("libwaveflow_b200.so ABI version mismatch: rebuild with `python -m waveflow_b200.build --force`")
 
 

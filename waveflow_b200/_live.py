@@ -168,7 +168,44 @@ def pack_params(spec: LiveSpec, transform_params, sp_params, device, fold_prior:
         parts.append(pack_net(sp_params, spec.D, spec.tab_P.P, device, fold=fold))
     out = torch.cat(parts).contiguous()
     out.wf_folded = folded
+    out.wf_tc = None
+    if out.is_cuda and tc_capable(spec) and (spec.prior != "B" or folded):
+        out.wf_tc = pack_tc(spec, out)
     return out
+
+
+def tc_capable(spec: LiveSpec) -> bool:
+    """Models the tensor-core kernels (csrc/live_tc.cuh) are instantiated for."""
+    return 2 <= spec.D <= 4
+
+
+def pack_tc(spec: LiveSpec, packed: torch.Tensor) -> torch.Tensor:
+    """wf_live_pack_tc: the packed weights -> the tensor-core image (TF32 hi / lo planes of layers 2 and 3 in the swizzled
+    K-major layout of the tcgen05 shared-memory descriptors); one launch."""
+    n_nets = spec.n_layers + (1 if spec.prior is not None else 0)
+    out = torch.empty(n_nets * int(lib.wf_live_net_floats_tc(spec.D)), dtype=torch.float32, device=packed.device)
+    check(lib.wf_live_pack_tc(spec.D, n_nets, ptr(packed), ptr(out), stream_ptr()), "wf_live_pack_tc")
+    out.wf_folded = getattr(packed, "wf_folded", False)
+    return out
+
+
+TC_MIN_ROWS = 4096      # below this many (walker, component) rows the batch does not fill the SMs' tiles: CUDA-core kernel
+TC_AUTO = False         # 'auto' picks the tensor-core kernels (flipped once they are validated and measured on the B200)
+
+
+def select_weights(spec: LiveSpec, weights: torch.Tensor, n: int, lap: bool, mode: str | None = None):
+    """-> (weights buffer, layout) for a forward / local-energy call on `n` walkers.  mode (or the environment variable
+    WAVEFLOW_B200_LIVE) = 'simt' | 'tc' forces a path ('tc' raises when the model has no tensor-core image); default 'auto':
+    tensor cores once the batch fills the machine."""
+    import os
+    mode = mode or os.environ.get("WAVEFLOW_B200_LIVE", "auto")
+    tc = getattr(weights, "wf_tc", None)
+    if mode == "tc" and tc is None:
+        raise _ffi.WaveflowB200Error("WAVEFLOW_B200_LIVE=tc but this model / parameter set has no tensor-core image")
+    rows = n * (spec.D + 2 if lap else 1)
+    if tc is not None and mode != "simt" and (mode == "tc" or (TC_AUTO and rows >= TC_MIN_ROWS)):
+        return tc, _ffi.WEIGHTS_TC
+    return weights, _ffi.WEIGHTS_SIMT
 
 
 def packed_for(spec: LiveSpec, transform_params, sp_params, device, fold_prior: bool = True) -> torch.Tensor:
@@ -181,10 +218,11 @@ def packed_for(spec: LiveSpec, transform_params, sp_params, device, fold_prior: 
     return cache.get(key, tree, lambda: pack_params(spec, transform_params, sp_params, device, fold_prior=fold_prior))
 
 
-def _struct_for(spec: LiveSpec, weights) -> LiveModelStruct:
+def _struct_for(spec: LiveSpec, weights, layout: int = _ffi.WEIGHTS_SIMT) -> LiveModelStruct:
     st = spec.struct()
     if getattr(weights, "wf_folded", False):
         st.bc_P |= 4
+    st.weight_layout = layout
     return st
 
 
@@ -203,7 +241,7 @@ def _tables(spec: LiveSpec, device) -> _ffi.LiveTablesStruct:
     return t
 
 
-def forward(spec: LiveSpec, weights: torch.Tensor, x: torch.Tensor, want=("u", "logdet")):
+def forward(spec: LiveSpec, weights: torch.Tensor, x: torch.Tensor, want=("u", "logdet"), mode: str | None = None):
     """wf_live_forward.  want: subset of {'u','logdet','logpdf','psi'} -> dict of tensors."""
     x = _ffi.f32(x)
     N = x.shape[0]
@@ -215,15 +253,17 @@ def forward(spec: LiveSpec, weights: torch.Tensor, x: torch.Tensor, want=("u", "
     for k in ("logdet", "logpdf", "psi"):
         if k in want:
             out[k] = torch.empty(N, dtype=torch.float32, device=dev)
-    st = lib.wf_live_forward(C.byref(_struct_for(spec, weights)), C.byref(tabs), ptr(weights), ptr(x), N, ptr(out.get("u")),
+    weights, layout = select_weights(spec, weights, N, lap=False, mode=mode)
+    st = lib.wf_live_forward(C.byref(_struct_for(spec, weights, layout)), C.byref(tabs), ptr(weights), ptr(x), N, ptr(out.get("u")),
                              ptr(out.get("logdet")), ptr(out.get("logpdf")), ptr(out.get("psi")), stream_ptr())
     check(st, "wf_live_forward")
     return out
 
 
 def local_energy(spec: LiveSpec, weights: torch.Tensor, x: torch.Tensor, protons, want=("psi", "hpsi", "eloc"),
-                 sums: torch.Tensor | None = None):
-    """wf_local_energy.  want: subset of {'psi','hpsi','eloc','grad','lap'}; sums: float64 [4] accumulator (zeroed by caller)."""
+                 sums: torch.Tensor | None = None, exchange=None, mode: str | None = None):
+    """wf_local_energy.  want: subset of {'psi','hpsi','eloc','grad','lap'}; sums: float64 [4] accumulator (zeroed by caller).
+    exchange: a vqmc.PeerExchange -- the block sums are all-reduced over the ranks into exchange.out by the same call."""
     x = _ffi.f32(x)
     N = x.shape[0]
     dev = x.device
@@ -237,10 +277,23 @@ def local_energy(spec: LiveSpec, weights: torch.Tensor, x: torch.Tensor, protons
         out["grad"] = torch.empty(N, spec.D, dtype=torch.float32, device=dev)
     if sums is not None and (sums.dtype != torch.float64 or sums.numel() != 4):
         raise _ffi.WaveflowB200Error("sums must be a float64 tensor with 4 elements")
-    st = lib.wf_local_energy(C.byref(_struct_for(spec, weights)), C.byref(tabs), ptr(weights), _ffi.np_ptr(prot), int(prot.size), ptr(x),
-                             N, ptr(out.get("psi")), ptr(out.get("hpsi")), ptr(out.get("eloc")), ptr(out.get("grad")),
-                             ptr(out.get("lap")), ptr(sums), stream_ptr())
-    check(st, "wf_local_energy")
+    weights, layout = select_weights(spec, weights, N, lap=True, mode=mode)
+    if exchange is None:
+        st = lib.wf_local_energy(C.byref(_struct_for(spec, weights, layout)), C.byref(tabs), ptr(weights), _ffi.np_ptr(prot),
+                                 int(prot.size), ptr(x), N, ptr(out.get("psi")), ptr(out.get("hpsi")), ptr(out.get("eloc")),
+                                 ptr(out.get("grad")), ptr(out.get("lap")), ptr(sums), stream_ptr())
+        check(st, "wf_local_energy")
+    else:
+        # local energy + estimator exchange over peer memory (vqmc.PeerExchange): fused into the kernel tail on the
+        # tensor-core path, a second 32-thread launch otherwise
+        if sums is None:
+            raise _ffi.WaveflowB200Error("the estimator exchange needs the `sums` accumulator")
+        step = exchange.next_step()
+        st = lib.wf_local_energy_exchange(C.byref(_struct_for(spec, weights, layout)), C.byref(tabs), ptr(weights), _ffi.np_ptr(prot),
+                                          int(prot.size), ptr(x), N, ptr(out.get("psi")), ptr(out.get("hpsi")), ptr(out.get("eloc")),
+                                          ptr(out.get("grad")), ptr(out.get("lap")), ptr(sums), ptr(exchange.ptrs), exchange.rank,
+                                          exchange.world, C.c_uint64(step), ptr(exchange.out), ptr(exchange.counter), stream_ptr())
+        check(st, "wf_local_energy_exchange")
     return out
 
 

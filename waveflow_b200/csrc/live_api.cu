@@ -2,6 +2,7 @@
 #include <string.h>
 #include "live_kernel.cuh"
 #include "live_inverse.cuh"
+#include "live_tc.cuh"
 
 using namespace wf;
 
@@ -31,6 +32,7 @@ int fill_params(const wf_live_model* m, const wf_live_tables* t, const float* we
   if (m->D < 2 || m->D > WF_MAX_D || m->n_layers < 0 || m->n_layers > WF_MAX_LAYERS || m->T < 2) return WF_ERR_INVALID_ARG;
   if (m->P_I < 2 || m->P_I > WF_MAX_P || m->k_I < 0) return WF_ERR_INVALID_ARG;
   if (m->D > 4) return WF_ERR_UNSUPPORTED;
+  if (m->weight_layout != WF_WEIGHTS_SIMT && m->weight_layout != WF_WEIGHTS_TC) return WF_ERR_INVALID_ARG;
   const bool pnet = m->prior_kind == WF_KIND_B || m->prior_kind == WF_KIND_M;
   if (!weights && (m->n_layers > 0 || pnet)) return WF_ERR_INVALID_ARG;
   if (m->n_layers > 0 && (!t->rec_I || !t->lo_I)) return WF_ERR_INVALID_ARG;
@@ -54,8 +56,24 @@ int fill_params(const wf_live_model* m, const wf_live_tables* t, const float* we
   return WF_OK;
 }
 
+int dispatch_tc(LiveParams& P, bool lap, const ltc::TcExtra& X, cudaStream_t s) {
+  // tensor-core image: B prior only with the pre-multiplied third layer (bit 2 of bc_P)
+  if (P.m.prior_kind == WF_KIND_B && !(P.m.bc_P & 4)) return WF_ERR_INVALID_ARG;
+  switch (P.m.D) {
+    case 2: return lap ? launch_live_tc_d2_lap1(P, X, s) : launch_live_tc_d2_lap0(P, X, s);
+    case 3: return lap ? launch_live_tc_d3_lap1(P, X, s) : launch_live_tc_d3_lap0(P, X, s);
+    case 4: return lap ? launch_live_tc_d4_lap1(P, X, s) : launch_live_tc_d4_lap0(P, X, s);
+    default: return WF_ERR_UNSUPPORTED;
+  }
+}
+
 int dispatch(LiveParams& P, bool lap, void* stream) {
   cudaStream_t s = (cudaStream_t)stream;
+  if (P.m.weight_layout == WF_WEIGHTS_TC) {
+    ltc::TcExtra X;
+    memset(&X, 0, sizeof(X));
+    return dispatch_tc(P, lap, X, s);
+  }
   switch (P.m.D) {
     case 2: return lap ? launch_live_d2_lap1(P, s) : launch_live_d2_lap0(P, s);
     case 3: return lap ? launch_live_d3_lap1(P, s) : launch_live_d3_lap0(P, s);
@@ -104,6 +122,7 @@ int fill_inverse(const wf_live_model* m, const wf_live_tables* t, const float* w
   if (st != WF_OK) return st;
   if (m->n_layers > 0 && !(m->tol > 0.f)) return WF_ERR_INVALID_ARG;
   if (m->bc_P & 4) return WF_ERR_INVALID_ARG;     // the sampler / inverse need the raw conditioner outputs (unfolded weights)
+  if (m->weight_layout != WF_WEIGHTS_SIMT) return WF_ERR_INVALID_ARG;
   const bool pnet = m->prior_kind == WF_KIND_B || m->prior_kind == WF_KIND_M;
   if (sample && !pnet) return WF_ERR_INVALID_ARG;
   if (sample && m->prior_kind == WF_KIND_B && !t->b_to_ob) return WF_ERR_INVALID_ARG;
@@ -147,4 +166,97 @@ extern "C" int wf_live_sample(const wf_live_model* model, const wf_live_tables* 
   if (st != WF_OK) return st;
   P.x_out = x; P.u_out = u_out; P.seed = seed; P.exact = exact ? 1 : 0; P.do_sample = 1;
   return dispatch_inverse(P, stream);
+}
+
+// ---------------------------------------------------------------------------------------------- local energy + estimator exchange
+namespace {
+__global__ void __launch_bounds__(32) p2p_after_kernel(p2p::Args a, const double* __restrict__ local) {
+  __shared__ double vals[p2p::MAX_WORLD * 4];
+  p2p::allreduce_warp(a, local, vals, p2p::TIMEOUT_CYCLES);
+}
+}  // namespace
+
+extern "C" int wf_local_energy_exchange(const wf_live_model* model, const wf_live_tables* tables, const float* weights,
+                                        const float* protons, int n_protons, const float* x, int64_t N, float* psi, float* hpsi,
+                                        float* eloc, float* grad, float* lap, double* sums, const uint64_t* peer_bufs_dev, int rank,
+                                        int world, uint64_t step, double* sums_out, uint32_t* done_counter, void* stream) {
+  if (!sums || !sums_out || !peer_bufs_dev || !done_counter || world < 1 || world > p2p::MAX_WORLD || rank < 0 || rank >= world || step == 0)
+    return WF_ERR_INVALID_ARG;
+  cudaStream_t s = (cudaStream_t)stream;
+  p2p::Args a{reinterpret_cast<const unsigned long long*>(peer_bufs_dev), rank, world, (unsigned long long)step, sums_out};
+  if (N > 0 && model && model->weight_layout == WF_WEIGHTS_TC) {
+    LiveParams P;
+    const int st = fill_params(model, tables, weights, x, N, P);
+    if (st != WF_OK) return st;
+    if (model->prior_kind != WF_KIND_B) return WF_ERR_INVALID_ARG;
+    if (n_protons < 0 || n_protons > WF_MAX_D || (n_protons > 0 && !protons)) return WF_ERR_INVALID_ARG;
+    P.psi = psi; P.hpsi = hpsi; P.eloc = eloc; P.grad = grad; P.lap = lap; P.sums = sums;
+    P.n_protons = n_protons;
+    for (int i = 0; i < n_protons; ++i) P.protons[i] = protons[i];
+    ltc::TcExtra X;
+    X.xchg = a; X.done_counter = done_counter;
+    return dispatch_tc(P, true, X, s);        // the last CTA to retire runs the exchange: one launch per step
+  }
+  // CUDA-core kernel (or an empty shard): the exchange follows as its own 32-thread launch
+  const int st = wf_local_energy(model, tables, weights, protons, n_protons, x, N, psi, hpsi, eloc, grad, lap, sums, stream);
+  if (st != WF_OK) return st;
+  p2p_after_kernel<<<1, 32, 0, s>>>(a, sums);
+  WF_LAUNCH_CHECK();
+  return WF_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- tensor-core weight image
+namespace {
+// one thread per float of the destination image (layout: live_tc.cuh, net_floats_tc)
+__global__ void pack_tc_kernel(const float* __restrict__ src, float* __restrict__ dst, int D, int n_nets) {
+  const int netf_s = net_floats(D), netf_t = ltc::net_floats_tc(D);
+  const int64_t total = (int64_t)n_nets * netf_t;
+  const int N3 = D * WF_MAX_P;
+  const int w2p = WF_HIDDEN * WF_HIDDEN, w3p = N3 * WF_HIDDEN;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int net = (int)(i / netf_t);
+    int e = (int)(i % netf_t);
+    const float* sn = src + (size_t)net * netf_s;
+    const float* W1 = sn;
+    const float* b1 = W1 + D * WF_HIDDEN;
+    const float* W2 = b1 + WF_HIDDEN;
+    const float* b2 = W2 + WF_HIDDEN * WF_HIDDEN;
+    const float* W3 = b2 + WF_HIDDEN;
+    const float* b3 = W3 + WF_HIDDEN * N3;
+    float v;
+    if (e < 2 * w2p + 2 * w3p) {
+      // plane element: [k-block][row n][8 chunks of 4 floats], 16-byte chunk c stored at position c ^ (n % 8)
+      const bool third = e >= 2 * w2p;
+      if (third) e -= 2 * w2p;
+      const int plane = third ? w3p : w2p, rows = third ? N3 : WF_HIDDEN;
+      const bool lo = e >= plane;
+      if (lo) e -= plane;
+      const int kb = e / (rows * 32), r = (e / 32) % rows, pos = (e % 32) / 4, el = e % 4;
+      const int k = kb * 32 + ((pos ^ (r & 7)) * 4) + el;
+      const float w = third ? W3[(size_t)k * N3 + r] : W2[(size_t)k * WF_HIDDEN + r];
+      const float hi = ltc::tf32_rn(w);
+      v = lo ? ltc::tf32_rn(w - hi) : hi;
+    } else {
+      e -= 2 * w2p + 2 * w3p;
+      if (e < D * WF_HIDDEN) v = W1[e];
+      else if ((e -= D * WF_HIDDEN) < WF_HIDDEN) v = b1[e];
+      else if ((e -= WF_HIDDEN) < WF_HIDDEN) v = b2[e];
+      else v = b3[e - WF_HIDDEN];
+    }
+    dst[i] = v;
+  }
+}
+}  // namespace
+
+extern "C" int64_t wf_live_net_floats_tc(int D) { return (D >= 2 && D <= 4) ? (int64_t)ltc::net_floats_tc(D) : -1; }
+
+extern "C" int wf_live_pack_tc(int D, int n_nets, const float* weights, float* weights_tc, void* stream) {
+  if (D < 2 || D > 4) return WF_ERR_UNSUPPORTED;
+  if (n_nets < 0 || (n_nets > 0 && (!weights || !weights_tc))) return WF_ERR_INVALID_ARG;
+  if (n_nets == 0) return WF_OK;
+  if (reinterpret_cast<uintptr_t>(weights_tc) & 15) return WF_ERR_INVALID_ARG;
+  const int64_t total = (int64_t)n_nets * ltc::net_floats_tc(D);
+  pack_tc_kernel<<<(int)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(weights, weights_tc, D, n_nets);
+  WF_LAUNCH_CHECK();
+  return WF_OK;
 }

@@ -91,51 +91,7 @@ __global__ void __launch_bounds__(LIVE_THREADS, 1) live_kernel(const __grid_cons
     // ---------------------------------------------------------------- box transform (made.py:118-137,156-183)
     float us[D];        // 1-register bundles of the current layer input
     J ld = cx.constant(0.f);
-    {
-      J X[D];
-#pragma unroll
-      for (int d = 0; d < D; ++d) X[d] = J{cx.is_v ? xs[d] : (cx.comp == d + 1 ? 1.f : 0.f), 0.f, xs[d]};
-      if (M.has_box) {
-        const float L = M.box, tolr = 1e-7f;
-        J U[D];
-        if (M.coord_mean) {
-          J sum = X[0];
-#pragma unroll
-          for (int d = 1; d < D; ++d) sum = cx.add(sum, X[d]);
-          J mean = cx.scale(sum, 1.f / (float)D);
-          mean.v = sum.v / (float)D; if (cx.is_v) mean.m = mean.v;
-          const J l = cx.sub(mean, X[0]);
-          const J wd = cx.sub(X[D - 1], X[0]);
-          J space = cx.constant(2.f * L);
-#pragma unroll
-          for (int i = 0; i < D - 1; ++i) {
-            const J diff = cx.sub(X[i + 1], X[i]);
-            const J den = cx.addc(space, tolr);
-            U[i] = cx.div(diff, den);
-            ld = cx.sub(ld, cx.log(den));
-            space = cx.sub(space, diff);
-          }
-          const J den = cx.addc(cx.rsubc(2.f * L, wd), tolr);
-          U[D - 1] = cx.div(cx.sub(cx.addc(mean, L), l), den);
-          ld = cx.sub(ld, cx.log(den));
-        } else {
-          U[0] = cx.scale(cx.addc(X[0], L), 1.f / (2.f * L));
-          U[0].v = (xs[0] + L) / (2.f * L); if (cx.is_v) U[0].m = U[0].v;
-          ld = cx.addc(ld, -logf(2.f * L));
-#pragma unroll
-          for (int i = 1; i < D; ++i) {
-            const J den = cx.addc(cx.rsubc(L, X[i - 1]), tolr);
-            U[i] = cx.div(cx.sub(X[i], X[i - 1]), den);
-            ld = cx.sub(ld, cx.log(den));
-          }
-        }
-#pragma unroll
-        for (int d = 0; d < D; ++d) us[d] = cx.fold(U[d]);
-      } else {
-#pragma unroll
-        for (int d = 0; d < D; ++d) us[d] = X[d].m;
-      }
-    }
+    box_transform<D, LAP>(cx, M, xs, us, ld);
 
     float uout[D];      // flow output (value), for the `u` result
 #pragma unroll

@@ -1,0 +1,687 @@
+// Tensor-core variant of the fused live path (same arithmetic as live_kernel.cuh, conditioner layers 2 and 3 on tcgen05).
+//
+// The forward-Laplacian of the live path propagates, for every walker, G = D + 2 jet components (value, D gradient entries,
+// Laplacian) through the conditioner MLPs.  A linear layer acts on every component alike, so with rows = (walker, component)
+// the hidden and output layers are plain [rows, 64] x [64, 64 | 32 D] products -- 86 % of the dense FLOPs of the path.
+// live_kernel.cuh evaluates them with FFMAs fed by broadcast shared-memory loads (ncu: FMA pipe 37 %, short-scoreboard
+// stalls on the weight LDS.128, 12 warps per SM); here they run on the 5th-generation tensor cores:
+//
+//   * one TILE = 128 rows = 4 warps x (32 / G) walkers x G components; the lane <-> (walker, component) mapping inside a
+//     warp is exactly Ctx<D, LAP>'s, so the jet algebra of live_device.cuh (warp shuffles between the components of a
+//     walker) is reused unchanged, and thread r of a warpgroup owns TMEM lane r;
+//   * the A operand (activations) lives in TENSOR MEMORY: every thread writes its row of tanh outputs as two TF32-exact
+//     planes (hi, lo) with tcgen05.st, the MMAs read them with the .ts form ([d_tmem], [a_tmem], b_desc) -- no shared-memory
+//     staging of the activations, no swizzling, no bank conflicts;
+//   * the B operand (weights, hi / lo planes) is a pre-swizzled SWIZZLE_128B K-major image produced once per parameter set
+//     (wf_live_pack_tc) and dropped into shared memory by one cp.async.bulk per layer and net;
+//   * "3xTF32": D = A_hi B_hi + A_hi B_lo + A_lo B_hi accumulated in fp32 in TMEM -- float32-grade results (the scheme of
+//     tc_gemm.cuh, measured there at 3e-6 relative for K = 512);
+//   * accumulators are read back with tcgen05.ld by the thread that owns the row and the tanh / sigmoid-normalise-spline /
+//     B-prior jet algebra runs as the epilogue, straight from tensor memory.
+//
+// CTA = 512 threads = 2 tiles x 2 warpgroups.  Both warpgroups of a tile hold the same 128 rows (warp w and warp w + 4 share
+// a TMEM lane quarter) and split the per-row work: hidden features 0..31 / 32..63 in the tanh layers, output dimensions
+// [0, D/2) / [D/2, D) in the spline glue; the per-dimension results are exchanged through the scratch columns.
+// TMEM: 2 tiles x (A_hi 64 + A_lo 64 + accumulator 128) = 512 columns.  Shared memory: W2 planes 32 KB + W3 planes 16 D KB +
+// 32 floats of scratch per thread (64 KB).
+//
+// Reference: the same lines as live_device.cuh / live_kernel.cuh.
+#pragma once
+#include "live_device.cuh"
+#include "p2p_device.cuh"
+
+namespace wf {
+namespace ltc {
+
+constexpr int THREADS = 512;
+constexpr int TILE_THREADS = 256;          // two warpgroups
+constexpr int TILES = 2;
+constexpr int SCR = 32;                    // floats of thread-private scratch
+constexpr int W2_PLANE_BYTES = WF_HIDDEN * WF_HIDDEN * 4;          // 16 KB
+__host__ __device__ constexpr int w3_plane_bytes(int D) { return D * WF_MAX_P * WF_HIDDEN * 4; }   // 8 KB per dimension
+__host__ __device__ constexpr int small_floats(int D) { return D * WF_HIDDEN + WF_HIDDEN + WF_HIDDEN + D * WF_MAX_P; }
+// packed image of one conditioner (floats): W2 hi | W2 lo | W3 hi | W3 lo | W1 [D][64] | b1 [64] | b2 [64] | b3 [D][32]
+__host__ __device__ constexpr int net_floats_tc(int D) {
+  return 2 * (W2_PLANE_BYTES / 4) + 2 * (w3_plane_bytes(D) / 4) + small_floats(D);
+}
+
+// ---------------------------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem]^T, kind::tf32, M = 128 (A: lane = row, one column per K element)
+__device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  tmem_wait_ld();
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, "
+      "%19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  tmem_wait_ld();
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};\n" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+      "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (rows of 128 bytes, 8-row groups 1024 bytes apart); see tc_gemm.cuh
+__device__ __forceinline__ uint64_t smem_desc_sw128(const void* p) {
+  const uint64_t addr = (uint64_t)(smem_u32(p) >> 4) & 0x3FFFull;
+  return addr | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// kind::tf32, fp32 accumulate, A and B K-major, M = 128
+__host__ __device__ constexpr uint32_t instr_desc_tf32(int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+__device__ __forceinline__ float tf32_rn(float a) {
+  uint32_t u = __float_as_uint(a);
+  u += 0x0FFFu + ((u >> 13) & 1u);
+  return __uint_as_float(u & 0xFFFFE000u);
+}
+
+// mbarrier wait with a watchdog: a protocol error must end the kernel (trap -> launch failure), never hang the device
+__device__ __forceinline__ void mbar_wait_guard(uint64_t* bar, uint32_t parity) {
+  uint32_t done = 0;
+  for (uint32_t spin = 0; !done; ++spin) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    if (!done && spin > (1u << 26)) __trap();
+  }
+}
+
+// One conditioner layer on the tensor cores: acc[128 x N] = A (hi + lo planes in TMEM) x W^T (hi / lo images in shared memory)
+template <int N>
+__device__ __forceinline__ void issue_layer(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, const unsigned char* b_hi, const unsigned char* b_lo) {
+  constexpr uint32_t idesc = instr_desc_tf32(N);
+#pragma unroll
+  for (int kb = 0; kb < WF_HIDDEN / 32; ++kb) {
+    const uint64_t dh = smem_desc_sw128(b_hi + (size_t)kb * N * 128), dl = smem_desc_sw128(b_lo + (size_t)kb * N * 128);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint32_t acol = (uint32_t)(kb * 32 + k * 8);
+      const uint64_t adv = (uint64_t)((k * 32) >> 4);       // 32 bytes per k-step inside the 128-byte swizzle span
+      umma_tf32_ts(d_tmem, a_hi + acol, dh + adv, idesc, (kb | k) != 0 ? 1u : 0u);
+      umma_tf32_ts(d_tmem, a_hi + acol, dl + adv, idesc, 1u);
+      umma_tf32_ts(d_tmem, a_lo + acol, dh + adv, idesc, 1u);
+    }
+  }
+}
+
+struct ScratchT {
+  float* col;
+  __device__ __forceinline__ float& operator[](int slot) const { return col[slot * THREADS]; }
+};
+
+// 16 activations -> TF32-exact planes -> this thread's row of the A operand (columns col .. col + 15)
+__device__ __forceinline__ void store_planes16(uint32_t a_hi, uint32_t a_lo, uint32_t col, const float (&h)[16]) {
+  uint32_t hi[16], lo[16];
+#pragma unroll
+  for (int t = 0; t < 16; ++t) {
+    const float f = tf32_rn(h[t]);
+    hi[t] = __float_as_uint(f);
+    lo[t] = __float_as_uint(tf32_rn(h[t] - f));
+  }
+  tmem_st16(a_hi + col, hi);
+  tmem_st16(a_lo + col, lo);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// sigmoid_spline of live_device.cuh with the conditioner outputs in REGISTERS (read from tensor memory): pass A is unrolled
+// over the 32 coefficient slots; only s_q's own component is parked in the scratch column for the window pass, whose
+// pending second-derivative term is rebuilt from it:  p = s'' o'^2 = (1 - 2 s) m^2 / (s (1 - s))  with  m = s' o'.
+template <int D, bool LAP, int NOUT, bool PREFIX_ONE>
+__device__ __forceinline__ void sigmoid_spline_regs(const Ctx<D, LAP>& cx, const float (&o)[WF_MAX_P], const ScratchT& S, int P,
+                                                    const float* __restrict__ wq, float reg, const float* __restrict__ rec,
+                                                    const int32_t* __restrict__ lo, const float* __restrict__ dense, int T, float xd,
+                                                    float xv, J& y, J& dy) {
+  constexpr int NK = LAP ? NOUT + 2 : NOUT;
+  const float np_ = (float)(T - 1);
+  const NodeIdx n = node_index(xv, T);
+  const int lo_l = __ldg(lo + n.l), lo_r = __ldg(lo + n.r);
+  const int sh = lo_r - lo_l;
+  const bool local = (sh == 0) || (sh == 1);
+  const int lo_w = local ? lo_l : 0;
+
+  J Ssum = {0.f, 0.f, 0.f}, SW = {0.f, 0.f, 0.f}, PRE = {0.f, 0.f, 0.f};
+  float Wsum = 0.f, Wpre = 0.f;
+#pragma unroll
+  for (int q = 0; q < WF_MAX_P; ++q) {
+    if (q < P) {
+      const float ov = cx.bv(o[q]);
+      const float s = fast_sigmoid(ov);
+      const float d1 = s * (1.f - s);
+      const J sq = cx.unary(J{o[q], 0.f, ov}, s, d1, d1 * (1.f - 2.f * s));
+      const float w = wq[q];
+      Ssum = cx.add(Ssum, sq);
+      SW = cx.axpy(w, sq, SW);
+      Wsum += w;
+      if (PREFIX_ONE) {
+        const float wp = (q < lo_w) ? w : 0.f;
+        PRE = cx.axpy(wp, sq, PRE);
+        Wpre += wp;
+      }
+      S[q] = sq.m;
+    }
+  }
+  auto reload = [&](int qc) {
+    J sq;
+    sq.m = S[qc];
+    sq.v = cx.bv(sq.m);
+    if constexpr (LAP) {
+      const float d1 = fmaxf(sq.v * (1.f - sq.v), 1e-30f);
+      sq.p = cx.is_g ? __fdividef((1.f - 2.f * sq.v) * sq.m * sq.m, d1) : 0.f;
+    } else sq.p = 0.f;
+    return sq;
+  };
+  J Sk[NK];
+  float Wk[NK];
+#pragma unroll
+  for (int k = 0; k < NK; ++k) { Sk[k] = J{0.f, 0.f, 0.f}; Wk[k] = 0.f; }
+  if (PREFIX_ONE) { Sk[0] = PRE; Wk[0] = Wpre; }
+  if (local) {
+#pragma unroll 2
+    for (int t = 0; t < WF_WIN; ++t) {
+      const int q = lo_l + t;
+      const int qc = q < P ? q : P - 1;
+      const float w = q < P ? wq[qc] : 0.f;
+      const J sq = reload(qc);
+      const int tr = t - sh;
+#pragma unroll
+      for (int k = 0; k < NK; ++k) {
+        const int nd = k < 3 ? k : 3;
+        const float yl = __ldg(rec + ((size_t)n.l * 4 + nd) * WF_WIN + t);
+        const float yrr = __ldg(rec + ((size_t)n.r * 4 + nd) * WF_WIN + (tr < 0 ? 0 : tr));
+        const float yr = tr < 0 ? ((PREFIX_ONE && nd == 0) ? 1.f : 0.f) : yrr;
+        const float fw = lerp_tab(yl, yr, np_, n.dx) * w;
+        Sk[k] = cx.axpy(fw, sq, Sk[k]);
+        Wk[k] += fw;
+      }
+    }
+  } else {
+    // reference-exact dense evaluation (arguments outside [0, 1]: JAX gather wrap / clamp semantics)
+    if (PREFIX_ONE) { Sk[0] = J{0.f, 0.f, 0.f}; Wk[0] = 0.f; }
+    for (int q = 0; q < P; ++q) {
+      const J sq = reload(q);
+      const float w = wq[q];
+#pragma unroll
+      for (int k = 0; k < NK; ++k) {
+        const int nd = k < 3 ? k : 3;
+        const float yl = __ldg(dense + ((size_t)n.l * 4 + nd) * WF_MAX_P + q);
+        const float yr = __ldg(dense + ((size_t)n.r * 4 + nd) * WF_MAX_P + q);
+        const float fw = lerp_tab(yl, yr, np_, n.dx) * w;
+        Sk[k] = cx.axpy(fw, sq, Sk[k]);
+        Wk[k] += fw;
+      }
+    }
+  }
+  const J r = cx.recip(Ssum);
+  const J iz = cx.recip(cx.addc(cx.mul(SW, r), reg * Wsum));
+  J A[NK];
+#pragma unroll
+  for (int k = 0; k < NK; ++k) A[k] = cx.mul(cx.addc(cx.mul(Sk[k], r), reg * Wk[k]), iz);
+  if constexpr (LAP) {
+    y = spline_assemble<D, LAP>(cx, A[0], A[1], A[2], xd);
+    if (NOUT == 2) dy = spline_assemble<D, LAP>(cx, A[1], A[2], A[NK - 1], xd);
+  } else {
+    y = A[0];
+    if (NOUT == 2) dy = A[NOUT - 1];
+  }
+}
+
+// B prior factor with the third layer pre-multiplied by mask @ ob_to_b (bit 2 of bc_P; see bprior_factor): o[q] = c'_q,
+// o[31] = sum of the raw conditioner outputs.  Everything in registers.
+template <int D, bool LAP>
+__device__ __forceinline__ J bprior_factor_regs(const Ctx<D, LAP>& cx, const float (&o)[WF_MAX_P], int P, const float* __restrict__ tab,
+                                                int T, float xd_in, float xv) {
+  constexpr int NK = LAP ? 3 : 1;
+  const float xc = fminf(fmaxf(xv, 0.f), 1.f);
+  const float xd = ((xv > 0.f) && (xv < 1.f)) ? xd_in : 0.f;
+  const float np_ = (float)(T - 1);
+  const NodeIdx n = node_index(xc, T);
+  const float sgn = cx.bv(o[WF_MAX_P - 1]) < 0.f ? -1.f : 1.f;
+  J A[NK];
+#pragma unroll
+  for (int k = 0; k < NK; ++k) A[k] = J{0.f, 0.f, 0.f};
+  J Q = {0.f, 0.f, 0.f};
+#pragma unroll
+  for (int j0 = 0; j0 < WF_MAX_P; j0 += 4) {
+    if (j0 < P) {
+      float f[NK][4];
+#pragma unroll
+      for (int k = 0; k < NK; ++k) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(tab + ((size_t)n.l * 4 + k) * WF_MAX_P + j0));
+        const float4 b = __ldg(reinterpret_cast<const float4*>(tab + ((size_t)n.r * 4 + k) * WF_MAX_P + j0));
+        f[k][0] = lerp_tab(a.x, b.x, np_, n.dx); f[k][1] = lerp_tab(a.y, b.y, np_, n.dx);
+        f[k][2] = lerp_tab(a.z, b.z, np_, n.dx); f[k][3] = lerp_tab(a.w, b.w, np_, n.dx);
+      }
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const float c = (j0 + t < P) ? o[j0 + t] : 0.f;
+        const float cv = cx.bv(c);
+#pragma unroll
+        for (int k = 0; k < NK; ++k) { A[k].m = fmaf(f[k][t], c, A[k].m); A[k].v = fmaf(f[k][t], cv, A[k].v); }
+        Q.v = fmaf(cv, cv, Q.v);
+        if constexpr (LAP) {
+          Q.m = cx.is_v ? Q.v : fmaf(2.f * cv, c, Q.m);
+          Q.p = cx.is_g ? fmaf(2.f * c, c, Q.p) : 0.f;
+        } else Q.m = Q.v;
+      }
+    }
+  }
+  J num;
+  if constexpr (LAP) num = spline_assemble<D, LAP>(cx, A[0], A[1], A[2], xd); else num = A[0];
+  const float isq = 1.f / sqrtf(Q.v);
+  const J iq = cx.unary(Q, isq, -0.5f * isq / Q.v, 0.75f * isq / (Q.v * Q.v));
+  return cx.scale(cx.mul(num, iq), sgn);
+}
+
+template <int D>
+__device__ __forceinline__ float soft_coulomb_tc(const float (&xs)[D], const float* protons, int n_protons) {
+  float pe = 0.f;
+  for (int p = 0; p < n_protons; ++p)
+#pragma unroll
+    for (int e = 0; e < D; ++e) { const float d = protons[p] - xs[e]; pe += 1.f / sqrtf(1.f + d * d); }
+  float ee = 0.f;
+#pragma unroll
+  for (int i = 1; i < D; ++i)
+#pragma unroll
+    for (int j = 0; j < i; ++j) { const float d = xs[i] - xs[j]; ee += 1.f / sqrtf(1.f + d * d); }
+  return ee - pe;
+}
+
+// Shared memory (1024-byte aligned): W2 hi | W2 lo | W3 hi | W3 lo | scratch [32][512] | reduction [4][16] doubles | barriers ...
+struct Smem {
+  static __host__ __device__ constexpr size_t w2_off() { return 0; }
+  static __host__ __device__ constexpr size_t w3_off() { return 2 * (size_t)W2_PLANE_BYTES; }
+  static __host__ __device__ constexpr size_t scr_off(int D) { return w3_off() + 2 * (size_t)w3_plane_bytes(D); }
+  static __host__ __device__ constexpr size_t red_off(int D) { return scr_off(D) + (size_t)SCR * THREADS * 4; }
+  static __host__ __device__ constexpr size_t bar_off(int D) { return red_off(D) + 4 * (THREADS / 32) * sizeof(double); }
+  static __host__ __device__ constexpr size_t total(int D) { return bar_off(D) + 128 + 1024; }   // + alignment slack
+};
+
+struct TcExtra {
+  p2p::Args xchg;            // estimator exchange in the kernel tail (world > 1), else peer_bufs == nullptr
+  unsigned int* done_counter;
+};
+
+template <int D, bool LAP>
+__global__ void __launch_bounds__(THREADS, 1) live_tc_kernel(const __grid_constant__ LiveParams P, const __grid_constant__ TcExtra X) {
+  using C = Ctx<D, LAP>;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  constexpr int N3 = D * WF_MAX_P;
+  constexpr int NETF = net_floats_tc(D);
+  constexpr uint32_t W2_BYTES = 2 * W2_PLANE_BYTES, W3_BYTES = 2 * w3_plane_bytes(D);
+  const wf_live_model& M = P.m;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tile = tid / TILE_THREADS;                 // 0 / 1
+  const int wg = (tid / 128) & 1;                      // warpgroup inside the tile
+  const int quarter = warp & 3;                        // TMEM lane quarter of this warp
+  const bool leader = (tid % TILE_THREADS) == 0;       // issues this tile's MMAs
+
+  unsigned char* w2_s = smem + Smem::w2_off();
+  unsigned char* w3_s = smem + Smem::w3_off();
+  float* scratch = reinterpret_cast<float*>(smem + Smem::scr_off(D));
+  double* red_s = reinterpret_cast<double*>(smem + Smem::red_off(D));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Smem::bar_off(D));
+  uint64_t* w2_full = bars;            // count 1 + tx
+  uint64_t* w3_full = bars + 1;
+  uint64_t* d_ready = bars + 2;        // [TILES], arrived by tcgen05.commit
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 4);
+  int* w_cnt = reinterpret_cast<int*>(tmem_ptr + 1);   // [2]: tiles done with W2 / W3 of the current net
+
+  if (tid == 0) {
+    mbar_init(w2_full, 1); mbar_init(w3_full, 1);
+    mbar_init(&d_ready[0], 1); mbar_init(&d_ready[1], 1);
+    w_cnt[0] = 0; w_cnt[1] = 0;
+    mbar_fence_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_ptr, 512);
+  fence_before();
+  __syncthreads();
+  fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+  const uint32_t cbase = tmem_base + (uint32_t)(tile * 256);
+  const uint32_t a_hi = cbase, a_lo = cbase + 64, dacc = cbase + 128;   // MMA operands (lane field 0)
+  const uint32_t my_hi = a_hi + lane_addr, my_lo = a_lo + lane_addr, my_acc = dacc + lane_addr;
+
+  C cx;
+  cx.init(lane);
+  const ScratchT S{scratch + tid};
+  const ScratchT Sp{scratch + (tid ^ 128)};            // the partner thread (same row, other warpgroup)
+  constexpr int WPT = 4 * C::WPW;                      // walkers per tile
+  const int64_t n_tiles = (P.N + WPT - 1) / WPT;
+  const int64_t slots = (int64_t)gridDim.x * TILES;
+  const int64_t rounds = (n_tiles + slots - 1) / slots;
+  const int n_nets = P.n_nets;
+  const bool has_prior_net = M.prior_kind == WF_KIND_B || M.prior_kind == WF_KIND_M;
+  const int64_t g_total = rounds * n_nets;
+  // dimensions of the spline glue handled by this warpgroup
+  const int d_lo = wg == 0 ? 0 : D / 2, d_hi = wg == 0 ? D / 2 : D;
+  const int fbase = wg * 32;                           // hidden features of the tanh layers handled by this warpgroup
+  double accE = 0.0, accE2 = 0.0, accN = 0.0, accP2 = 0.0;
+
+  auto issue_w2 = [&](int64_t g) {
+    mbar_expect_tx(w2_full, W2_BYTES);
+    bulk_g2s(w2_s, P.weights + (size_t)(g % n_nets) * NETF, W2_BYTES, w2_full);
+  };
+  auto issue_w3 = [&](int64_t g) {
+    mbar_expect_tx(w3_full, W3_BYTES);
+    bulk_g2s(w3_s, P.weights + (size_t)(g % n_nets) * NETF + W2_BYTES / 4, W3_BYTES, w3_full);
+  };
+  if (tid == 0 && g_total > 0) { issue_w2(0); issue_w3(0); }
+
+  int64_t g = 0;
+  for (int64_t round = 0; round < rounds; ++round) {
+    const int64_t tile_idx = round * slots + (int64_t)blockIdx.x * TILES + tile;
+    const int64_t w_raw = tile_idx * WPT + (int64_t)quarter * C::WPW + cx.slot;
+    const bool lane_live = (!LAP || lane < C::WPW * C::G) && w_raw < P.N;
+    const int64_t w = w_raw < P.N ? w_raw : P.N - 1;
+
+    float xs[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) xs[d] = __ldg(P.x + w * D + d);
+    float us[D];
+    J ld = cx.constant(0.f);
+    box_transform<D, LAP>(cx, M, xs, us, ld);
+    float ldf = wg == 0 ? cx.fold(ld) : 0.f;           // this warpgroup's share of log|det J| as a 1-register bundle
+    if (!LAP && wg != 0) ldf = 0.f;
+
+    float uout[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) uout[d] = 0.f;
+    if (M.n_layers == 0) {
+#pragma unroll
+      for (int d = 0; d < D; ++d) uout[d] = cx.bv(us[d]);
+    }
+    J psi = cx.constant(1.f);                           // product of this warpgroup's prior factors
+    float lp = 0.f;
+
+#pragma unroll 1
+    for (int net_idx = 0; net_idx < n_nets; ++net_idx, ++g) {
+      const bool is_prior = has_prior_net && net_idx == n_nets - 1;
+      const float* netw = P.weights + (size_t)net_idx * NETF;
+      const float* W1 = netw + (W2_BYTES + W3_BYTES) / 4;
+      const float* b1 = W1 + D * WF_HIDDEN;
+      const float* b2 = b1 + WF_HIDDEN;
+      const float* b3 = b2 + WF_HIDDEN;
+
+      // ------------------------------------------------ layer 1 (K = D, CUDA cores) -> A planes
+#pragma unroll 1
+      for (int c = 0; c < 2; ++c) {
+        float h[16];
+#pragma unroll
+        for (int t = 0; t < 16; ++t) {
+          const int j = fbase + c * 16 + t;
+          float acc = cx.is_v ? __ldg(b1 + j) : 0.f;
+#pragma unroll
+          for (int d = 0; d < D; ++d) acc = fmaf(us[d], __ldg(W1 + d * WF_HIDDEN + j), acc);
+          h[t] = tanh_bundle<D, LAP>(cx, acc);
+        }
+        store_planes16(my_hi, my_lo, (uint32_t)(fbase + c * 16), h);
+      }
+      tmem_wait_st();
+      fence_before();
+      bar_sync(1 + tile, TILE_THREADS);
+      if (leader) {
+        fence_after();
+        mbar_wait_guard(w2_full, (uint32_t)(g & 1));
+        issue_layer<WF_HIDDEN>(dacc, a_hi, a_lo, w2_s, w2_s + W2_PLANE_BYTES);
+        umma_commit(&d_ready[tile]);
+      }
+      mbar_wait_guard(&d_ready[tile], 0u);
+      fence_after();
+      if (leader) {                                     // the second tile to get here refills W2 with the next net
+        const int old = atomicAdd(&w_cnt[0], 1);
+        if (old == 2 * g + 1 && g + 1 < g_total) issue_w2(g + 1);
+      }
+
+      // ------------------------------------------------ layer 2 epilogue: bias + tanh -> A planes
+#pragma unroll 1
+      for (int c = 0; c < 2; ++c) {
+        float v[16], h[16];
+        tmem_ld16(my_acc + (uint32_t)(fbase + c * 16), v);
+#pragma unroll
+        for (int t = 0; t < 16; ++t) {
+          const float acc = cx.is_v ? v[t] + __ldg(b2 + fbase + c * 16 + t) : v[t];
+          h[t] = tanh_bundle<D, LAP>(cx, acc);
+        }
+        store_planes16(my_hi, my_lo, (uint32_t)(fbase + c * 16), h);
+      }
+      tmem_wait_st();
+      fence_before();
+      bar_sync(1 + tile, TILE_THREADS);
+      if (leader) {
+        fence_after();
+        mbar_wait_guard(w3_full, (uint32_t)(g & 1));
+        issue_layer<N3>(dacc, a_hi, a_lo, w3_s, w3_s + w3_plane_bytes(D));
+        umma_commit(&d_ready[tile]);
+      }
+      mbar_wait_guard(&d_ready[tile], 1u);
+      fence_after();
+      if (leader) {
+        const int old = atomicAdd(&w_cnt[1], 1);
+        if (old == 2 * g + 1 && g + 1 < g_total) issue_w3(g + 1);
+      }
+
+      // ------------------------------------------------ layer 3 epilogue: spline glue of this warpgroup's dimensions
+      float ys[D];
+#pragma unroll
+      for (int d = 0; d < D; ++d) ys[d] = 0.f;
+#pragma unroll 1
+      for (int d = d_lo; d < d_hi; ++d) {
+        float o[WF_MAX_P];
+        tmem_ld32(my_acc + (uint32_t)(d * WF_MAX_P), o);
+        if (cx.is_v) {
+#pragma unroll
+          for (int q = 0; q < WF_MAX_P; ++q) o[q] += __ldg(b3 + d * WF_MAX_P + q);
+        }
+        float xd = us[0];
+#pragma unroll
+        for (int dd = 1; dd < D; ++dd) xd = (d == dd) ? us[dd] : xd;
+        const float xv = cx.bv(xd);
+        if (!is_prior) {
+          J y, dy;
+          sigmoid_spline_regs<D, LAP, 2, true>(cx, o, S, M.P_I, P.wq_I, M.reg, P.rec_I, P.lo_I, P.tab_I, M.T, xd, xv, y, dy);
+          const float yf = cx.fold(y);
+#pragma unroll
+          for (int dd = 0; dd < D; ++dd) ys[dd] = (d == dd) ? yf : ys[dd];
+          const J l = cx.log(cx.addc(dy, LOG_TOL));
+          ldf += LAP ? cx.fold(l) : l.v;
+        } else {
+          const bool cons = M.coord_mean ? (d < D - 1) : (d >= 1);
+          if (M.prior_kind == WF_KIND_B) {
+            J phi = bprior_factor_regs<D, LAP>(cx, o, M.P_P, P.tab_P, M.T, xd, xv);
+            if (!LAP) {
+              float pr = phi.v * phi.v;
+              if (cons) pr = pr / 2.f;
+              lp += logf(pr + LOG_TOL);
+            }
+            if (cons) phi = cx.scale(phi, 0.70710678118654752f);
+            psi = cx.mul(psi, phi);
+          } else {
+            const float xc = fminf(fmaxf(xv, 0.f), 1.f);
+            const float xdc = (xv > 0.f && xv < 1.f) ? xd : 0.f;
+            J y, dy;
+            sigmoid_spline_regs<D, LAP, 1, false>(cx, o, S, M.P_P, P.wq_P, 0.f, P.rec_P, P.lo_P, P.tab_P, M.T, xdc, xc, y, dy);
+            lp += logf(y.v + LOG_TOL);
+          }
+        }
+      }
+      // ------------------------------------------------ exchange the per-dimension results between the two warpgroups
+      if (!is_prior) {
+#pragma unroll
+        for (int d = 0; d < D; ++d)
+          if (d >= d_lo && d < d_hi) S[d] = ys[d];
+        fence_before();                                 // (the accumulator columns are free again after this barrier)
+        bar_sync(1 + tile, TILE_THREADS);
+#pragma unroll
+        for (int d = 0; d < D; ++d)
+          if (!(d >= d_lo && d < d_hi)) ys[d] = Sp[d];
+#pragma unroll
+        for (int d = 0; d < D; ++d) us[d] = ys[D - 1 - d];          // Reverse (bijections.py:336-345)
+        if (net_idx == M.n_layers - 1) {
+#pragma unroll
+          for (int d = 0; d < D; ++d) uout[d] = cx.bv(us[d]);
+        }
+      }
+    }
+
+    // ------------------------------------------------ combine the two warpgroups: psi = prod phi * exp(0.5 log_det)
+    const float psif = cx.fold(psi);
+    bar_sync(1 + tile, TILE_THREADS);                   // partner finished reading the previous exchange
+    S[0] = psif; S[1] = ldf; S[2] = lp;
+    fence_before();
+    bar_sync(1 + tile, TILE_THREADS);
+    const float psif_o = Sp[0], ldf_o = Sp[1], lp_o = Sp[2];
+    // identical operand order in both warpgroups (warpgroup 0's share first): bit-identical totals
+    const float pa = wg == 0 ? psif : psif_o, pb = wg == 0 ? psif_o : psif;
+    const float la = wg == 0 ? ldf : ldf_o, lb = wg == 0 ? ldf_o : ldf;
+    const float lp_tot = (wg == 0 ? lp : lp_o) + (wg == 0 ? lp_o : lp);
+    const float ld_tot = la + lb;
+    const J LD = J{ld_tot, 0.f, cx.bv(ld_tot)};
+    J psi_t = cx.mul(J{pa, 0.f, cx.bv(pa)}, J{pb, 0.f, cx.bv(pb)});
+    if (M.prior_kind == WF_KIND_B) psi_t = cx.mul(psi_t, cx.exp(cx.scale(LD, 0.5f)));
+    const float psi1 = cx.fold(psi_t);
+
+    // ------------------------------------------------ outputs (warpgroup 0 writes)
+    const bool writer = wg == 0 && lane_live;
+    if (writer && cx.is_v) {
+      if (P.u) {
+#pragma unroll
+        for (int d = 0; d < D; ++d) P.u[w * D + d] = uout[d];
+      }
+      if (P.logdet) P.logdet[w] = LD.v;
+      if (P.logpdf) P.logpdf[w] = lp_tot + LD.v;
+      if (P.psi) P.psi[w] = psi_t.v;
+    }
+    if constexpr (LAP) {
+      const float lapv = __shfl_sync(FULL, psi1, cx.gbase + D + 1);
+      if (writer && cx.is_g && P.grad) P.grad[w * D + (cx.comp - 1)] = psi1;
+      if (writer && cx.is_v) {
+        const float V = soft_coulomb_tc<D>(xs, P.protons, P.n_protons);
+        const float hp = fmaf(-0.5f, lapv, V * psi_t.v);         // physics.py:84
+        const float el = hp / (psi_t.v + 1e-8f);                // vqmc.py:200
+        if (P.lap) P.lap[w] = lapv;
+        if (P.hpsi) P.hpsi[w] = hp;
+        if (P.eloc) P.eloc[w] = el;
+        accE += (double)el; accE2 += (double)el * (double)el; accN += 1.0; accP2 += (double)psi_t.v * (double)psi_t.v;
+      }
+    }
+  }
+
+  bool last_cta = false;
+  if constexpr (LAP) {
+    if (P.sums) {
+      double v[4] = {accE, accE2, accN, accP2};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v[k] += __shfl_xor_sync(FULL, v[k], off);
+        if (lane == 0) red_s[k * (THREADS / 32) + warp] = v[k];
+      }
+      __syncthreads();
+      if (tid < 4) {
+        double s = 0.0;
+        for (int i = 0; i < THREADS / 32; ++i) s += red_s[tid * (THREADS / 32) + i];
+        atomicAdd(P.sums + tid, s);
+      }
+      // estimator exchange in the tail of the kernel: the last CTA to retire publishes the block sums to the peers
+      if (X.xchg.peer_bufs != nullptr) {
+        __shared__ int is_last;
+        __syncthreads();
+        if (tid == 0) {
+          __threadfence();
+          const unsigned int done = atomicAdd(X.done_counter, 1u);
+          is_last = (done == gridDim.x - 1) ? 1 : 0;
+          if (is_last) *X.done_counter = 0u;                 // ready for the next launch
+        }
+        __syncthreads();
+        last_cta = is_last != 0;
+      }
+    }
+  }
+  fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 512);
+  if constexpr (LAP) {
+    if (last_cta && warp == 1) {
+      __threadfence();
+      __shared__ double xv_s[p2p::MAX_WORLD * 4];
+      __shared__ double loc_s[4];
+      if (lane < 4) loc_s[lane] = atomicAdd(P.sums + lane, 0.0);     // coherent read of the completed sums
+      __syncwarp();
+      p2p::allreduce_warp(X.xchg, loc_s, xv_s, p2p::TIMEOUT_CYCLES);
+    }
+  }
+}
+
+template <int D, bool LAP>
+int launch_live_tc(LiveParams& P, const TcExtra& X, cudaStream_t s) {
+  const size_t smem = Smem::total(D);
+  if (smem > 227 * 1024) return WF_ERR_UNSUPPORTED;
+  const int wpw = LAP ? 32 / (D + 2) : 32;
+  const int64_t wpt = 4 * wpw;
+  const int64_t n_tiles = (P.N + wpt - 1) / wpt;
+  const int64_t want = (n_tiles + TILES - 1) / TILES;
+  const int blocks = (int)(want < num_sms() ? want : num_sms());
+  WF_CUDA(cudaFuncSetAttribute(live_tc_kernel<D, LAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  live_tc_kernel<D, LAP><<<blocks, THREADS, smem, s>>>(P, X);
+  WF_LAUNCH_CHECK();
+  return WF_OK;
+}
+
+}  // namespace ltc
+
+#define WF_DECL_LIVE_TC(D) \
+  int launch_live_tc_d##D##_lap0(LiveParams& P, const ltc::TcExtra& X, cudaStream_t s); \
+  int launch_live_tc_d##D##_lap1(LiveParams& P, const ltc::TcExtra& X, cudaStream_t s);
+WF_DECL_LIVE_TC(2) WF_DECL_LIVE_TC(3) WF_DECL_LIVE_TC(4)
+#undef WF_DECL_LIVE_TC
+
+}  // namespace wf

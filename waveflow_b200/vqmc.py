@@ -136,9 +136,14 @@ class PeerExchange:
         self.handle = symm_mem.rendezvous(self.buf, group)
         self.ptrs = torch.tensor([int(p) for p in self.handle.buffer_ptrs], dtype=torch.int64, device=device)
         self.out = torch.zeros(4, dtype=torch.float64, device=device)
+        self.counter = torch.zeros(1, dtype=torch.int32, device=device)      # CTA retirement counter of the fused tail
         self.step = 0
         torch.cuda.synchronize(device)
         dist.barrier(group)                       # every buffer is zeroed and mapped before the first flag is written
+
+    def next_step(self) -> int:
+        self.step += 1
+        return self.step
 
     def all_reduce(self, sums: torch.Tensor) -> torch.Tensor:
         from ._ffi import check, lib, ptr, stream_ptr
@@ -185,6 +190,15 @@ class EnergyEstimator:
         _live.local_energy(self.spec, self.packed, walkers, self.h_fn.protons, want=(), sums=sums)
         return sums
 
+    def step_sums(self, walkers: torch.Tensor, sums: torch.Tensor) -> torch.Tensor:
+        """One estimator step: local block sums of this rank's walkers + the exchange, -> the global sums on every rank.
+        With a peer exchange this is ONE call of wf_local_energy_exchange (on the tensor-core path one kernel launch: the
+        last CTA to retire does the peer stores and the flag wait); otherwise local_sums followed by exchange."""
+        if _world(self.group) > 1 and self.peer is not None:
+            _live.local_energy(self.spec, self.packed, walkers, self.h_fn.protons, want=(), sums=sums, exchange=self.peer)
+            return self.peer.out
+        return self.exchange(self.local_sums(walkers, sums))
+
     def exchange(self, sums: torch.Tensor) -> torch.Tensor:
         """Device-side exchange of the block sums (no host synchronisation): -> the global sums on every rank."""
         if _world(self.group) == 1:
@@ -218,7 +232,7 @@ class EnergyEstimator:
 
     def estimate(self, walkers: torch.Tensor):
         """-> dict(energy, variance, n) over all ranks."""
-        return self.finish_checked(self.exchange(self.local_sums(walkers)))
+        return self.finish_checked(self.step_sums(walkers, torch.zeros(4, dtype=torch.float64, device=self.device)))
 
 
 class ModelTrainer:
