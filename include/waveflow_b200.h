@@ -159,6 +159,8 @@ typedef struct wf_live_tables {
   const int32_t* lo_P;
   const float* ob_to_b;
   const float* b_to_ob;   /* [P_P][P_P], B prior, sampler only (bsplines_jax.py:163-165) */
+  const float* rec_I_t;   /* rec_I transposed to [T][8][4] (window slot major, the 4 derivative orders contiguous); needed by */
+  const float* rec_P_t;   /* the WF_WEIGHTS_TC kernels only (rec_P_t: M prior), 16-byte aligned, else NULL                   */
 } wf_live_tables;
 
 /* Packed weights (device, float32), one block per conditioner, IMADE nets first then the prior net; per net

@@ -378,6 +378,35 @@ def log_pdf(m: LiveModel, params, x: np.ndarray, return_sample: bool = False):
     return lp
 
 
+# --------------------------------------------------------------------------- f2: samplers (statistical parity only)
+def mspline_rejection_sample(m: LiveModel, c: np.ndarray, rng: np.random.Generator) -> np.ndarray:
+    """MSpline_fun.sample_fun_vec with num_samples = 1 (msplines_jax.py:129-154): per row, propose x ~ U(0,1), y ~ U(0, ymax)
+    with the convex-hull bound ymax = max(c) * n_knots (:145-148) until y < sum_q c_q M_q(x).  c [N, P] -> x [N].
+    The random stream is numpy's, not JAX's threefry: the draws agree with the reference in distribution only."""
+    N, P = c.shape
+    ymax = c.max(-1) * c.dtype.type(P + m.k_p)              # n_knots = len(knots) = P + k (msplines_jax.py:72-75)
+    x = np.zeros(N, dtype=c.dtype)
+    todo = np.arange(N)
+    while todo.size:
+        xs = rng.uniform(0.0, 1.0, todo.size).astype(c.dtype)
+        ys = rng.uniform(0.0, 1.0, todo.size).astype(c.dtype) * ymax[todo]
+        ok = ys < spline_apply(m.tab_P, c[todo], xs, 0)
+        x[todo[ok]] = xs[ok]
+        todo = todo[~ok]
+    return x
+
+
+def mflow_sample(m: LiveModel, params, n: int, rng: np.random.Generator, dtype=np.float32):
+    """MFlow.sample (distributions.py:165-190): D rounds of (prior conditioner on the columns drawn so far -> rejection
+    sample of column i), then Serial.inverse_fun.  -> (x [n, D] data space, u [n, D] prior space)."""
+    tp, sp = params
+    u = np.zeros((n, m.D), dtype=dtype)
+    for i in range(m.D):
+        c = prior_coeffs(m, sp, u).reshape(n, m.D, m.P_P)[:, i, :]
+        u[:, i] = mspline_rejection_sample(m, np.ascontiguousarray(c), rng)
+    return flow_inverse(m, tp, u), u
+
+
 # --------------------------------------------------------------------------- a12: potential
 def potential(x: np.ndarray, protons: np.ndarray) -> np.ndarray:
     """get_potential (utils/physics.py:60-76): soft-Coulomb, 1 space dimension per particle."""

@@ -37,7 +37,8 @@ class LiveModelStruct(C.Structure):
 
 class LiveTablesStruct(C.Structure):
     """struct wf_live_tables (include/waveflow_b200.h): device pointers."""
-    _fields_ = [(n, C.c_void_p) for n in ("dense_I", "rec_I", "lo_I", "dense_P", "rec_P", "lo_P", "ob_to_b", "b_to_ob")]
+    _fields_ = [(n, C.c_void_p) for n in ("dense_I", "rec_I", "lo_I", "dense_P", "rec_P", "lo_P", "ob_to_b", "b_to_ob",
+                                          "rec_I_t", "rec_P_t")]
 
 
 def _load() -> C.CDLL:

@@ -189,8 +189,10 @@ def pack_tc(spec: LiveSpec, packed: torch.Tensor) -> torch.Tensor:
     return out
 
 
-TC_MIN_ROWS = 4096      # below this many (walker, component) rows the batch does not fill the SMs' tiles: CUDA-core kernel
-TC_AUTO = False         # 'auto' picks the tensor-core kernels (flipped once they are validated and measured on the B200)
+# 'auto' = the tensor-core kernels whenever the model has an image: measured on the B200 (tools/tc_time.py) they are faster
+# than the CUDA-core kernels at every batch size tried, 256 ... 65 536 walkers (1.05x - 2.8x), so there is no size threshold
+TC_MIN_ROWS = 0
+TC_AUTO = True
 
 
 def select_weights(spec: LiveSpec, weights: torch.Tensor, n: int, lap: bool, mode: str | None = None):
@@ -231,13 +233,13 @@ def _tables(spec: LiveSpec, device) -> _ffi.LiveTablesStruct:
     t = _ffi.LiveTablesStruct()
     dI = spec.tab_I.dev(device)
     p = lambda x: None if x is None else x.data_ptr()
-    t.dense_I, t.rec_I, t.lo_I = p(dI["dense32"]), p(dI["rec"]), p(dI["lo"])
+    t.dense_I, t.rec_I, t.lo_I, t.rec_I_t = p(dI["dense32"]), p(dI["rec"]), p(dI["lo"]), p(dI["rec_t"])
     if spec.prior == "B":
         dP = spec.tab_P.dev(device)
         t.dense_P, t.ob_to_b, t.b_to_ob = p(dP["ob_dense32"]), p(dP["ob_to_b"]), p(dP["b_to_ob"])
     elif spec.prior == "M":
         dP = spec.tab_P.dev(device)
-        t.dense_P, t.rec_P, t.lo_P = p(dP["dense32"]), p(dP["rec"]), p(dP["lo"])
+        t.dense_P, t.rec_P, t.lo_P, t.rec_P_t = p(dP["dense32"]), p(dP["rec"]), p(dP["lo"]), p(dP["rec_t"])
     return t
 
 

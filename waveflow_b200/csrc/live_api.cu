@@ -53,6 +53,14 @@ int fill_params(const wf_live_model* m, const wf_live_tables* t, const float* we
   P.n_nets = m->n_layers + (pnet ? 1 : 0);
   coeff_weights(WF_KIND_I, m->k_I, m->P_I, m->bc_I, true, P.wq_I);
   if (pnet) coeff_weights(m->prior_kind, m->k_P, m->P_P, m->bc_P, m->prior_kind == WF_KIND_M, P.wq_P);
+  P.rec_I_t = t->rec_I_t; P.rec_P_t = t->rec_P_t;
+  for (int q = 0; q < m->P_I; ++q) P.wsum_I += P.wq_I[q];
+  if (pnet) for (int q = 0; q < m->P_P; ++q) P.wsum_P += P.wq_P[q];
+  if (m->weight_layout == WF_WEIGHTS_TC) {
+    if (m->n_layers > 0 && !t->rec_I_t) return WF_ERR_INVALID_ARG;
+    if (m->prior_kind == WF_KIND_M && !t->rec_P_t) return WF_ERR_INVALID_ARG;
+    if ((reinterpret_cast<uintptr_t>(t->rec_I_t) & 15) || (reinterpret_cast<uintptr_t>(t->rec_P_t) & 15)) return WF_ERR_INVALID_ARG;
+  }
   return WF_OK;
 }
 

@@ -95,6 +95,46 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+  tmem_wait_ld();
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+// issue only: the registers are valid after the next tmem_wait_ld() (lets the next chunk's load fly under the current chunk's math)
+__device__ __forceinline__ void tmem_ld8_issue(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+}
+// wait::ld that names the destination registers as read-write operands: uses of them cannot be scheduled above the wait
+__device__ __forceinline__ void tmem_wait_ld8(uint32_t (&r)[8]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7])
+               :: "memory");
+}
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, float (&v)[4]) {
+  uint32_t r[4];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr));
+  tmem_wait_ld();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ float tmem_ld1(uint32_t taddr) {
+  uint32_t r;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];\n" : "=r"(r) : "r"(taddr));
+  tmem_wait_ld();
+  return __uint_as_float(r);
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
+               "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};\n" ::"r"(taddr),
@@ -113,10 +153,19 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(const void* p) {
 __host__ __device__ constexpr uint32_t instr_desc_tf32(int n) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
-__device__ __forceinline__ float tf32_rn(float a) {
-  uint32_t u = __float_as_uint(a);
+__device__ __host__ __forceinline__ float tf32_rn(float a) {       // round-to-nearest-even to TF32 (weight images, host tests)
+  uint32_t u;
+  memcpy(&u, &a, 4);
   u += 0x0FFFu + ((u >> 13) & 1u);
-  return __uint_as_float(u & 0xFFFFE000u);
+  u &= 0xFFFFE000u;
+  memcpy(&a, &u, 4);
+  return a;
+}
+// activations: one instruction (cvt.rna.tf32.f32, round to nearest, ties away)
+__device__ __forceinline__ float tf32_rna(float a) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(a));
+  return __uint_as_float(u);
 }
 
 // mbarrier wait with a watchdog: a protocol error must end the kernel (trap -> launch failure), never hang the device
@@ -133,21 +182,25 @@ __device__ __forceinline__ void mbar_wait_guard(uint64_t* bar, uint32_t parity) 
   }
 }
 
-// One conditioner layer on the tensor cores: acc[128 x N] = A (hi + lo planes in TMEM) x W^T (hi / lo images in shared memory)
-template <int N>
-__device__ __forceinline__ void issue_layer(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, const unsigned char* b_hi, const unsigned char* b_lo) {
-  constexpr uint32_t idesc = instr_desc_tf32(N);
-#pragma unroll
-  for (int kb = 0; kb < WF_HIDDEN / 32; ++kb) {
-    const uint64_t dh = smem_desc_sw128(b_hi + (size_t)kb * N * 128), dl = smem_desc_sw128(b_lo + (size_t)kb * N * 128);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const uint32_t acol = (uint32_t)(kb * 32 + k * 8);
-      const uint64_t adv = (uint64_t)((k * 32) >> 4);       // 32 bytes per k-step inside the 128-byte swizzle span
-      umma_tf32_ts(d_tmem, a_hi + acol, dh + adv, idesc, (kb | k) != 0 ? 1u : 0u);
-      umma_tf32_ts(d_tmem, a_hi + acol, dl + adv, idesc, 1u);
-      umma_tf32_ts(d_tmem, a_lo + acol, dh + adv, idesc, 1u);
-    }
+// 32 output columns of one conditioner layer on the tensor cores:
+//   acc[128 x 32] = A (hi + lo planes in TMEM) x W[rows r0 .. r0 + 31]^T (hi / lo images in shared memory, N_ROWS rows per k-block).
+// The layers are issued in 32-column groups, each committed to its own mbarrier, so that the warpgroup that consumes a group
+// starts its epilogue as soon as THAT group is done instead of waiting for the whole layer.
+template <int N_ROWS>
+__device__ __forceinline__ void issue_group32(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, const unsigned char* b_hi,
+                                              const unsigned char* b_lo, int r0) {
+  constexpr uint32_t idesc = instr_desc_tf32(32);
+  uint64_t dh = smem_desc_sw128(b_hi + (size_t)r0 * 128), dl = smem_desc_sw128(b_lo + (size_t)r0 * 128);
+  // rolled on purpose (code size: the kernel must stay inside the instruction cache); 8 k-steps x 3 MMAs
+#pragma unroll 1
+  for (int ks = 0; ks < WF_HIDDEN / 8; ++ks) {
+    const uint32_t acol = (uint32_t)(ks * 8);
+    umma_tf32_ts(d_tmem, a_hi + acol, dh, idesc, ks != 0 ? 1u : 0u);
+    umma_tf32_ts(d_tmem, a_hi + acol, dl, idesc, 1u);
+    umma_tf32_ts(d_tmem, a_lo + acol, dh, idesc, 1u);
+    // next k-step: 32 bytes further inside the 128-byte swizzle span, or the start of the next 32-float k-block
+    const uint64_t adv = ((ks & 3) == 3) ? (uint64_t)((N_ROWS * 128 - 96) >> 4) : (uint64_t)(32 >> 4);
+    dh += adv; dl += adv;
   }
 }
 
@@ -156,28 +209,36 @@ struct ScratchT {
   __device__ __forceinline__ float& operator[](int slot) const { return col[slot * THREADS]; }
 };
 
-// 16 activations -> TF32-exact planes -> this thread's row of the A operand (columns col .. col + 15)
-__device__ __forceinline__ void store_planes16(uint32_t a_hi, uint32_t a_lo, uint32_t col, const float (&h)[16]) {
-  uint32_t hi[16], lo[16];
+// 8 activations -> (hi, lo) planes -> this thread's row of the A operand (columns col .. col + 7).
+// hi = TF32(h) (round to nearest), lo = h - hi EXACTLY (|lo| <= 2^-11 |h|); the tensor core reads the top 19 bits of lo,
+// i.e. truncates it: the pair carries h to 2^-21 relative, 2 instructions per value.
+__device__ __forceinline__ void store_planes8(uint32_t a_hi, uint32_t a_lo, uint32_t col, const float (&h)[8]) {
+  uint32_t hi[8], lo[8];
 #pragma unroll
-  for (int t = 0; t < 16; ++t) {
-    const float f = tf32_rn(h[t]);
+  for (int t = 0; t < 8; ++t) {
+    const float f = tf32_rna(h[t]);
     hi[t] = __float_as_uint(f);
-    lo[t] = __float_as_uint(tf32_rn(h[t] - f));
+    lo[t] = __float_as_uint(h[t] - f);
   }
-  tmem_st16(a_hi + col, hi);
-  tmem_st16(a_lo + col, lo);
+  tmem_st8(a_hi + col, hi);
+  tmem_st8(a_lo + col, lo);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
 // sigmoid_spline of live_device.cuh with the conditioner outputs in REGISTERS (read from tensor memory): pass A is unrolled
 // over the 32 coefficient slots; only s_q's own component is parked in the scratch column for the window pass, whose
 // pending second-derivative term is rebuilt from it:  p = s'' o'^2 = (1 - 2 s) m^2 / (s (1 - s))  with  m = s' o'.
+// The running sums carry only this lane's component (m) and the pending term (p); the VALUE of a sum, which every lane
+// needs for the products that follow, is the value lane's m and is fetched by one shuffle per sum at the end (same bits as
+// accumulating it redundantly on every lane, 3 FMAs per coefficient cheaper).
+// rec_t: the compact node records transposed to [node][8 window slots][4 derivative orders], one 128-bit load per slot.
+struct MP { float m, p; };
+
 template <int D, bool LAP, int NOUT, bool PREFIX_ONE>
-__device__ __forceinline__ void sigmoid_spline_regs(const Ctx<D, LAP>& cx, const float (&o)[WF_MAX_P], const ScratchT& S, int P,
-                                                    const float* __restrict__ wq, float reg, const float* __restrict__ rec,
-                                                    const int32_t* __restrict__ lo, const float* __restrict__ dense, int T, float xd,
-                                                    float xv, J& y, J& dy) {
+__device__ __forceinline__ void sigmoid_spline_regs(const Ctx<D, LAP>& cx, uint32_t tacc, const float* __restrict__ bias,
+                                                    const ScratchT& S, int P, const float* __restrict__ wq, float wsum, float reg,
+                                                    const float4* __restrict__ rec_t, const int32_t* __restrict__ lo,
+                                                    const float* __restrict__ dense, int T, float xd, float xv, J& y, J& dy) {
   constexpr int NK = LAP ? NOUT + 2 : NOUT;
   const float np_ = (float)(T - 1);
   const NodeIdx n = node_index(xv, T);
@@ -185,27 +246,47 @@ __device__ __forceinline__ void sigmoid_spline_regs(const Ctx<D, LAP>& cx, const
   const int sh = lo_r - lo_l;
   const bool local = (sh == 0) || (sh == 1);
   const int lo_w = local ? lo_l : 0;
+  auto axpy = [&](float s, const J& a, MP& acc) {
+    acc.m = fmaf(s, a.m, acc.m);
+    if constexpr (LAP) acc.p = fmaf(s, a.p, acc.p);
+  };
+  auto full = [&](const MP& a) { return J{a.m, LAP ? a.p : 0.f, cx.bv(a.m)}; };
 
-  J Ssum = {0.f, 0.f, 0.f}, SW = {0.f, 0.f, 0.f}, PRE = {0.f, 0.f, 0.f};
-  float Wsum = 0.f, Wpre = 0.f;
+  MP Ssum = {0.f, 0.f}, SW = {0.f, 0.f}, PRE = {0.f, 0.f};
+  float Wpre = 0.f;
+  // conditioner outputs of this dimension: 8 accumulator columns at a time straight from tensor memory (+ bias on the value
+  // lane); the chunk loop stays rolled to keep the kernel inside the instruction cache
+  uint32_t nxt[8];
+  tmem_ld8_issue(tacc, nxt);
+  tmem_wait_ld8(nxt);
+#pragma unroll 1
+  for (int c = 0; c < WF_MAX_P / 8; ++c) {
+    float o8[8];
 #pragma unroll
-  for (int q = 0; q < WF_MAX_P; ++q) {
-    if (q < P) {
-      const float ov = cx.bv(o[q]);
-      const float s = fast_sigmoid(ov);
-      const float d1 = s * (1.f - s);
-      const J sq = cx.unary(J{o[q], 0.f, ov}, s, d1, d1 * (1.f - 2.f * s));
-      const float w = wq[q];
-      Ssum = cx.add(Ssum, sq);
-      SW = cx.axpy(w, sq, SW);
-      Wsum += w;
-      if (PREFIX_ONE) {
-        const float wp = (q < lo_w) ? w : 0.f;
-        PRE = cx.axpy(wp, sq, PRE);
-        Wpre += wp;
+    for (int t = 0; t < 8; ++t) o8[t] = __uint_as_float(nxt[t]);
+    if (c + 1 < WF_MAX_P / 8) tmem_ld8_issue(tacc + (uint32_t)((c + 1) * 8), nxt);      // lands while this chunk is processed
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      const int q = c * 8 + t;
+      if (q < P) {
+        const float oq = cx.is_v ? o8[t] + bias[q] : o8[t];
+        const float ov = cx.bv(oq);
+        const float s = fast_sigmoid(ov);
+        const float d1 = s * (1.f - s);
+        const J sq = cx.unary(J{oq, 0.f, ov}, s, d1, d1 * (1.f - 2.f * s));
+        const float w = wq[q];
+        Ssum.m += sq.m;
+        if constexpr (LAP) Ssum.p += sq.p;
+        axpy(w, sq, SW);
+        if (PREFIX_ONE) {
+          const float wp = (q < lo_w) ? w : 0.f;
+          axpy(wp, sq, PRE);
+          Wpre += wp;
+        }
+        S[q] = sq.m;
       }
-      S[q] = sq.m;
     }
+    tmem_wait_ld8(nxt);
   }
   auto reload = [&](int qc) {
     J sq;
@@ -217,10 +298,10 @@ __device__ __forceinline__ void sigmoid_spline_regs(const Ctx<D, LAP>& cx, const
     } else sq.p = 0.f;
     return sq;
   };
-  J Sk[NK];
+  MP Sk[NK];
   float Wk[NK];
 #pragma unroll
-  for (int k = 0; k < NK; ++k) { Sk[k] = J{0.f, 0.f, 0.f}; Wk[k] = 0.f; }
+  for (int k = 0; k < NK; ++k) { Sk[k] = MP{0.f, 0.f}; Wk[k] = 0.f; }
   if (PREFIX_ONE) { Sk[0] = PRE; Wk[0] = Wpre; }
   if (local) {
 #pragma unroll 2
@@ -229,21 +310,23 @@ __device__ __forceinline__ void sigmoid_spline_regs(const Ctx<D, LAP>& cx, const
       const int qc = q < P ? q : P - 1;
       const float w = q < P ? wq[qc] : 0.f;
       const J sq = reload(qc);
-      const int tr = t - sh;
+      const int tr = t - sh;                     // slot of this basis in the right node's record
+      const float4 L4 = __ldg(rec_t + (size_t)n.l * WF_WIN + t);
+      const float4 R4 = __ldg(rec_t + (size_t)n.r * WF_WIN + (tr < 0 ? 0 : tr));
+      const float yl[4] = {L4.x, L4.y, L4.z, L4.w};
+      const float yrr[4] = {R4.x, R4.y, R4.z, R4.w};
 #pragma unroll
       for (int k = 0; k < NK; ++k) {
         const int nd = k < 3 ? k : 3;
-        const float yl = __ldg(rec + ((size_t)n.l * 4 + nd) * WF_WIN + t);
-        const float yrr = __ldg(rec + ((size_t)n.r * 4 + nd) * WF_WIN + (tr < 0 ? 0 : tr));
-        const float yr = tr < 0 ? ((PREFIX_ONE && nd == 0) ? 1.f : 0.f) : yrr;
-        const float fw = lerp_tab(yl, yr, np_, n.dx) * w;
-        Sk[k] = cx.axpy(fw, sq, Sk[k]);
+        const float yr = tr < 0 ? ((PREFIX_ONE && nd == 0) ? 1.f : 0.f) : yrr[nd];
+        const float fw = lerp_tab(yl[nd], yr, np_, n.dx) * w;
+        axpy(fw, sq, Sk[k]);
         Wk[k] += fw;
       }
     }
   } else {
     // reference-exact dense evaluation (arguments outside [0, 1]: JAX gather wrap / clamp semantics)
-    if (PREFIX_ONE) { Sk[0] = J{0.f, 0.f, 0.f}; Wk[0] = 0.f; }
+    if (PREFIX_ONE) { Sk[0] = MP{0.f, 0.f}; Wk[0] = 0.f; }
     for (int q = 0; q < P; ++q) {
       const J sq = reload(q);
       const float w = wq[q];
@@ -253,16 +336,17 @@ __device__ __forceinline__ void sigmoid_spline_regs(const Ctx<D, LAP>& cx, const
         const float yl = __ldg(dense + ((size_t)n.l * 4 + nd) * WF_MAX_P + q);
         const float yr = __ldg(dense + ((size_t)n.r * 4 + nd) * WF_MAX_P + q);
         const float fw = lerp_tab(yl, yr, np_, n.dx) * w;
-        Sk[k] = cx.axpy(fw, sq, Sk[k]);
+        axpy(fw, sq, Sk[k]);
         Wk[k] += fw;
       }
     }
   }
-  const J r = cx.recip(Ssum);
-  const J iz = cx.recip(cx.addc(cx.mul(SW, r), reg * Wsum));
+  // r = 1/S;  Z = SW * r + reg * Wsum;  iz = 1/Z;  N_k = Sk * r + reg * Wk;  A_k = N_k * iz
+  const J r = cx.recip(full(Ssum));
+  const J iz = cx.recip(cx.addc(cx.mul(full(SW), r), reg * wsum));
   J A[NK];
 #pragma unroll
-  for (int k = 0; k < NK; ++k) A[k] = cx.mul(cx.addc(cx.mul(Sk[k], r), reg * Wk[k]), iz);
+  for (int k = 0; k < NK; ++k) A[k] = cx.mul(cx.addc(cx.mul(full(Sk[k]), r), reg * Wk[k]), iz);
   if constexpr (LAP) {
     y = spline_assemble<D, LAP>(cx, A[0], A[1], A[2], xd);
     if (NOUT == 2) dy = spline_assemble<D, LAP>(cx, A[1], A[2], A[NK - 1], xd);
@@ -272,44 +356,46 @@ __device__ __forceinline__ void sigmoid_spline_regs(const Ctx<D, LAP>& cx, const
   }
 }
 
-// B prior factor with the third layer pre-multiplied by mask @ ob_to_b (bit 2 of bc_P; see bprior_factor): o[q] = c'_q,
-// o[31] = sum of the raw conditioner outputs.  Everything in registers.
+// B prior factor with the third layer pre-multiplied by mask @ ob_to_b (bit 2 of bc_P; see bprior_factor): accumulator column q
+// of this dimension holds c'_q, column 31 the sum of the raw conditioner outputs.  Four columns at a time from tensor memory.
 template <int D, bool LAP>
-__device__ __forceinline__ J bprior_factor_regs(const Ctx<D, LAP>& cx, const float (&o)[WF_MAX_P], int P, const float* __restrict__ tab,
-                                                int T, float xd_in, float xv) {
+__device__ __forceinline__ J bprior_factor_regs(const Ctx<D, LAP>& cx, uint32_t tacc, const float* __restrict__ bias, int P,
+                                                const float* __restrict__ tab, int T, float xd_in, float xv) {
   constexpr int NK = LAP ? 3 : 1;
   const float xc = fminf(fmaxf(xv, 0.f), 1.f);
   const float xd = ((xv > 0.f) && (xv < 1.f)) ? xd_in : 0.f;
   const float np_ = (float)(T - 1);
   const NodeIdx n = node_index(xc, T);
-  const float sgn = cx.bv(o[WF_MAX_P - 1]) < 0.f ? -1.f : 1.f;
+  const float osum = tmem_ld1(tacc + (uint32_t)(WF_MAX_P - 1));
+  const float sgn = cx.bv(cx.is_v ? osum + bias[WF_MAX_P - 1] : osum) < 0.f ? -1.f : 1.f;
   J A[NK];
 #pragma unroll
   for (int k = 0; k < NK; ++k) A[k] = J{0.f, 0.f, 0.f};
   J Q = {0.f, 0.f, 0.f};
+#pragma unroll 1
+  for (int j0 = 0; j0 < P; j0 += 4) {
+    float o4[4];
+    tmem_ld4(tacc + (uint32_t)j0, o4);
+    float f[NK][4];
 #pragma unroll
-  for (int j0 = 0; j0 < WF_MAX_P; j0 += 4) {
-    if (j0 < P) {
-      float f[NK][4];
+    for (int k = 0; k < NK; ++k) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(tab + ((size_t)n.l * 4 + k) * WF_MAX_P + j0));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(tab + ((size_t)n.r * 4 + k) * WF_MAX_P + j0));
+      f[k][0] = lerp_tab(a.x, b.x, np_, n.dx); f[k][1] = lerp_tab(a.y, b.y, np_, n.dx);
+      f[k][2] = lerp_tab(a.z, b.z, np_, n.dx); f[k][3] = lerp_tab(a.w, b.w, np_, n.dx);
+    }
 #pragma unroll
-      for (int k = 0; k < NK; ++k) {
-        const float4 a = __ldg(reinterpret_cast<const float4*>(tab + ((size_t)n.l * 4 + k) * WF_MAX_P + j0));
-        const float4 b = __ldg(reinterpret_cast<const float4*>(tab + ((size_t)n.r * 4 + k) * WF_MAX_P + j0));
-        f[k][0] = lerp_tab(a.x, b.x, np_, n.dx); f[k][1] = lerp_tab(a.y, b.y, np_, n.dx);
-        f[k][2] = lerp_tab(a.z, b.z, np_, n.dx); f[k][3] = lerp_tab(a.w, b.w, np_, n.dx);
-      }
+    for (int t = 0; t < 4; ++t) {
+      const float oq = cx.is_v ? o4[t] + bias[j0 + t] : o4[t];
+      const float c = (j0 + t < P) ? oq : 0.f;
+      const float cv = cx.bv(c);
 #pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        const float c = (j0 + t < P) ? o[j0 + t] : 0.f;
-        const float cv = cx.bv(c);
-#pragma unroll
-        for (int k = 0; k < NK; ++k) { A[k].m = fmaf(f[k][t], c, A[k].m); A[k].v = fmaf(f[k][t], cv, A[k].v); }
-        Q.v = fmaf(cv, cv, Q.v);
-        if constexpr (LAP) {
-          Q.m = cx.is_v ? Q.v : fmaf(2.f * cv, c, Q.m);
-          Q.p = cx.is_g ? fmaf(2.f * c, c, Q.p) : 0.f;
-        } else Q.m = Q.v;
-      }
+      for (int k = 0; k < NK; ++k) { A[k].m = fmaf(f[k][t], c, A[k].m); A[k].v = fmaf(f[k][t], cv, A[k].v); }
+      Q.v = fmaf(cv, cv, Q.v);
+      if constexpr (LAP) {
+        Q.m = cx.is_v ? Q.v : fmaf(2.f * cv, c, Q.m);
+        Q.p = cx.is_g ? fmaf(2.f * c, c, Q.p) : 0.f;
+      } else Q.m = Q.v;
     }
   }
   J num;
@@ -319,25 +405,31 @@ __device__ __forceinline__ J bprior_factor_regs(const Ctx<D, LAP>& cx, const flo
   return cx.scale(cx.mul(num, iq), sgn);
 }
 
+// 1 / sqrt(1 + d^2) with IEEE square root and division (utils/physics.py:66-71).  Deliberately NOT inlined: the correctly
+// rounded sequences are ~50 instructions each and the potential needs D (n_protons + (D - 1) / 2) of them, once per walker.
+static __device__ __noinline__ float inv_sqrt_1p_sq(float d) { return 1.f / sqrtf(1.f + d * d); }
+
 template <int D>
 __device__ __forceinline__ float soft_coulomb_tc(const float (&xs)[D], const float* protons, int n_protons) {
   float pe = 0.f;
   for (int p = 0; p < n_protons; ++p)
-#pragma unroll
-    for (int e = 0; e < D; ++e) { const float d = protons[p] - xs[e]; pe += 1.f / sqrtf(1.f + d * d); }
+#pragma unroll 1
+    for (int e = 0; e < D; ++e) pe += inv_sqrt_1p_sq(protons[p] - xs[e]);
   float ee = 0.f;
 #pragma unroll
   for (int i = 1; i < D; ++i)
 #pragma unroll
-    for (int j = 0; j < i; ++j) { const float d = xs[i] - xs[j]; ee += 1.f / sqrtf(1.f + d * d); }
+    for (int j = 0; j < i; ++j) ee += inv_sqrt_1p_sq(xs[i] - xs[j]);
   return ee - pe;
 }
 
-// Shared memory (1024-byte aligned): W2 hi | W2 lo | W3 hi | W3 lo | scratch [32][512] | reduction [4][16] doubles | barriers ...
+// Shared memory (1024-byte aligned): W2 hi | W2 lo | W3 hi | W3 lo | 2 x (W1, b1, b2, b3) | scratch [32][512] | reduction
+// [4][16] doubles | barriers ...
 struct Smem {
   static __host__ __device__ constexpr size_t w2_off() { return 0; }
   static __host__ __device__ constexpr size_t w3_off() { return 2 * (size_t)W2_PLANE_BYTES; }
-  static __host__ __device__ constexpr size_t scr_off(int D) { return w3_off() + 2 * (size_t)w3_plane_bytes(D); }
+  static __host__ __device__ constexpr size_t small_off(int D) { return w3_off() + 2 * (size_t)w3_plane_bytes(D); }
+  static __host__ __device__ constexpr size_t scr_off(int D) { return small_off(D) + 2 * (size_t)small_floats(D) * 4; }
   static __host__ __device__ constexpr size_t red_off(int D) { return scr_off(D) + (size_t)SCR * THREADS * 4; }
   static __host__ __device__ constexpr size_t bar_off(int D) { return red_off(D) + 4 * (THREADS / 32) * sizeof(double); }
   static __host__ __device__ constexpr size_t total(int D) { return bar_off(D) + 128 + 1024; }   // + alignment slack
@@ -355,7 +447,7 @@ __global__ void __launch_bounds__(THREADS, 1) live_tc_kernel(const __grid_consta
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   constexpr int N3 = D * WF_MAX_P;
   constexpr int NETF = net_floats_tc(D);
-  constexpr uint32_t W2_BYTES = 2 * W2_PLANE_BYTES, W3_BYTES = 2 * w3_plane_bytes(D);
+  constexpr uint32_t W2_BYTES = 2 * W2_PLANE_BYTES, W3_BYTES = 2 * w3_plane_bytes(D), SMALL_BYTES = small_floats(D) * 4;
   const wf_live_model& M = P.m;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int tile = tid / TILE_THREADS;                 // 0 / 1
@@ -365,18 +457,21 @@ __global__ void __launch_bounds__(THREADS, 1) live_tc_kernel(const __grid_consta
 
   unsigned char* w2_s = smem + Smem::w2_off();
   unsigned char* w3_s = smem + Smem::w3_off();
+  float* small_s = reinterpret_cast<float*>(smem + Smem::small_off(D));      // [2][small_floats]: W1 | b1 | b2 | b3 of net g & 1
   float* scratch = reinterpret_cast<float*>(smem + Smem::scr_off(D));
   double* red_s = reinterpret_cast<double*>(smem + Smem::red_off(D));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Smem::bar_off(D));
-  uint64_t* w2_full = bars;            // count 1 + tx
+  uint64_t* w2_full = bars;            // count 1 + tx: W2 planes + the small arrays of a net
   uint64_t* w3_full = bars + 1;
-  uint64_t* d_ready = bars + 2;        // [TILES], arrived by tcgen05.commit
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 4);
+  uint64_t* l2_done = bars + 2;        // [TILES][2]: 32-column halves of layer 2, arrived by tcgen05.commit
+  uint64_t* l3_done = bars + 6;        // [TILES][4]: per-dimension 32-column groups of layer 3
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 14);
   int* w_cnt = reinterpret_cast<int*>(tmem_ptr + 1);   // [2]: tiles done with W2 / W3 of the current net
 
   if (tid == 0) {
     mbar_init(w2_full, 1); mbar_init(w3_full, 1);
-    mbar_init(&d_ready[0], 1); mbar_init(&d_ready[1], 1);
+    for (int i = 0; i < 4; ++i) mbar_init(&l2_done[i], 1);
+    for (int i = 0; i < 8; ++i) mbar_init(&l3_done[i], 1);
     w_cnt[0] = 0; w_cnt[1] = 0;
     mbar_fence_init();
   }
@@ -407,8 +502,10 @@ __global__ void __launch_bounds__(THREADS, 1) live_tc_kernel(const __grid_consta
   double accE = 0.0, accE2 = 0.0, accN = 0.0, accP2 = 0.0;
 
   auto issue_w2 = [&](int64_t g) {
-    mbar_expect_tx(w2_full, W2_BYTES);
-    bulk_g2s(w2_s, P.weights + (size_t)(g % n_nets) * NETF, W2_BYTES, w2_full);
+    const float* src = P.weights + (size_t)(g % n_nets) * NETF;
+    mbar_expect_tx(w2_full, W2_BYTES + SMALL_BYTES);
+    bulk_g2s(w2_s, src, W2_BYTES, w2_full);
+    bulk_g2s(small_s + (size_t)(g & 1) * small_floats(D), src + (W2_BYTES + W3_BYTES) / 4, SMALL_BYTES, w2_full);
   };
   auto issue_w3 = [&](int64_t g) {
     mbar_expect_tx(w3_full, W3_BYTES);
@@ -418,7 +515,8 @@ __global__ void __launch_bounds__(THREADS, 1) live_tc_kernel(const __grid_consta
 
   int64_t g = 0;
   for (int64_t round = 0; round < rounds; ++round) {
-    const int64_t tile_idx = round * slots + (int64_t)blockIdx.x * TILES + tile;
+    // consecutive tiles go to DIFFERENT CTAs, so that the ragged last round leaves one tile per SM rather than idle SMs
+    const int64_t tile_idx = round * slots + (int64_t)tile * gridDim.x + blockIdx.x;
     const int64_t w_raw = tile_idx * WPT + (int64_t)quarter * C::WPW + cx.slot;
     const bool lane_live = (!LAP || lane < C::WPW * C::G) && w_raw < P.N;
     const int64_t w = w_raw < P.N ? w_raw : P.N - 1;
@@ -430,7 +528,6 @@ __global__ void __launch_bounds__(THREADS, 1) live_tc_kernel(const __grid_consta
     J ld = cx.constant(0.f);
     box_transform<D, LAP>(cx, M, xs, us, ld);
     float ldf = wg == 0 ? cx.fold(ld) : 0.f;           // this warpgroup's share of log|det J| as a 1-register bundle
-    if (!LAP && wg != 0) ldf = 0.f;
 
     float uout[D];
 #pragma unroll
@@ -445,36 +542,41 @@ __global__ void __launch_bounds__(THREADS, 1) live_tc_kernel(const __grid_consta
 #pragma unroll 1
     for (int net_idx = 0; net_idx < n_nets; ++net_idx, ++g) {
       const bool is_prior = has_prior_net && net_idx == n_nets - 1;
-      const float* netw = P.weights + (size_t)net_idx * NETF;
-      const float* W1 = netw + (W2_BYTES + W3_BYTES) / 4;
+      // W1 | b1 | b2 | b3 of this net were dropped into shared memory together with its W2 planes
+      mbar_wait_guard(w2_full, (uint32_t)(g & 1));
+      const float* W1 = small_s + (size_t)(g & 1) * small_floats(D);
       const float* b1 = W1 + D * WF_HIDDEN;
       const float* b2 = b1 + WF_HIDDEN;
       const float* b3 = b2 + WF_HIDDEN;
+      const uint32_t par = (uint32_t)(g & 1);
 
       // ------------------------------------------------ layer 1 (K = D, CUDA cores) -> A planes
 #pragma unroll 1
-      for (int c = 0; c < 2; ++c) {
-        float h[16];
+      for (int c = 0; c < 4; ++c) {
+        float h[8];
 #pragma unroll
-        for (int t = 0; t < 16; ++t) {
-          const int j = fbase + c * 16 + t;
-          float acc = cx.is_v ? __ldg(b1 + j) : 0.f;
+        for (int t = 0; t < 8; ++t) {
+          const int j = fbase + c * 8 + t;
+          float acc = cx.is_v ? b1[j] : 0.f;
 #pragma unroll
-          for (int d = 0; d < D; ++d) acc = fmaf(us[d], __ldg(W1 + d * WF_HIDDEN + j), acc);
+          for (int d = 0; d < D; ++d) acc = fmaf(us[d], W1[d * WF_HIDDEN + j], acc);
           h[t] = tanh_bundle<D, LAP>(cx, acc);
         }
-        store_planes16(my_hi, my_lo, (uint32_t)(fbase + c * 16), h);
+        store_planes8(my_hi, my_lo, (uint32_t)(fbase + c * 8), h);
       }
       tmem_wait_st();
       fence_before();
       bar_sync(1 + tile, TILE_THREADS);
-      if (leader) {
+      // every 32-column group is issued by ONE lane of a different warp (warp 0 / 1 of the warpgroup that consumes it): the issue
+      // work (24 MMAs per group) is spread instead of serialised in front of one warp's epilogue
+      if ((warp & 3) == 0 && lane == 0) {
         fence_after();
-        mbar_wait_guard(w2_full, (uint32_t)(g & 1));
-        issue_layer<WF_HIDDEN>(dacc, a_hi, a_lo, w2_s, w2_s + W2_PLANE_BYTES);
-        umma_commit(&d_ready[tile]);
+        issue_group32<WF_HIDDEN>(dacc + (uint32_t)fbase, a_hi, a_lo, w2_s, w2_s + W2_PLANE_BYTES, fbase);
+        umma_commit(&l2_done[tile * 2 + wg]);
       }
-      mbar_wait_guard(&d_ready[tile], 0u);
+      // the A planes are overwritten below: BOTH halves of layer 2 must have been read by the tensor core
+      mbar_wait_guard(&l2_done[tile * 2 + wg], par);
+      mbar_wait_guard(&l2_done[tile * 2 + (wg ^ 1)], par);
       fence_after();
       if (leader) {                                     // the second tile to get here refills W2 with the next net
         const int old = atomicAdd(&w_cnt[0], 1);
@@ -483,30 +585,28 @@ __global__ void __launch_bounds__(THREADS, 1) live_tc_kernel(const __grid_consta
 
       // ------------------------------------------------ layer 2 epilogue: bias + tanh -> A planes
 #pragma unroll 1
-      for (int c = 0; c < 2; ++c) {
-        float v[16], h[16];
-        tmem_ld16(my_acc + (uint32_t)(fbase + c * 16), v);
+      for (int c = 0; c < 4; ++c) {
+        float v[8], h[8];
+        tmem_ld8(my_acc + (uint32_t)(fbase + c * 8), v);
 #pragma unroll
-        for (int t = 0; t < 16; ++t) {
-          const float acc = cx.is_v ? v[t] + __ldg(b2 + fbase + c * 16 + t) : v[t];
+        for (int t = 0; t < 8; ++t) {
+          const float acc = cx.is_v ? v[t] + b2[fbase + c * 8 + t] : v[t];
           h[t] = tanh_bundle<D, LAP>(cx, acc);
         }
-        store_planes16(my_hi, my_lo, (uint32_t)(fbase + c * 16), h);
+        store_planes8(my_hi, my_lo, (uint32_t)(fbase + c * 8), h);
       }
       tmem_wait_st();
       fence_before();
       bar_sync(1 + tile, TILE_THREADS);
-      if (leader) {
-        fence_after();
-        mbar_wait_guard(w3_full, (uint32_t)(g & 1));
-        issue_layer<N3>(dacc, a_hi, a_lo, w3_s, w3_s + w3_plane_bytes(D));
-        umma_commit(&d_ready[tile]);
-      }
-      mbar_wait_guard(&d_ready[tile], 1u);
-      fence_after();
-      if (leader) {
-        const int old = atomicAdd(&w_cnt[1], 1);
-        if (old == 2 * g + 1 && g + 1 < g_total) issue_w3(g + 1);
+      {
+        // layer 3: one 32-column group per output dimension, issued by warp (d - d_lo) of the warpgroup that owns dimension d
+        const int d_mine = d_lo + (warp & 3);
+        if (lane == 0 && d_mine < d_hi) {
+          fence_after();
+          mbar_wait_guard(w3_full, par);
+          issue_group32<N3>(dacc + (uint32_t)(d_mine * WF_MAX_P), a_hi, a_lo, w3_s, w3_s + w3_plane_bytes(D), d_mine * WF_MAX_P);
+          umma_commit(&l3_done[tile * 4 + d_mine]);
+        }
       }
 
       // ------------------------------------------------ layer 3 epilogue: spline glue of this warpgroup's dimensions
@@ -515,19 +615,18 @@ __global__ void __launch_bounds__(THREADS, 1) live_tc_kernel(const __grid_consta
       for (int d = 0; d < D; ++d) ys[d] = 0.f;
 #pragma unroll 1
       for (int d = d_lo; d < d_hi; ++d) {
-        float o[WF_MAX_P];
-        tmem_ld32(my_acc + (uint32_t)(d * WF_MAX_P), o);
-        if (cx.is_v) {
-#pragma unroll
-          for (int q = 0; q < WF_MAX_P; ++q) o[q] += __ldg(b3 + d * WF_MAX_P + q);
-        }
+        mbar_wait_guard(&l3_done[tile * 4 + d], par);
+        fence_after();
+        const uint32_t tacc = my_acc + (uint32_t)(d * WF_MAX_P);      // this row's 32 conditioner outputs of dimension d
+        const float* b3d = b3 + d * WF_MAX_P;
         float xd = us[0];
 #pragma unroll
         for (int dd = 1; dd < D; ++dd) xd = (d == dd) ? us[dd] : xd;
         const float xv = cx.bv(xd);
         if (!is_prior) {
           J y, dy;
-          sigmoid_spline_regs<D, LAP, 2, true>(cx, o, S, M.P_I, P.wq_I, M.reg, P.rec_I, P.lo_I, P.tab_I, M.T, xd, xv, y, dy);
+          sigmoid_spline_regs<D, LAP, 2, true>(cx, tacc, b3d, S, M.P_I, P.wq_I, P.wsum_I, M.reg, reinterpret_cast<const float4*>(P.rec_I_t),
+                                               P.lo_I, P.tab_I, M.T, xd, xv, y, dy);
           const float yf = cx.fold(y);
 #pragma unroll
           for (int dd = 0; dd < D; ++dd) ys[dd] = (d == dd) ? yf : ys[dd];
@@ -536,7 +635,7 @@ __global__ void __launch_bounds__(THREADS, 1) live_tc_kernel(const __grid_consta
         } else {
           const bool cons = M.coord_mean ? (d < D - 1) : (d >= 1);
           if (M.prior_kind == WF_KIND_B) {
-            J phi = bprior_factor_regs<D, LAP>(cx, o, M.P_P, P.tab_P, M.T, xd, xv);
+            J phi = bprior_factor_regs<D, LAP>(cx, tacc, b3d, M.P_P, P.tab_P, M.T, xd, xv);
             if (!LAP) {
               float pr = phi.v * phi.v;
               if (cons) pr = pr / 2.f;
@@ -548,10 +647,17 @@ __global__ void __launch_bounds__(THREADS, 1) live_tc_kernel(const __grid_consta
             const float xc = fminf(fmaxf(xv, 0.f), 1.f);
             const float xdc = (xv > 0.f && xv < 1.f) ? xd : 0.f;
             J y, dy;
-            sigmoid_spline_regs<D, LAP, 1, false>(cx, o, S, M.P_P, P.wq_P, 0.f, P.rec_P, P.lo_P, P.tab_P, M.T, xdc, xc, y, dy);
+            sigmoid_spline_regs<D, LAP, 1, false>(cx, tacc, b3d, S, M.P_P, P.wq_P, P.wsum_P, 0.f, reinterpret_cast<const float4*>(P.rec_P_t),
+                                                  P.lo_P, P.tab_P, M.T, xdc, xc, y, dy);
             lp += logf(y.v + LOG_TOL);
           }
         }
+      }
+      if (leader) {                                     // W3 is free once ALL groups of both tiles are done: refill it
+#pragma unroll
+        for (int d = D / 2; d < D; ++d) mbar_wait_guard(&l3_done[tile * 4 + d], par);
+        const int old = atomicAdd(&w_cnt[1], 1);
+        if (old == 2 * g + 1 && g + 1 < g_total) issue_w3(g + 1);
       }
       // ------------------------------------------------ exchange the per-dimension results between the two warpgroups
       if (!is_prior) {

@@ -60,6 +60,8 @@ class SplineTables:
             d["dense"] = torch.from_numpy(dense).to(device)
             d["rec"] = None if rec is None else torch.from_numpy(rec).to(device)
             d["lo"] = None if lo is None else torch.from_numpy(lo).to(device)
+            # [T][8 window slots][4 derivative orders]: one 128-bit load per window slot in the tensor-core live kernels
+            d["rec_t"] = None if rec is None else torch.from_numpy(np.ascontiguousarray(np.transpose(rec, (0, 2, 1)))).to(device)
             d["dense32"] = torch.from_numpy(self._pad32(self.tab32)).to(device)
             if self.kind == "B":
                 ob32 = self.ob64.astype(np.float32)

@@ -52,10 +52,13 @@ def construct_hamiltonian_function(fn, protons=np.array([[0, 0]]), n_space_dimen
         raise NotImplementedError("finite-difference Laplacian (physics.py:28-46) is not part of the hot path")
     prot = np.asarray(protons, dtype=np.float32).reshape(-1)
 
-    def _construct(weight_dict, x, return_all=False, sums=None, packed=None):
+    def _construct(weight_dict, x, return_all=False, sums=None, packed=None, exchange=None, want=("psi", "hpsi", "eloc")):
+        """h_fn(params, x) -> H psi [N, 1] (physics.py:84-93).  Extras of this build: return_all -> dict(psi, hpsi, eloc);
+        sums: float64 [4] accumulator of {sum E, sum E^2, n, sum psi^2}; exchange: a vqmc.PeerExchange (the sums are
+        all-reduced over the ranks by the same call); packed: pre-packed weights (default: the per-model cache)."""
         xx = f32(x)
         w = packed if packed is not None else _live.packed_for(spec, weight_dict[0], weight_dict[1], xx.device)
-        out = _live.local_energy(spec, w, xx, prot, want=("psi", "hpsi", "eloc"), sums=sums)
+        out = _live.local_energy(spec, w, xx, prot, want=want, sums=sums, exchange=exchange)
         if return_all:
             return out
         return out["hpsi"][:, None]
