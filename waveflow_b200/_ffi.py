@@ -109,8 +109,8 @@ class _DeviceGuardedLib:
 
         def call(*args):
             dev = _pending_device()
-            if dev is None:
-                return fn(*args)
+            if dev is None or dev.index is None or dev.index == torch.cuda.current_device():
+                return fn(*args)                      # the common case (one process per GPU): nothing to switch
             with torch.cuda.device(dev):
                 return fn(*args)
 
@@ -220,7 +220,7 @@ def bump_version(t: torch.Tensor):
 
 
 def params_key(tree) -> tuple:
-    """Identity of a parameter pytree: (storage address, version counter, size) per torch leaf -- in-place updates bump
+    """Identity of a parameter pytree: (storage address, version counter) per torch leaf -- in-place updates bump
     the version (optimisers through torch, wf_adam_step through `bump_version`), new tensors have new addresses that are
     kept alive by the cache entry holding them.  numpy leaves are keyed by object identity and buffer address: like the
     reference's immutable JAX arrays they are expected not to be mutated in place."""
@@ -231,7 +231,7 @@ def params_key(tree) -> tuple:
             for c in t:
                 walk(c)
         elif isinstance(t, torch.Tensor):
-            key.append((t.data_ptr(), t._version, t.numel(), t.device.index))
+            key.append((t.data_ptr(), t._version))
         elif isinstance(t, np.ndarray):
             key.append((id(t), t.__array_interface__["data"][0], t.size))
         else:
