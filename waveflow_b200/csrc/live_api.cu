@@ -1,4 +1,5 @@
 // C-ABI entry points of the fused live path (wf_live_forward, wf_local_energy).
+#include <stdlib.h>
 #include <string.h>
 #include "live_kernel.cuh"
 #include "live_inverse.cuh"
@@ -55,6 +56,7 @@ int fill_params(const wf_live_model* m, const wf_live_tables* t, const float* we
   if (pnet) coeff_weights(m->prior_kind, m->k_P, m->P_P, m->bc_P, m->prior_kind == WF_KIND_M, P.wq_P);
   P.rec_I_t = t->rec_I_t; P.rec_P_t = t->rec_P_t;
   for (int q = 0; q < m->P_I; ++q) P.wsum_I += P.wq_I[q];
+  for (int q = 0; q < WF_MAX_P; ++q) P.cwq_I[q + 1] = P.cwq_I[q] + P.wq_I[q];
   if (pnet) for (int q = 0; q < m->P_P; ++q) P.wsum_P += P.wq_P[q];
   if (m->weight_layout == WF_WEIGHTS_TC) {
     if (m->n_layers > 0 && !t->rec_I_t) return WF_ERR_INVALID_ARG;

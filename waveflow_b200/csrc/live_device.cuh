@@ -54,6 +54,7 @@ struct LiveParams {
   const float* rec_I_t;   // compact records transposed to [T][8][4] (tensor-core kernels: one 128-bit load per window slot)
   const float* rec_P_t;
   float wsum_I, wsum_P;   // sum_q wq_I[q], sum_q wq_P[q] (sequential float32 sums)
+  float cwq_I[WF_MAX_P + 1];   // cwq_I[j] = sum_{q < j} wq_I[q] (sequential float32 prefix sums)
   float wq_I[WF_MAX_P];   // remove_bias scale x boundary mask of the I-spline coefficients (0 beyond P_I)
   float wq_P[WF_MAX_P];   // same for the prior coefficients (M: remove_bias x mask, B: mask)
   float protons[WF_MAX_D];

@@ -116,6 +116,13 @@ __device__ __forceinline__ void tmem_wait_ld8(uint32_t (&r)[8]) {
                : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7])
                :: "memory");
 }
+__device__ __forceinline__ void tmem_ld4_issue(uint32_t taddr, uint32_t (&r)[4]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_wait_ld4(uint32_t (&r)[4]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]) :: "memory");
+}
 __device__ __forceinline__ void tmem_ld4(uint32_t taddr, float (&v)[4]) {
   uint32_t r[4];
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];\n"
@@ -236,7 +243,8 @@ struct MP { float m, p; };
 
 template <int D, bool LAP, int NOUT, bool PREFIX_ONE>
 __device__ __forceinline__ void sigmoid_spline_regs(const Ctx<D, LAP>& cx, uint32_t tacc, const float* __restrict__ bias,
-                                                    const ScratchT& S, int P, const float* __restrict__ wq, float wsum, float reg,
+                                                    const ScratchT& S, int P, const float* __restrict__ wq,
+                                                    const float* __restrict__ cwq, float wsum, float reg,
                                                     const float4* __restrict__ rec_t, const int32_t* __restrict__ lo,
                                                     const float* __restrict__ dense, int T, float xd, float xv, J& y, J& dy) {
   constexpr int NK = LAP ? NOUT + 2 : NOUT;
@@ -252,8 +260,10 @@ __device__ __forceinline__ void sigmoid_spline_regs(const Ctx<D, LAP>& cx, uint3
   };
   auto full = [&](const MP& a) { return J{a.m, LAP ? a.p : 0.f, cx.bv(a.m)}; };
 
+  // the prefix sum over the bases below the window (identically 1 there) is the running weighted sum SW at q == lo_w, and its
+  // weight the host-computed prefix sum cwq[lo_w] of wq: a snapshot instead of a second predicated accumulation per coefficient
   MP Ssum = {0.f, 0.f}, SW = {0.f, 0.f}, PRE = {0.f, 0.f};
-  float Wpre = 0.f;
+  const float Wpre = PREFIX_ONE ? cwq[lo_w] : 0.f;
   // conditioner outputs of this dimension: 8 accumulator columns at a time straight from tensor memory (+ bias on the value
   // lane); the chunk loop stays rolled to keep the kernel inside the instruction cache
   uint32_t nxt[8];
@@ -275,18 +285,19 @@ __device__ __forceinline__ void sigmoid_spline_regs(const Ctx<D, LAP>& cx, uint3
         const float d1 = s * (1.f - s);
         const J sq = cx.unary(J{oq, 0.f, ov}, s, d1, d1 * (1.f - 2.f * s));
         const float w = wq[q];
+        if (PREFIX_ONE) {
+          if (q == lo_w) PRE = SW;                     // SW holds the bases 0 .. q - 1 here
+        }
         Ssum.m += sq.m;
         if constexpr (LAP) Ssum.p += sq.p;
         axpy(w, sq, SW);
-        if (PREFIX_ONE) {
-          const float wp = (q < lo_w) ? w : 0.f;
-          axpy(wp, sq, PRE);
-          Wpre += wp;
-        }
         S[q] = sq.m;
       }
     }
     tmem_wait_ld8(nxt);
+  }
+  if (PREFIX_ONE) {
+    if (lo_w >= P) PRE = SW;                           // (window entirely beyond the last basis: every basis is in the prefix)
   }
   auto reload = [&](int qc) {
     J sq;
@@ -304,7 +315,7 @@ __device__ __forceinline__ void sigmoid_spline_regs(const Ctx<D, LAP>& cx, uint3
   for (int k = 0; k < NK; ++k) { Sk[k] = MP{0.f, 0.f}; Wk[k] = 0.f; }
   if (PREFIX_ONE) { Sk[0] = PRE; Wk[0] = Wpre; }
   if (local) {
-#pragma unroll 2
+#pragma unroll 4
     for (int t = 0; t < WF_WIN; ++t) {
       const int q = lo_l + t;
       const int qc = q < P ? q : P - 1;
@@ -372,10 +383,15 @@ __device__ __forceinline__ J bprior_factor_regs(const Ctx<D, LAP>& cx, uint32_t 
 #pragma unroll
   for (int k = 0; k < NK; ++k) A[k] = J{0.f, 0.f, 0.f};
   J Q = {0.f, 0.f, 0.f};
+  uint32_t nxt[4];
+  tmem_ld4_issue(tacc, nxt);
+  tmem_wait_ld4(nxt);
 #pragma unroll 1
   for (int j0 = 0; j0 < P; j0 += 4) {
     float o4[4];
-    tmem_ld4(tacc + (uint32_t)j0, o4);
+#pragma unroll
+    for (int t = 0; t < 4; ++t) o4[t] = __uint_as_float(nxt[t]);
+    if (j0 + 4 < P) tmem_ld4_issue(tacc + (uint32_t)(j0 + 4), nxt);
     float f[NK][4];
 #pragma unroll
     for (int k = 0; k < NK; ++k) {
@@ -397,6 +413,7 @@ __device__ __forceinline__ J bprior_factor_regs(const Ctx<D, LAP>& cx, uint32_t 
         Q.p = cx.is_g ? fmaf(2.f * c, c, Q.p) : 0.f;
       } else Q.m = Q.v;
     }
+    tmem_wait_ld4(nxt);
   }
   J num;
   if constexpr (LAP) num = spline_assemble<D, LAP>(cx, A[0], A[1], A[2], xd); else num = A[0];
@@ -450,10 +467,7 @@ __global__ void __launch_bounds__(THREADS, 1) live_tc_kernel(const __grid_consta
   constexpr uint32_t W2_BYTES = 2 * W2_PLANE_BYTES, W3_BYTES = 2 * w3_plane_bytes(D), SMALL_BYTES = small_floats(D) * 4;
   const wf_live_model& M = P.m;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int tile = tid / TILE_THREADS;                 // 0 / 1
-  const int wg = (tid / 128) & 1;                      // warpgroup inside the tile
   const int quarter = warp & 3;                        // TMEM lane quarter of this warp
-  const bool leader = (tid % TILE_THREADS) == 0;       // issues this tile's MMAs
 
   unsigned char* w2_s = smem + Smem::w2_off();
   unsigned char* w3_s = smem + Smem::w3_off();
@@ -466,7 +480,7 @@ __global__ void __launch_bounds__(THREADS, 1) live_tc_kernel(const __grid_consta
   uint64_t* l2_done = bars + 2;        // [TILES][2]: 32-column halves of layer 2, arrived by tcgen05.commit
   uint64_t* l3_done = bars + 6;        // [TILES][4]: per-dimension 32-column groups of layer 3
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 14);
-  int* w_cnt = reinterpret_cast<int*>(tmem_ptr + 1);   // [2]: tiles done with W2 / W3 of the current net
+  int* w_cnt = reinterpret_cast<int*>(tmem_ptr + 1);   // [2]: teams done with W2 / W3 (cumulative over the nets)
 
   if (tid == 0) {
     mbar_init(w2_full, 1); mbar_init(w3_full, 1);
@@ -481,25 +495,22 @@ __global__ void __launch_bounds__(THREADS, 1) live_tc_kernel(const __grid_consta
   fence_after();
   const uint32_t tmem_base = *tmem_ptr;
   const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
-  const uint32_t cbase = tmem_base + (uint32_t)(tile * 256);
-  const uint32_t a_hi = cbase, a_lo = cbase + 64, dacc = cbase + 128;   // MMA operands (lane field 0)
-  const uint32_t my_hi = a_hi + lane_addr, my_lo = a_lo + lane_addr, my_acc = dacc + lane_addr;
 
   C cx;
   cx.init(lane);
   const ScratchT S{scratch + tid};
-  const ScratchT Sp{scratch + (tid ^ 128)};            // the partner thread (same row, other warpgroup)
   constexpr int WPT = 4 * C::WPW;                      // walkers per tile
   const int64_t n_tiles = (P.N + WPT - 1) / WPT;
   const int64_t slots = (int64_t)gridDim.x * TILES;
-  const int64_t rounds = (n_tiles + slots - 1) / slots;
+  // tile of (round, slot s) = round * slots + s * gridDim.x + blockIdx.x: consecutive tiles go to DIFFERENT CTAs, so the ragged
+  // last round leaves ONE tile per CTA (which then gets all 16 warps, see below) rather than idle SMs
+  const int64_t my_rounds = (int64_t)blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + slots - 1) / slots : 0;
   const int n_nets = P.n_nets;
   const bool has_prior_net = M.prior_kind == WF_KIND_B || M.prior_kind == WF_KIND_M;
-  const int64_t g_total = rounds * n_nets;
-  // dimensions of the spline glue handled by this warpgroup
-  const int d_lo = wg == 0 ? 0 : D / 2, d_hi = wg == 0 ? D / 2 : D;
-  const int fbase = wg * 32;                           // hidden features of the tanh layers handled by this warpgroup
+  const int64_t g_total = my_rounds * n_nets;
   double accE = 0.0, accE2 = 0.0, accN = 0.0, accP2 = 0.0;
+  // phase parities of the per-tile MMA barriers (a slot that sits out a SOLO round does not advance)
+  uint32_t par_s0 = 0, par_s1 = 0;
 
   auto issue_w2 = [&](int64_t g) {
     const float* src = P.weights + (size_t)(g % n_nets) * NETF;
@@ -514,45 +525,75 @@ __global__ void __launch_bounds__(THREADS, 1) live_tc_kernel(const __grid_consta
   if (tid == 0 && g_total > 0) { issue_w2(0); issue_w3(0); }
 
   int64_t g = 0;
-  for (int64_t round = 0; round < rounds; ++round) {
-    // consecutive tiles go to DIFFERENT CTAs, so that the ragged last round leaves one tile per SM rather than idle SMs
-    const int64_t tile_idx = round * slots + (int64_t)tile * gridDim.x + blockIdx.x;
+  int cum_teams = 0;                                    // arrivals expected on w_cnt[*] through the current net
+  for (int64_t round = 0; round < my_rounds; ++round) {
+    const int64_t t0 = round * slots + blockIdx.x, t1 = t0 + gridDim.x;
+    // SOLO round: only slot 0 has a tile -> all four warpgroups work on it (the hidden features and the output dimensions
+    // are split four ways instead of two): a lone tile is latency bound, this nearly halves its latency.  DUO: two teams of
+    // two warpgroups, one tile each.
+    const bool solo = t1 >= n_tiles;
+    // the warps of the other team join slot 0's tile: they must not touch its tensor memory before slot 0's own team has
+    // finished the previous (DUO) round there -- and slot 1's team must be done with its tile as well
+    if (solo && round > 0) __syncthreads();
+    const int n_wg = solo ? 4 : 2;
+    const int slot = solo ? 0 : tid / TILE_THREADS;
+    const int wg = solo ? warp >> 2 : (warp >> 2) & 1;   // warpgroup inside the team
+    const int team_tid0 = solo ? 0 : slot * TILE_THREADS;
+    const int team_threads = solo ? THREADS : TILE_THREADS;
+    const bool leader = tid == team_tid0;
+    const int teams = solo ? 1 : 2;
+    const uint32_t par = slot == 0 ? par_s0 : par_s1;
+    const uint32_t cbase = tmem_base + (uint32_t)(slot * 256);
+    const uint32_t a_hi = cbase, a_lo = cbase + 64, dacc = cbase + 128;   // MMA operands (lane field 0)
+    const uint32_t my_hi = a_hi + lane_addr, my_lo = a_lo + lane_addr, my_acc = dacc + lane_addr;
+    const int fw = WF_HIDDEN / n_wg;                     // hidden features of the tanh layers per warpgroup
+    const int fbase = wg * fw;
+    // output dimensions of the spline glue handled by this warpgroup
+    const int d_lo = solo ? (wg < D ? wg : D) : (wg == 0 ? 0 : D / 2);
+    const int d_hi = solo ? (wg < D ? wg + 1 : D) : (wg == 0 ? D / 2 : D);
+    auto owner_col = [&](int owner_wg) { return scratch + team_tid0 + owner_wg * 128 + (tid & 127); };
+    auto owner_of = [&](int d) { return solo ? d : (d >= D / 2 ? 1 : 0); };
+
+    const int64_t tile_idx = slot == 0 ? t0 : t1;
     const int64_t w_raw = tile_idx * WPT + (int64_t)quarter * C::WPW + cx.slot;
     const bool lane_live = (!LAP || lane < C::WPW * C::G) && w_raw < P.N;
     const int64_t w = w_raw < P.N ? w_raw : P.N - 1;
 
-    float xs[D];
-#pragma unroll
-    for (int d = 0; d < D; ++d) xs[d] = __ldg(P.x + w * D + d);
     float us[D];
-    J ld = cx.constant(0.f);
-    box_transform<D, LAP>(cx, M, xs, us, ld);
-    float ldf = wg == 0 ? cx.fold(ld) : 0.f;           // this warpgroup's share of log|det J| as a 1-register bundle
-
-    float uout[D];
+    // per-DIMENSION partial results (log-det contributions summed over the nets, prior factor, log prior): the final
+    // combination below always runs over the dimensions in index order, so every walker's result is bit-identical whichever
+    // team layout (SOLO / DUO) -- i.e. whichever batch size or sharding -- evaluated it
+    float ldbox, ldv[D], phiv[D], lpv[D];
 #pragma unroll
-    for (int d = 0; d < D; ++d) uout[d] = 0.f;
-    if (M.n_layers == 0) {
+    for (int d = 0; d < D; ++d) { ldv[d] = 0.f; phiv[d] = cx.is_v ? 1.f : 0.f; lpv[d] = 0.f; }
+    {
+      float xs[D];
 #pragma unroll
-      for (int d = 0; d < D; ++d) uout[d] = cx.bv(us[d]);
+      for (int d = 0; d < D; ++d) xs[d] = __ldg(P.x + w * D + d);
+      J ld = cx.constant(0.f);
+      box_transform<D, LAP>(cx, M, xs, us, ld);
+      ldbox = cx.fold(ld);                                // 1-register bundle (every warpgroup holds it; warpgroup 0 exports it)
     }
-    J psi = cx.constant(1.f);                           // product of this warpgroup's prior factors
-    float lp = 0.f;
+    if (M.n_layers == 0 && wg == 0 && lane_live && cx.is_v && P.u) {
+#pragma unroll
+      for (int d = 0; d < D; ++d) P.u[w * D + d] = us[d];
+    }
 
 #pragma unroll 1
     for (int net_idx = 0; net_idx < n_nets; ++net_idx, ++g) {
       const bool is_prior = has_prior_net && net_idx == n_nets - 1;
+      cum_teams += teams;
       // W1 | b1 | b2 | b3 of this net were dropped into shared memory together with its W2 planes
       mbar_wait_guard(w2_full, (uint32_t)(g & 1));
       const float* W1 = small_s + (size_t)(g & 1) * small_floats(D);
       const float* b1 = W1 + D * WF_HIDDEN;
       const float* b2 = b1 + WF_HIDDEN;
       const float* b3 = b2 + WF_HIDDEN;
-      const uint32_t par = (uint32_t)(g & 1);
+      const uint32_t mpar = (par + (uint32_t)net_idx) & 1u;
 
       // ------------------------------------------------ layer 1 (K = D, CUDA cores) -> A planes
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < fw / 8; ++c) {
         float h[8];
 #pragma unroll
         for (int t = 0; t < 8; ++t) {
@@ -566,46 +607,55 @@ __global__ void __launch_bounds__(THREADS, 1) live_tc_kernel(const __grid_consta
       }
       tmem_wait_st();
       fence_before();
-      bar_sync(1 + tile, TILE_THREADS);
-      // every 32-column group is issued by ONE lane of a different warp (warp 0 / 1 of the warpgroup that consumes it): the issue
-      // work (24 MMAs per group) is spread instead of serialised in front of one warp's epilogue
-      if ((warp & 3) == 0 && lane == 0) {
+      bar_sync(1 + slot, team_threads);
+      // every 32-column group is issued by ONE lane of a different warp: the issue work (24 MMAs per group) is spread
+      // instead of serialised in front of one warp's epilogue.  Layer 2: two groups (output units 0..31 / 32..63).
+      if ((warp & 3) == 0 && lane == 0 && (solo ? (wg & 1) == 0 : true)) {
+        const int h = solo ? wg >> 1 : wg;
         fence_after();
-        issue_group32<WF_HIDDEN>(dacc + (uint32_t)fbase, a_hi, a_lo, w2_s, w2_s + W2_PLANE_BYTES, fbase);
-        umma_commit(&l2_done[tile * 2 + wg]);
+        issue_group32<WF_HIDDEN>(dacc + (uint32_t)(h * 32), a_hi, a_lo, w2_s, w2_s + W2_PLANE_BYTES, h * 32);
+        umma_commit(&l2_done[slot * 2 + h]);
       }
       // the A planes are overwritten below: BOTH halves of layer 2 must have been read by the tensor core
-      mbar_wait_guard(&l2_done[tile * 2 + wg], par);
-      mbar_wait_guard(&l2_done[tile * 2 + (wg ^ 1)], par);
+      mbar_wait_guard(&l2_done[slot * 2 + 0], mpar);
+      mbar_wait_guard(&l2_done[slot * 2 + 1], mpar);
       fence_after();
-      if (leader) {                                     // the second tile to get here refills W2 with the next net
+      if (leader) {                                     // the last team to get here refills W2 with the next net
         const int old = atomicAdd(&w_cnt[0], 1);
-        if (old == 2 * g + 1 && g + 1 < g_total) issue_w2(g + 1);
+        if (old + 1 == cum_teams && g + 1 < g_total) issue_w2(g + 1);
       }
 
       // ------------------------------------------------ layer 2 epilogue: bias + tanh -> A planes
+      {
+        uint32_t nxt[8];
+        tmem_ld8_issue(my_acc + (uint32_t)fbase, nxt);
+        tmem_wait_ld8(nxt);
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        float v[8], h[8];
-        tmem_ld8(my_acc + (uint32_t)(fbase + c * 8), v);
+        for (int c = 0; c < fw / 8; ++c) {
+          float v[8], h[8];
 #pragma unroll
-        for (int t = 0; t < 8; ++t) {
-          const float acc = cx.is_v ? v[t] + b2[fbase + c * 8 + t] : v[t];
-          h[t] = tanh_bundle<D, LAP>(cx, acc);
+          for (int t = 0; t < 8; ++t) v[t] = __uint_as_float(nxt[t]);
+          if (c + 1 < fw / 8) tmem_ld8_issue(my_acc + (uint32_t)(fbase + (c + 1) * 8), nxt);    // in flight under this chunk's tanh
+#pragma unroll
+          for (int t = 0; t < 8; ++t) {
+            const float acc = cx.is_v ? v[t] + b2[fbase + c * 8 + t] : v[t];
+            h[t] = tanh_bundle<D, LAP>(cx, acc);
+          }
+          tmem_wait_ld8(nxt);
+          store_planes8(my_hi, my_lo, (uint32_t)(fbase + c * 8), h);
         }
-        store_planes8(my_hi, my_lo, (uint32_t)(fbase + c * 8), h);
       }
       tmem_wait_st();
       fence_before();
-      bar_sync(1 + tile, TILE_THREADS);
+      bar_sync(1 + slot, team_threads);
       {
         // layer 3: one 32-column group per output dimension, issued by warp (d - d_lo) of the warpgroup that owns dimension d
         const int d_mine = d_lo + (warp & 3);
         if (lane == 0 && d_mine < d_hi) {
           fence_after();
-          mbar_wait_guard(w3_full, par);
+          mbar_wait_guard(w3_full, (uint32_t)(g & 1));
           issue_group32<N3>(dacc + (uint32_t)(d_mine * WF_MAX_P), a_hi, a_lo, w3_s, w3_s + w3_plane_bytes(D), d_mine * WF_MAX_P);
-          umma_commit(&l3_done[tile * 4 + d_mine]);
+          umma_commit(&l3_done[slot * 4 + d_mine]);
         }
       }
 
@@ -615,7 +665,7 @@ __global__ void __launch_bounds__(THREADS, 1) live_tc_kernel(const __grid_consta
       for (int d = 0; d < D; ++d) ys[d] = 0.f;
 #pragma unroll 1
       for (int d = d_lo; d < d_hi; ++d) {
-        mbar_wait_guard(&l3_done[tile * 4 + d], par);
+        mbar_wait_guard(&l3_done[slot * 4 + d], mpar);
         fence_after();
         const uint32_t tacc = my_acc + (uint32_t)(d * WF_MAX_P);      // this row's 32 conditioner outputs of dimension d
         const float* b3d = b3 + d * WF_MAX_P;
@@ -625,83 +675,97 @@ __global__ void __launch_bounds__(THREADS, 1) live_tc_kernel(const __grid_consta
         const float xv = cx.bv(xd);
         if (!is_prior) {
           J y, dy;
-          sigmoid_spline_regs<D, LAP, 2, true>(cx, tacc, b3d, S, M.P_I, P.wq_I, P.wsum_I, M.reg, reinterpret_cast<const float4*>(P.rec_I_t),
+          sigmoid_spline_regs<D, LAP, 2, true>(cx, tacc, b3d, S, M.P_I, P.wq_I, P.cwq_I, P.wsum_I, M.reg, reinterpret_cast<const float4*>(P.rec_I_t),
                                                P.lo_I, P.tab_I, M.T, xd, xv, y, dy);
           const float yf = cx.fold(y);
 #pragma unroll
           for (int dd = 0; dd < D; ++dd) ys[dd] = (d == dd) ? yf : ys[dd];
           const J l = cx.log(cx.addc(dy, LOG_TOL));
-          ldf += LAP ? cx.fold(l) : l.v;
+          const float lf = LAP ? cx.fold(l) : l.v;
+#pragma unroll
+          for (int dd = 0; dd < D; ++dd) ldv[dd] = (d == dd) ? ldv[dd] + lf : ldv[dd];
         } else {
           const bool cons = M.coord_mean ? (d < D - 1) : (d >= 1);
           if (M.prior_kind == WF_KIND_B) {
             J phi = bprior_factor_regs<D, LAP>(cx, tacc, b3d, M.P_P, P.tab_P, M.T, xd, xv);
+            float lpd = 0.f;
             if (!LAP) {
               float pr = phi.v * phi.v;
               if (cons) pr = pr / 2.f;
-              lp += logf(pr + LOG_TOL);
+              lpd = logf(pr + LOG_TOL);
             }
             if (cons) phi = cx.scale(phi, 0.70710678118654752f);
-            psi = cx.mul(psi, phi);
+            const float pf = cx.fold(phi);
+#pragma unroll
+            for (int dd = 0; dd < D; ++dd) { phiv[dd] = (d == dd) ? pf : phiv[dd]; lpv[dd] = (d == dd) ? lpd : lpv[dd]; }
           } else {
             const float xc = fminf(fmaxf(xv, 0.f), 1.f);
             const float xdc = (xv > 0.f && xv < 1.f) ? xd : 0.f;
             J y, dy;
-            sigmoid_spline_regs<D, LAP, 1, false>(cx, tacc, b3d, S, M.P_P, P.wq_P, P.wsum_P, 0.f, reinterpret_cast<const float4*>(P.rec_P_t),
+            sigmoid_spline_regs<D, LAP, 1, false>(cx, tacc, b3d, S, M.P_P, P.wq_P, P.cwq_I, P.wsum_P, 0.f, reinterpret_cast<const float4*>(P.rec_P_t),
                                                   P.lo_P, P.tab_P, M.T, xdc, xc, y, dy);
-            lp += logf(y.v + LOG_TOL);
+            const float lpd = logf(y.v + LOG_TOL);
+#pragma unroll
+            for (int dd = 0; dd < D; ++dd) lpv[dd] = (d == dd) ? lpd : lpv[dd];
           }
         }
       }
-      if (leader) {                                     // W3 is free once ALL groups of both tiles are done: refill it
+      if (leader) {                                     // W3 is free once ALL groups of all teams are done: refill it
 #pragma unroll
-        for (int d = D / 2; d < D; ++d) mbar_wait_guard(&l3_done[tile * 4 + d], par);
+        for (int d = 0; d < D; ++d) mbar_wait_guard(&l3_done[slot * 4 + d], mpar);
         const int old = atomicAdd(&w_cnt[1], 1);
-        if (old == 2 * g + 1 && g + 1 < g_total) issue_w3(g + 1);
+        if (old + 1 == cum_teams && g + 1 < g_total) issue_w3(g + 1);
       }
-      // ------------------------------------------------ exchange the per-dimension results between the two warpgroups
+      // ------------------------------------------------ exchange the per-dimension results between the warpgroups of the team
       if (!is_prior) {
 #pragma unroll
         for (int d = 0; d < D; ++d)
           if (d >= d_lo && d < d_hi) S[d] = ys[d];
         fence_before();                                 // (the accumulator columns are free again after this barrier)
-        bar_sync(1 + tile, TILE_THREADS);
+        bar_sync(1 + slot, team_threads);
 #pragma unroll
-        for (int d = 0; d < D; ++d)
-          if (!(d >= d_lo && d < d_hi)) ys[d] = Sp[d];
+        for (int d = 0; d < D; ++d) ys[d] = owner_col(owner_of(d))[d * THREADS];
 #pragma unroll
         for (int d = 0; d < D; ++d) us[d] = ys[D - 1 - d];          // Reverse (bijections.py:336-345)
-        if (net_idx == M.n_layers - 1) {
+        if (net_idx == M.n_layers - 1 && wg == 0 && lane_live && cx.is_v && P.u) {      // (the value lane's bundle IS the value)
 #pragma unroll
-          for (int d = 0; d < D; ++d) uout[d] = cx.bv(us[d]);
+          for (int d = 0; d < D; ++d) P.u[w * D + d] = us[d];
         }
       }
     }
+    // every thread tracks the phase of BOTH slots' barriers (it may serve either slot in a later round)
+    par_s0 = (par_s0 + (uint32_t)n_nets) & 1u;
+    if (!solo) par_s1 = (par_s1 + (uint32_t)n_nets) & 1u;
 
-    // ------------------------------------------------ combine the two warpgroups: psi = prod phi * exp(0.5 log_det)
-    const float psif = cx.fold(psi);
-    bar_sync(1 + tile, TILE_THREADS);                   // partner finished reading the previous exchange
-    S[0] = psif; S[1] = ldf; S[2] = lp;
+    // ------------------------------------------------ combine the warpgroups: psi = prod_d phi_d * exp(0.5 log_det)
+    bar_sync(1 + slot, team_threads);                   // every warpgroup finished reading the previous exchange
+#pragma unroll
+    for (int d = 0; d < D; ++d)
+      if (d >= d_lo && d < d_hi) { S[d] = phiv[d]; S[D + d] = ldv[d]; S[2 * D + d] = lpv[d]; }
     fence_before();
-    bar_sync(1 + tile, TILE_THREADS);
-    const float psif_o = Sp[0], ldf_o = Sp[1], lp_o = Sp[2];
-    // identical operand order in both warpgroups (warpgroup 0's share first): bit-identical totals
-    const float pa = wg == 0 ? psif : psif_o, pb = wg == 0 ? psif_o : psif;
-    const float la = wg == 0 ? ldf : ldf_o, lb = wg == 0 ? ldf_o : ldf;
-    const float lp_tot = (wg == 0 ? lp : lp_o) + (wg == 0 ? lp_o : lp);
-    const float ld_tot = la + lb;
+    bar_sync(1 + slot, team_threads);
+    float ld_tot = ldbox, lp_tot = 0.f;
+    J psi_t = cx.constant(1.f);
+#pragma unroll
+    for (int d = 0; d < D; ++d) {                       // fixed order over the dimensions, identical in every warpgroup
+      const float* col = owner_col(owner_of(d));
+      const float pk = col[d * THREADS];
+      ld_tot += col[(D + d) * THREADS];
+      lp_tot += col[(2 * D + d) * THREADS];
+      const J ph = J{pk, 0.f, cx.bv(pk)};
+      if (d == 0) psi_t = ph;
+      else {
+        psi_t = cx.mul(psi_t, ph);
+        if constexpr (LAP) { const float f = cx.fold(psi_t); psi_t = J{f, 0.f, psi_t.v}; }
+      }
+    }
     const J LD = J{ld_tot, 0.f, cx.bv(ld_tot)};
-    J psi_t = cx.mul(J{pa, 0.f, cx.bv(pa)}, J{pb, 0.f, cx.bv(pb)});
     if (M.prior_kind == WF_KIND_B) psi_t = cx.mul(psi_t, cx.exp(cx.scale(LD, 0.5f)));
     const float psi1 = cx.fold(psi_t);
 
-    // ------------------------------------------------ outputs (warpgroup 0 writes)
+    // ------------------------------------------------ outputs (warpgroup 0 of the team writes)
     const bool writer = wg == 0 && lane_live;
     if (writer && cx.is_v) {
-      if (P.u) {
-#pragma unroll
-        for (int d = 0; d < D; ++d) P.u[w * D + d] = uout[d];
-      }
       if (P.logdet) P.logdet[w] = LD.v;
       if (P.logpdf) P.logpdf[w] = lp_tot + LD.v;
       if (P.psi) P.psi[w] = psi_t.v;
@@ -709,14 +773,19 @@ __global__ void __launch_bounds__(THREADS, 1) live_tc_kernel(const __grid_consta
     if constexpr (LAP) {
       const float lapv = __shfl_sync(FULL, psi1, cx.gbase + D + 1);
       if (writer && cx.is_g && P.grad) P.grad[w * D + (cx.comp - 1)] = psi1;
-      if (writer && cx.is_v) {
-        const float V = soft_coulomb_tc<D>(xs, P.protons, P.n_protons);
-        const float hp = fmaf(-0.5f, lapv, V * psi_t.v);         // physics.py:84
-        const float el = hp / (psi_t.v + 1e-8f);                // vqmc.py:200
-        if (P.lap) P.lap[w] = lapv;
-        if (P.hpsi) P.hpsi[w] = hp;
-        if (P.eloc) P.eloc[w] = el;
-        accE += (double)el; accE2 += (double)el * (double)el; accN += 1.0; accP2 += (double)psi_t.v * (double)psi_t.v;
+      if (wg == 0) {
+        float xs[D];
+#pragma unroll
+        for (int d = 0; d < D; ++d) xs[d] = __ldg(P.x + w * D + d);
+        if (writer && cx.is_v) {
+          const float V = soft_coulomb_tc<D>(xs, P.protons, P.n_protons);
+          const float hp = fmaf(-0.5f, lapv, V * psi_t.v);         // physics.py:84
+          const float el = hp / (psi_t.v + 1e-8f);                // vqmc.py:200
+          if (P.lap) P.lap[w] = lapv;
+          if (P.hpsi) P.hpsi[w] = hp;
+          if (P.eloc) P.eloc[w] = el;
+          accE += (double)el; accE2 += (double)el * (double)el; accN += 1.0; accP2 += (double)psi_t.v * (double)psi_t.v;
+        }
       }
     }
   }
@@ -774,8 +843,8 @@ int launch_live_tc(LiveParams& P, const TcExtra& X, cudaStream_t s) {
   const int wpw = LAP ? 32 / (D + 2) : 32;
   const int64_t wpt = 4 * wpw;
   const int64_t n_tiles = (P.N + wpt - 1) / wpt;
-  const int64_t want = (n_tiles + TILES - 1) / TILES;
-  const int blocks = (int)(want < num_sms() ? want : num_sms());
+  // up to one tile per SM: every CTA runs its tile with all four warpgroups (SOLO); beyond that two tiles share an SM (DUO)
+  const int blocks = (int)(n_tiles < num_sms() ? n_tiles : num_sms());
   WF_CUDA(cudaFuncSetAttribute(live_tc_kernel<D, LAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   live_tc_kernel<D, LAP><<<blocks, THREADS, smem, s>>>(P, X);
   WF_LAUNCH_CHECK();
