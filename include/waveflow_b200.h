@@ -104,6 +104,16 @@ int wf_enforce_bc(int kind, int P, int n_left, const int* nd_left_host, const fl
 int wf_spline_reverse(const float* dense_t, int T, int P, const float* c, const float* y, int64_t M, float tol,
                       float* out, int32_t* n_iter, void* stream);
 
+/* sample_fun_vec of MSpline_fun (msplines_jax.py:129-154, kind WF_KIND_M) and BSpline_fun (bsplines_jax.py:144-171, kind
+ * WF_KIND_B): out[m][s], s < num_samples, are rejection samples of the density proportional to sum_q params[m][q] M_q(x)
+ * (M; bound ymax = max_q params[m][q] * n_knots) or (sum_j c_j OB_j(x))^2 with c = params[m] @ ob_to_b / ||.|| (B; bound
+ * max((c @ b_to_ob)^2)).  dense_t: the [T][4][PP] layout of the M tables / of the orthonormalised B tables.
+ * Philox4x32-10 streams keyed by (seed, row_keys[m] (nullable), m * num_samples + s, attempt): the draws agree with the
+ * reference's threefry streams in distribution, not bit by bit. */
+int wf_spline_sample(const float* dense_t, int kind, int T, int P, const float* ob_to_b, const float* b_to_ob, int n_knots,
+                     const float* params, int64_t M, int num_samples, uint64_t seed, const int64_t* row_keys, float* out,
+                     void* stream);
+
 /* unconstrained_RQS (flows/bijections/neural_splines.py:16-71,74-184): rational-quadratic spline with K bins on
  * [-tail_bound, tail_bound], identity tails.  inputs [M], uw/uh [M][K], ud [M][K-1] (unnormalised).
  * flags: WF_RQS_INVERSE runs the inverse branch and returns -logabsdet (the reference's `inverse=True`);

@@ -92,3 +92,47 @@ def test_sampler_draws_follow_the_prior_density(cuda, kind):
     # exact-mode samples have density exp(log_pdf): E[log p(x)] is finite and the round trip recovers the draws
     ub = _live.forward(spec, w, x, want=("u",))["u"].cpu().numpy()
     assert np.median(np.abs(ub - u)) < 1e-5
+
+
+@pytest.mark.parametrize("kind", ["M", "B"])
+def test_standalone_sample_fun_vec(cuda, kind):
+    """sample_fun_vec of MSpline_fun / BSpline_fun (msplines_jax.py:129-154, bsplines_jax.py:144-171) as an operator: the
+    histogram of the draws of each row follows the row's own density (chi-square against the oracle's spline evaluation)."""
+    from waveflow_b200.splines.factories import BSpline_fun, MSpline_fun
+    rng = np.random.default_rng(3)
+    if kind == "M":
+        init, apply_vec, _g, sample_vec, knots, bc, rb = MSpline_fun()(0, 3, 15, cardinal_splines=True, zero_border=False,
+                                                                      use_cached_bases=True, n_mesh_points=2000,
+                                                                      cached_bases_path_root=None)
+        P = init.shape[0]
+        params = rng.uniform(0.05, 1.0, (3, P)).astype(np.float32)
+        params /= params.sum(-1, keepdims=True)
+        dens = lambda p_, x_: apply_vec(p_, x_)
+    else:
+        init, apply_vec, _g, sample_vec, knots, bc = BSpline_fun()(0, 6, 23, cached_bases_path_root=None, n_mesh_points=2000)
+        P = init.shape[0]
+        params = rng.standard_normal((3, P)).astype(np.float32)
+        dens = lambda p_, x_: apply_vec(p_, x_) ** 2
+    n = 40000
+    tp = torch.from_numpy(params).to(cuda)
+    draws = sample_vec(7, tp, n)
+    assert tuple(draws.shape) == (3, n)
+    d = draws.cpu().numpy()
+    assert d.min() >= 0.0 and d.max() <= 1.0
+    again = sample_vec(7, tp, n)
+    assert torch.equal(draws, again)                                  # counter-based streams: reproducible
+    assert not torch.equal(draws, sample_vec(8, tp, n))
+    edges = np.linspace(0, 1, 41)
+    mids = torch.from_numpy(np.linspace(0, 1, 4001, dtype=np.float32)).to(cuda)
+    for r in range(3):
+        f = dens(tp[r:r + 1].expand(mids.shape[0], -1).contiguous(), mids).cpu().numpy().astype(np.float64)
+        cdf = np.concatenate([[0], np.cumsum(0.5 * (f[1:] + f[:-1]))]); cdf /= cdf[-1]
+        expect = np.diff(np.interp(edges, np.linspace(0, 1, 4001), cdf)) * n
+        obs = np.histogram(d[r], bins=edges)[0]
+        ok = expect > 20
+        chi2 = float((((obs - expect) ** 2) / np.maximum(expect, 1e-9))[ok].sum())
+        assert chi2 < 2.5 * ok.sum(), (kind, r, chi2, ok.sum())
+    # per-row keys (the reference passes one PRNG key per row)
+    keys = torch.arange(3, device=cuda, dtype=torch.int64)
+    dk = sample_vec(keys, tp, 16)
+    assert tuple(dk.shape) == (3, 16)

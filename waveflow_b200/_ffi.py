@@ -67,6 +67,7 @@ _SIGS = {
     "wf_remove_bias": (_i, [_i, _i, _i, _p, _l, _p, _p]),
     "wf_enforce_bc": (_i, [_i, _i, _i, _p, _p, _p, _i, _p, _p, _p, _p, _l, _p, _p]),
     "wf_spline_reverse": (_i, [_p, _i, _i, _p, _p, _l, _f, _p, _p, _p]),
+    "wf_spline_sample": (_i, [_p, _i, _i, _i, _p, _p, _i, _p, _l, _i, C.c_uint64, _p, _p, _p]),
     "wf_rqs_apply": (_i, [_p, _p, _p, _p, _l, _i, _f, _i, _p, _p, _p, _p]),
     "wf_live_net_floats": (_l, [_i]),
     "wf_live_net_floats_tc": (_l, [_i]),

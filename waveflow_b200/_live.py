@@ -310,6 +310,13 @@ def inverse(spec: LiveSpec, weights: torch.Tensor, u: torch.Tensor, exact: bool 
     return x
 
 
+def seed_of(rng) -> int:
+    """The reference passes jax PRNG keys; here an int seed or a torch.Generator (one draw from it) seeds the Philox streams."""
+    if isinstance(rng, torch.Generator):
+        return int(torch.randint(0, 2 ** 62, (1,), generator=rng).item())
+    return int(rng if rng is not None else 0)
+
+
 def sample(spec: LiveSpec, weights: torch.Tensor, seed: int, n: int, device, exact: bool = False):
     """wf_live_sample -> (x [n, D] data-space samples, u [n, D] prior-space draws)."""
     x = torch.empty(n, spec.D, dtype=torch.float32, device=device)

@@ -27,24 +27,6 @@ struct InvParams {
   float wq_P[WF_MAX_P];
 };
 
-// ---------------------------------------------------------------------------------------------- Philox4x32-10
-__device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t (&k)[2]) {
-  const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
-  const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
-  const uint32_t n0 = hi1 ^ c[1] ^ k[0], n1 = lo1, n2 = hi0 ^ c[3] ^ k[1], n3 = lo0;
-  c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
-  k[0] += 0x9E3779B9u; k[1] += 0xBB67AE85u;
-}
-// two uniforms in [0, 1) for (seed, sample, column, attempt)
-__device__ __forceinline__ void philox_uniform2(uint64_t seed, uint64_t sample, uint32_t col, uint32_t attempt, float& a, float& b) {
-  uint32_t c[4] = {(uint32_t)sample, (uint32_t)(sample >> 32), col, attempt};
-  uint32_t k[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
-#pragma unroll
-  for (int r = 0; r < 10; ++r) philox_round(c, k);
-  a = (float)(c[0] >> 8) * (1.0f / 16777216.0f);
-  b = (float)(c[1] >> 8) * (1.0f / 16777216.0f);
-}
-
 // I-spline coefficients of one dimension from the conditioner output parked in S[0..31]:
 //   c_q = w_q (s_q / S + reg) / Z   (made.py:67-72; see sigmoid_spline)  -> S[q];  exclusive prefix sums -> S[32 + q]
 __device__ __forceinline__ void imade_coefficients(const Scratch& S, int P, const float* __restrict__ wq, float reg) {

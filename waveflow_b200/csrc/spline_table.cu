@@ -508,3 +508,85 @@ extern "C" int wf_spline_reverse(const float* dense_t, int T, int P, const float
   WF_LAUNCH_CHECK();
   return WF_OK;
 }
+
+// ============================================================================================ stand-alone rejection samplers
+// sample_fun_vec of MSpline_fun (msplines_jax.py:129-154) and BSpline_fun (bsplines_jax.py:144-171): per row, num_samples
+// draws from the density proportional to f(x) = sum_q c_q M_q(x)  (M)  or  (sum_j c_j OB_j(x))^2  (B), by proposing
+// x ~ U(0,1), y ~ U(0, ymax) with the convex-hull bound of the reference until y < f(x).  One thread per (row, sample);
+// counter-based Philox4x32-10 streams keyed by (seed ^ row key, row * num_samples + sample, attempt): statistical parity
+// with JAX's threefry streams, not bit parity.
+namespace {
+constexpr int SAMPLE_THREADS = 128;
+
+__global__ void __launch_bounds__(SAMPLE_THREADS) spline_sample_kernel(const float* __restrict__ dense_t, int kind, int T, int P, int PP,
+                                                                       const float* __restrict__ ob_to_b, const float* __restrict__ b_to_ob,
+                                                                       int n_knots, const float* __restrict__ params, int64_t M,
+                                                                       int num_samples, uint64_t seed, const int64_t* __restrict__ row_keys,
+                                                                       float* __restrict__ out) {
+  extern __shared__ float mats[];                   // B: ob_to_b [P][P] | b_to_ob [P][P]
+  if (kind == WF_KIND_B) {
+    for (int i = threadIdx.x; i < P * P; i += SAMPLE_THREADS) { mats[i] = ob_to_b[i]; mats[P * P + i] = b_to_ob[i]; }
+  }
+  __syncthreads();
+  const float np_ = (float)(T - 1);
+  const int64_t total = M * num_samples;
+  for (int64_t e = (int64_t)blockIdx.x * SAMPLE_THREADS + threadIdx.x; e < total; e += (int64_t)gridDim.x * SAMPLE_THREADS) {
+    const int64_t row = e / num_samples;
+    const float* w = params + row * P;
+    float c[64];
+    float ymax = 0.f;
+    if (kind == WF_KIND_B) {
+      // obweights = params @ ob_to_b; /= ||.||; ymax = max((obweights @ b_to_ob)^2)     (bsplines_jax.py:163-165)
+      float n2 = 0.f;
+      for (int j = 0; j < P; ++j) {
+        float a = 0.f;
+        for (int i = 0; i < P; ++i) a = fmaf(w[i], mats[i * P + j], a);
+        c[j] = a; n2 = fmaf(a, a, n2);
+      }
+      const float inv = 1.f / sqrtf(n2);
+      for (int j = 0; j < P; ++j) c[j] *= inv;
+      for (int j = 0; j < P; ++j) {
+        float b = 0.f;
+        for (int i = 0; i < P; ++i) b = fmaf(c[i], mats[P * P + i * P + j], b);
+        ymax = fmaxf(ymax, b * b);
+      }
+    } else {
+      for (int q = 0; q < P; ++q) { c[q] = w[q]; ymax = fmaxf(ymax, c[q]); }       // ymax = params.max() * n_knots  (:145-148)
+      ymax *= (float)n_knots;
+    }
+    const uint64_t key = seed ^ (row_keys ? (uint64_t)row_keys[row] * 0x9E3779B97F4A7C15ull : 0ull);
+    float x = 0.f;
+    for (uint32_t attempt = 0; attempt < 1000000u; ++attempt) {
+      float r0, r1;
+      philox_uniform2(key, (uint64_t)e, 0u, attempt, r0, r1);
+      x = r0;
+      const NodeIdx n = node_index(x, T);
+      const float* tl = dense_t + (size_t)n.l * 4 * PP;
+      const float* tr = dense_t + (size_t)n.r * 4 * PP;
+      float f = 0.f;
+      for (int q = 0; q < P; ++q) f = fmaf(c[q], lerp_tab(__ldg(tl + q), __ldg(tr + q), np_, n.dx), f);
+      if (r1 * ymax < (kind == WF_KIND_B ? f * f : f)) break;
+    }
+    out[e] = x;
+  }
+}
+}  // namespace
+
+extern "C" int wf_spline_sample(const float* dense_t, int kind, int T, int P, const float* ob_to_b, const float* b_to_ob, int n_knots,
+                                const float* params, int64_t M, int num_samples, uint64_t seed, const int64_t* row_keys, float* out,
+                                void* stream) {
+  if (M == 0 || num_samples == 0) return WF_OK;
+  if (!dense_t || !params || !out || T < 2 || P < 1 || P > 64 || M < 0 || num_samples < 0) return WF_ERR_INVALID_ARG;
+  if (kind != WF_KIND_M && kind != WF_KIND_B) return WF_ERR_INVALID_ARG;
+  if (kind == WF_KIND_B && (!ob_to_b || !b_to_ob)) return WF_ERR_INVALID_ARG;
+  if (kind == WF_KIND_M && n_knots <= 0) return WF_ERR_INVALID_ARG;
+  const int PP = (P + 3) & ~3;
+  const int64_t total = M * num_samples;
+  const int64_t want = (total + SAMPLE_THREADS - 1) / SAMPLE_THREADS;
+  const int blocks = (int)(want < (int64_t)num_sms() * 8 ? want : (int64_t)num_sms() * 8);
+  const size_t smem = kind == WF_KIND_B ? (size_t)2 * P * P * sizeof(float) : 0;
+  spline_sample_kernel<<<blocks, SAMPLE_THREADS, smem, (cudaStream_t)stream>>>(dense_t, kind, T, P, PP, ob_to_b, b_to_ob, n_knots, params, M,
+                                                                              num_samples, seed, row_keys, out);
+  WF_LAUNCH_CHECK();
+  return WF_OK;
+}

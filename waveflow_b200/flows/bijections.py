@@ -96,10 +96,9 @@ def Serial(*init_funs):
         def inverse_fun(params, inputs, **kwargs):
             if spec is None:
                 return feed_forward(list(reversed(list(params))), list(reversed(inverse_funs)), inputs)
-            from .. import _inverse
             x = f32(inputs)
             w = _live.packed_for(spec, params, None, x.device)
-            return _inverse.flow_inverse(spec, w, x), 0
+            return _live.inverse(spec, w, x), 0
 
         direct_fun.wf_spec = spec
         direct_fun.wf_layerwise = lambda params, inputs: feed_forward(params, direct_funs, inputs)

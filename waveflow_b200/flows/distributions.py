@@ -124,12 +124,11 @@ def MFlow(transformation, sp_transformation, spline_degree, n_internal_knots, co
             return log_probs + log_det
 
         def sample(rng, params, num_samples=1, return_original_samples=False, device="cuda", exact_inverse=False):
-            from .. import _sampler
             if spec is None:
                 raise WaveflowB200Error("MFlow.sample needs the fused configuration built by model_factory.get_model")
             tp, sp = params
             w = _live.packed_for(spec, tp, sp, torch.device(device))
-            x, u = _sampler.sample(spec, w, rng, num_samples, torch.device(device), exact=exact_inverse)
+            x, u = _live.sample(spec, w, _live.seed_of(rng), num_samples, torch.device(device), exact=exact_inverse)
             if return_original_samples:
                 return x, u
             return x

@@ -169,8 +169,7 @@ def MSpline_fun():
             return spline_apply(tabs, _pad(params), x, 1, 1)[0]
 
         def sample_fun_vec(rng_array, params, num_samples):
-            from .. import _sampler
-            return _sampler.rejection_sample_spline(tabs, "M", rng_array, _pad(params), num_samples, n_knots=n_knots)
+            return spline_sample(tabs, "M", rng_array, _pad(params), num_samples, n_knots=n_knots)
 
         def enforce_boundary_conditions(weights):
             return _enforce_bc(tabs, "M", constraints_dict_left, constraints_dict_right, weights)
@@ -183,6 +182,32 @@ def MSpline_fun():
         return initial_params, apply_fun_vec, apply_fun_vec_grad, sample_fun_vec, knots, enforce_boundary_conditions, remove_bias
 
     return init_fun
+
+
+def spline_sample(tabs, kind: str, rng_array, params: torch.Tensor, num_samples: int, n_knots: int = 0) -> torch.Tensor:
+    """sample_fun_vec (msplines_jax.py:129-154, bsplines_jax.py:144-171): params [M, P] -> rejection samples [M, num_samples].
+    rng_array: an int seed, a torch.Generator, or an int64 tensor [M] of per-row keys (the reference passes one PRNG key per
+    row); wf_spline_sample, one thread per (row, sample)."""
+    from .._live import seed_of
+    params = f32(params)
+    Mrows, P = params.shape
+    if P != tabs.P:
+        raise _ffi.WaveflowB200Error(f"expected {tabs.P} spline coefficients per row, got {P}")
+    d = tabs.dev(params.device)
+    keys, seed = None, 0
+    if isinstance(rng_array, torch.Tensor) and rng_array.numel() > 1:
+        keys = rng_array.reshape(Mrows, -1)[:, -1].to(device=params.device, dtype=torch.int64).contiguous()
+    else:
+        seed = seed_of(rng_array if not isinstance(rng_array, torch.Tensor) else int(rng_array.reshape(-1)[0]))
+    out = torch.empty(Mrows, int(num_samples), dtype=torch.float32, device=params.device)
+    if kind == "B":
+        st = lib.wf_spline_sample(ptr(d["ob_dense"]), _ffi.KIND["B"], tabs.T, P, ptr(d["ob_to_b"]), ptr(d["b_to_ob"]), 0, ptr(params), Mrows,
+                                  int(num_samples), C.c_uint64(seed & (2 ** 64 - 1)), ptr(keys), ptr(out), stream_ptr())
+    else:
+        st = lib.wf_spline_sample(ptr(d["dense"]), _ffi.KIND["M"], tabs.T, P, None, None, int(n_knots), ptr(params), Mrows, int(num_samples),
+                                  C.c_uint64(seed & (2 ** 64 - 1)), ptr(keys), ptr(out), stream_ptr())
+    check(st, "wf_spline_sample")
+    return out
 
 
 # ============================================================================================ B-splines
@@ -213,8 +238,7 @@ def BSpline_fun():
             return _apply(params, x, 1)
 
         def sample_fun_vec(rng_array, params, num_samples):
-            from .. import _sampler
-            return _sampler.rejection_sample_spline(tabs, "B", rng_array, f32(params), num_samples)
+            return spline_sample(tabs, "B", rng_array, f32(params), num_samples)
 
         def enforce_boundary_conditions(weights):
             return _enforce_bc(tabs, "B", constraints_dict_left, constraints_dict_right, weights)

@@ -77,11 +77,10 @@ def Waveflow(transformation, sp_transformation, spline_degree, n_internal_knots,
             return phi.prod(-1) * torch.exp(0.5 * log_det)
 
         def sample(rng, params, num_samples=1, device="cuda", exact_inverse=False):
-            from . import _sampler
             if spec is None:
                 raise WaveflowB200Error("Waveflow.sample needs the fused configuration built by get_waveflow_model")
             w = _live.packed_for(spec, params[0], params[1], torch.device(device), fold_prior=False)
-            return _sampler.sample(spec, w, rng, num_samples, torch.device(device), exact=exact_inverse)[0]
+            return _live.sample(spec, w, _live.seed_of(rng), num_samples, torch.device(device), exact=exact_inverse)[0]
 
         psi.wf_spec = spec
         log_pdf.wf_spec = spec
