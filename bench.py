@@ -496,8 +496,20 @@ def run_b200(args):
         train_check = {"walkers": n_train, "step0_loss": float(loss0), "step0_grad_l2": float(g0.double().norm()),
                        "step0_grad_abs_sum": float(g0.double().abs().sum())}
 
+        gx = None
+        if world > 1 and est.peer is not None:
+            try:
+                gx = vqmc.GradExchange(opt_state.flat.numel(), dev)
+            except Exception as exc:                                      # noqa: BLE001 -- any failure: NCCL all-reduce
+                print(f"[bench] peer-memory gradient exchange unavailable ({type(exc).__name__}: {exc}); using NCCL", file=sys.stderr)
+                gx = None
+            ok = torch.tensor([1 if gx is not None else 0], device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if int(ok.item()) == 0:
+                gx = None
+
         def tstep(i):
-            return vqmc.train_step_efficient(i, psi, h_fn, opt_update, opt_state, tparams, x_train, 0.0, n_total=n_train)
+            return vqmc.train_step_efficient(i, psi, h_fn, opt_update, opt_state, tparams, x_train, 0.0, n_total=n_train, exchange=gx)
         for i in range(3):
             tstep(i)
         torch.cuda.synchronize()
@@ -793,7 +805,10 @@ def run_b200(args):
                  "walkers_total": n_train, "walkers_per_gpu": int(x_train.shape[0]), "ms_per_step": ms,
                  "walkers_per_s": n_train / (ms * 1e-3), "loss_after_13_steps": train_loss, "cross_n_checksum": train_check,
                  "walker_set": "the workload's 65536 walkers filtered to |psi| > 1e-4 max|psi| (identical on every rank and for every N)",
-                 "exchange": "none" if world == 1 else f"all-reduce of the flat gradient ({opt_state.flat.numel()} floats) + 32-byte loss sums per step",
+                 "exchange": "none" if world == 1 else (
+                     f"flat gradient ({opt_state.flat.numel()} floats) + 32-byte loss sums per step: " +
+                     ("one peer-memory kernel (wf_p2p_allreduce_vec) inside the CUDA graph of the step" if gx is not None
+                      else "two NCCL all-reduces between eagerly launched kernels")),
                  "algorithmic_tflops_per_gpu": tfl, "frac_of_measured_fp32_fma": tfl / fp32_peak,
                  "gpu_launches_per_step": 76 * ((int(x_train.shape[0]) + 65535) // 65536) + 1}
         if world == 1:

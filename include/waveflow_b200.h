@@ -326,6 +326,18 @@ int64_t wf_p2p_allreduce_buffer_bytes(int world);
 int wf_p2p_allreduce_sums(const uint64_t* peer_bufs_dev, int rank, int world, uint64_t step, const double* local, double* out,
                           void* stream);
 
+/* The same one-shot scheme for a float32 vector (the flat parameter gradient of the training step): data[0..n) is
+ * replaced by its sum over the ranks, added in rank order (bit-identical on every rank).  One CTA per 2048 floats stores its
+ * chunk into every peer's buffer, raises a per-chunk flag and waits for the peers' flags of the same chunk.
+ * peer_bufs_dev: `world` symmetric buffers of wf_p2p_allreduce_vec_buffer_bytes(world, n) bytes, zero-initialised.
+ * step: 1, 2, 3, ... identical on all ranks; or step_dev (device uint64, initialised to 1) which the kernel reads and advances
+ * itself (the last CTA to finish, counted in done_counter: device uint32, zero-initialised) -- a captured CUDA graph of the
+ * call can then be replayed.  Time-outs behave as in wf_p2p_allreduce_sums (NaN, sticky error word = the last 64 bytes).
+ * sums / sums_out (nullable, both or neither): four doubles (the loss sums of the step) all-reduced along with the vector. */
+int64_t wf_p2p_allreduce_vec_buffer_bytes(int world, int64_t n);
+int wf_p2p_allreduce_vec(const uint64_t* peer_bufs_dev, int rank, int world, uint64_t step, uint64_t* step_dev, float* data, int64_t n,
+                         const double* sums, double* sums_out, uint32_t* done_counter, void* stream);
+
 /* Single-GPU self-test of the same protocol: ALL `world` ranks are emulated by the warps of one CTA (one launch, so the
  * mutual flag waits cannot dead-lock on a device that serialises kernels).  peer_bufs_dev: `world` buffers on this
  * device; locals / outs: [world][4] doubles.  skip_rank >= 0: that rank never arrives (exercises the time-out path; pass a

@@ -167,3 +167,37 @@ def test_peer_memory_exchange_protocol_emulated_ranks(cuda):
     torch.cuda.synchronize()
     assert torch.equal(o, v)
     assert lib.wf_p2p_allreduce_sums(ptr(p1), 0, 1, C.c_uint64(0), ptr(v), ptr(o), C.c_void_p(0)) == -1
+
+
+def test_vector_allreduce_single_rank_and_step_counter(cuda):
+    """wf_p2p_allreduce_vec with world = 1 (the multi-rank run is tools/p2p_test.py under torchrun): the vector and the loss sums
+    come back unchanged, the device-side step counter advances once per call, a captured graph replays."""
+    import ctypes as C
+    from waveflow_b200._ffi import check, lib, ptr
+    n = 5000
+    nbytes = int(lib.wf_p2p_allreduce_vec_buffer_bytes(1, n))
+    assert nbytes > 2 * 6144 * 4 and lib.wf_p2p_allreduce_vec_buffer_bytes(0, n) == -1
+    buf = torch.zeros((nbytes + 7) // 8, dtype=torch.float64, device=cuda)
+    ptrs = torch.tensor([buf.data_ptr()], dtype=torch.int64, device=cuda)
+    step = torch.ones(1, dtype=torch.int64, device=cuda)
+    cnt = torch.zeros(1, dtype=torch.int32, device=cuda)
+    v = torch.randn(n, device=cuda)
+    keep = v.clone()
+    s4 = torch.tensor([1.0, 2.0, 3.0, 4.5], dtype=torch.float64, device=cuda)
+    so = torch.zeros(4, dtype=torch.float64, device=cuda)
+    call = lambda: check(lib.wf_p2p_allreduce_vec(ptr(ptrs), 0, 1, C.c_uint64(0), ptr(step), ptr(v), n, ptr(s4), ptr(so), ptr(cnt),
+                                                  C.c_void_p(torch.cuda.current_stream().cuda_stream)), "wf_p2p_allreduce_vec")
+    for k in range(3):
+        call()
+        torch.cuda.synchronize()
+        assert torch.equal(v, keep) and torch.equal(so, s4) and int(step.item()) == 2 + k and int(cnt.item()) == 0
+    side = torch.cuda.Stream(device=cuda)
+    side.wait_stream(torch.cuda.current_stream())
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        call()
+    before = int(step.item())
+    graph.replay(); graph.replay()
+    torch.cuda.synchronize()
+    assert int(step.item()) == before + 2 and torch.equal(v, keep)
+    assert lib.wf_p2p_allreduce_vec(ptr(ptrs), 0, 1, C.c_uint64(0), None, ptr(v), n, None, None, None, C.c_void_p(0)) == -1   # no step

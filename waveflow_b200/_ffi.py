@@ -91,6 +91,8 @@ _SIGS = {
     "wf_adam_step": (_i, [_p, _p, _p, _p, _l, _l, _p, _f, _f, _f, _f, _p]),
     "wf_p2p_allreduce_buffer_bytes": (_l, [_i]),
     "wf_p2p_allreduce_sums": (_i, [_p, _i, _i, C.c_uint64, _p, _p, _p]),
+    "wf_p2p_allreduce_vec_buffer_bytes": (_l, [_i, _l]),
+    "wf_p2p_allreduce_vec": (_i, [_p, _i, _i, C.c_uint64, _p, _p, _l, _p, _p, _p, _p]),
     "wf_p2p_allreduce_emulated": (_i, [_p, _i, C.c_uint64, _p, _p, _i, _l, _p]),
     "wf_local_energy": (_i, [C.POINTER(LiveModelStruct), C.POINTER(LiveTablesStruct), _p, _p, _i, _p, _l, _p, _p, _p, _p, _p,
                              _p, _p]),
@@ -122,7 +124,7 @@ class _DeviceGuardedLib:
 
 _HOST_ONLY = {"wf_abi_version", "wf_status_string", "wf_table_layout_host", "wf_live_net_floats", "wf_live_net_floats_tc",
               "wf_vqmc_param_floats",
-              "wf_vqmc_grad_workspace_floats", "wf_p2p_allreduce_buffer_bytes", "wf_rqs_coupling_net_floats",
+              "wf_vqmc_grad_workspace_floats", "wf_p2p_allreduce_buffer_bytes", "wf_p2p_allreduce_vec_buffer_bytes", "wf_rqs_coupling_net_floats",
               "wf_rqs_coupling_tc_net_floats", "wf_rqs_coupling_tc_workspace_floats"}
 _CALL_DEVICE = {"dev": None}
 

@@ -153,7 +153,7 @@ class GraphedTrainStep:
     graph replays them without host involvement.  Everything that changes between steps lives in device memory: the walkers
     (static buffer), the running average (float32[1]) and the Adam step index (int64[1])."""
 
-    def __init__(self, spec, opt_state: AdamState, opt_update, protons, batch_shape, device):
+    def __init__(self, spec, opt_state: AdamState, opt_update, protons, batch_shape, device, n_total=None, exchange=None):
         import weakref
         self.spec, self.state = spec, weakref.ref(opt_state)     # no strong reference: the cache entry must not keep it alive
         self.x = torch.zeros(batch_shape, dtype=torch.float32, device=device)
@@ -169,10 +169,13 @@ class GraphedTrainStep:
         def body():
             self.grad.zero_()
             self.sums.zero_()
-            loss_grad(spec, opt_state.flat, self.x, protons, 0.0, grad=self.grad, sums=self.sums, running_average_dev=self.ra,
-                      max_chunk=n, ws=self.ws)
+            # sharded step (exchange given): this rank's shard with the GLOBAL 1 / n_total, then the flat gradient and the loss
+            # sums are all-reduced by one peer-memory kernel inside the same graph
+            loss_grad(spec, opt_state.flat, self.x, protons, 0.0, n_total=n_total or n, grad=self.grad, sums=self.sums,
+                      running_average_dev=self.ra, max_chunk=n, ws=self.ws)
+            total = exchange.all_reduce(self.grad, self.sums) if exchange is not None else self.sums
             opt_update(0, self.grad, opt_state, step_dev=self.step)
-            self.loss.copy_((self.sums[0] / float(n)).to(torch.float32))
+            self.loss.copy_((total[0] / float(n_total or n)).to(torch.float32))
 
         # warm-up on a side stream (first-call attribute setup, workspace allocation), with the optimiser state restored after
         keep = (opt_state.flat.clone(), opt_state.m.clone(), opt_state.v.clone())

@@ -41,7 +41,7 @@ def _flat_of(params, opt_state, device):
 
 
 def value_and_grad_efficient(params, psi, h_fn, batch, running_average, group=None, opt_state=None, flat_grad=False,
-                             n_total=None):
+                             n_total=None, exchange=None):
     """value_and_grad(loss_fn_efficient, argnums=0)(params, psi, h_fn, batch, running_average)  (vqmc.py:220).
 
     -> (loss, gradients in the structure of `params`).  With torch.distributed initialised, `batch` is this rank's shard of
@@ -58,7 +58,7 @@ def value_and_grad_efficient(params, psi, h_fn, batch, running_average, group=No
     n_total = int(n_total) if n_total is not None else total_walkers(x.shape[0], dev, group)
     sums = torch.zeros(4, dtype=torch.float64, device=dev)
     grad, _ = _train.loss_grad(spec, flat, x, h_fn.protons, float(running_average), n_total=n_total, sums=sums)
-    loss = reduce_loss_and_grad(grad, sums, n_total, group)
+    loss = reduce_loss_and_grad(grad, sums, n_total, group, exchange=exchange)
     return loss, (grad if flat_grad else _train.unravel(params, grad))
 
 
@@ -76,45 +76,92 @@ def total_walkers(n_local: int, device, group=None) -> int:
     return int(cnt.item())
 
 
-def reduce_loss_and_grad(grad: torch.Tensor, sums: torch.Tensor, n_total: int, group=None) -> torch.Tensor:
+def reduce_loss_and_grad(grad: torch.Tensor, sums: torch.Tensor, n_total: int, group=None, exchange=None) -> torch.Tensor:
     """The exchange step of the sharded training step: every rank evaluated its shard with the global 1/N, so the
     flat gradients simply add; the loss is the mean over ALL walkers, as jnp.mean does: a non-finite E_loc is not dropped, it makes
     the loss (and the gradient) non-finite on every path -- kernels, eager loss_fn_efficient and the graph replay agree;
     sums[2] counts all walkers.  In place on grad / sums; backend-agnostic (NCCL, gloo in the CPU test)."""
     if _world(group) > 1:
-        torch.distributed.all_reduce(grad, group=group)
-        torch.distributed.all_reduce(sums, group=group)
+        if exchange is not None:
+            sums = exchange.all_reduce(grad, sums)        # one kernel over NVLink peer memory (GradExchange)
+        else:
+            torch.distributed.all_reduce(grad, group=group)
+            torch.distributed.all_reduce(sums, group=group)
     return (sums[0] / float(n_total)).to(torch.float32)
 
 
-GRAPH_MAX_BATCH = 4096      # at or below this many walkers the step is launch-bound and is replayed from a CUDA graph
+GRAPH_MAX_BATCH = 16384     # at or below this many walkers per rank the step is launch-bound and is replayed from a CUDA graph
 _GRAPHS: dict = {}
 
 
 def train_step_efficient(epoch, psi, h_fn, opt_update, opt_state, params, batch, running_average, group=None, use_graph=None,
-                         n_total=None):
+                         n_total=None, exchange=None):
     """vqmc.py:214-221: -> (opt_update(epoch, gradients, opt_state), loss_val).
 
-    Single-process steps on small batches (the reference trains with 128 / 256 walkers) are captured once per
-    (optimiser state, batch shape) in a CUDA graph and replayed (use_graph=False disables, True forces)."""
+    Steps on small batches (the reference trains with 128 / 256 walkers) are launch bound: they are captured once per (optimiser
+    state, batch shape) in a CUDA graph and replayed (use_graph=False disables, True forces).  Under torch.distributed `batch`
+    is this rank's shard; with `exchange` (a GradExchange: flat gradient + loss sums all-reduced by one kernel over NVLink peer
+    memory) and a known `n_total` the whole sharded step -- gradient, exchange, Adam -- is ONE graph replay per rank; without
+    it the exchange is an NCCL / gloo all-reduce between eagerly launched kernels."""
     dist = torch.distributed
     world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
     x = _live._ffi.f32(batch)
-    graphable = (world == 1 and getattr(opt_update, "graphable", False) and params is opt_state.tree
-                 and h_fn.wf_spec is not None)
+    graphable = (getattr(opt_update, "graphable", False) and params is opt_state.tree and h_fn.wf_spec is not None
+                 and (world == 1 or (exchange is not None and n_total is not None)))
     if use_graph is None:
         use_graph = graphable and x.shape[0] <= GRAPH_MAX_BATCH
     if use_graph and graphable:
-        key = (id(opt_state), tuple(x.shape), str(x.device))
+        key = (id(opt_state), tuple(x.shape), str(x.device), n_total if world > 1 else None)
         g = _GRAPHS.get(key)
         if g is None or g.state() is not opt_state:
             import weakref
-            g = _GRAPHS[key] = _train.GraphedTrainStep(h_fn.wf_spec, opt_state, opt_update, h_fn.protons, tuple(x.shape), x.device)
+            g = _GRAPHS[key] = _train.GraphedTrainStep(h_fn.wf_spec, opt_state, opt_update, h_fn.protons, tuple(x.shape), x.device,
+                                                       n_total=n_total if world > 1 else None,
+                                                       exchange=exchange if world > 1 else None)
             weakref.finalize(opt_state, _GRAPHS.pop, key, None)      # the graph (and its buffers) die with the optimiser state
         return opt_state, g(epoch, x, float(running_average))
     loss_val, gradients = value_and_grad_efficient(params, psi, h_fn, batch, running_average, group=group, opt_state=opt_state,
-                                                   flat_grad=True, n_total=n_total)
+                                                   flat_grad=True, n_total=n_total, exchange=exchange)
     return opt_update(epoch, gradients, opt_state), loss_val
+
+
+class GradExchange:
+    """All-reduce of the flat parameter gradient (+ the four loss sums) over NVLink peer memory: wf_p2p_allreduce_vec on
+    symmetric buffers from torch.distributed._symmetric_memory -- one kernel of ~24 CTAs instead of two NCCL all-reduces, and,
+    with the step counter in device memory, capturable in the CUDA graph of the training step.  Construction is collective."""
+
+    def __init__(self, n: int, device, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+        from ._ffi import lib
+        dist = torch.distributed
+        group = group if group is not None else dist.group.WORLD
+        self.n = int(n)
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        nbytes = int(lib.wf_p2p_allreduce_vec_buffer_bytes(self.world, self.n))
+        if nbytes < 0:
+            raise RuntimeError("unsupported world size for the peer-memory gradient exchange")
+        self.buf = symm_mem.empty((nbytes + 7) // 8, dtype=torch.float64, device=device)
+        self.buf.zero_()
+        self.handle = symm_mem.rendezvous(self.buf, group)
+        self.ptrs = torch.tensor([int(p) for p in self.handle.buffer_ptrs], dtype=torch.int64, device=device)
+        self.step = torch.ones(1, dtype=torch.int64, device=device)          # advanced by the kernel itself
+        self.counter = torch.zeros(1, dtype=torch.int32, device=device)
+        self.sums_out = torch.zeros(4, dtype=torch.float64, device=device)
+        torch.cuda.synchronize(device)
+        dist.barrier(group)
+
+    def all_reduce(self, grad: torch.Tensor, sums: torch.Tensor) -> torch.Tensor:
+        """grad (flat float32 [n]) is summed over the ranks in place; -> the summed loss sums (float64 [4])."""
+        from ._ffi import check, lib, ptr, stream_ptr
+        import ctypes as C
+        if grad.numel() != self.n or grad.dtype != torch.float32:
+            raise ValueError("gradient buffer does not match the exchange")
+        check(lib.wf_p2p_allreduce_vec(ptr(self.ptrs), self.rank, self.world, C.c_uint64(0), ptr(self.step), ptr(grad), self.n, ptr(sums),
+                                       ptr(self.sums_out), ptr(self.counter), stream_ptr()), "wf_p2p_allreduce_vec")
+        return self.sums_out
+
+    def failed_step(self) -> int:
+        return int(self.buf.view(torch.int64)[-8].item())
 
 
 class PeerExchange:
