@@ -107,6 +107,10 @@ def test_standalone_sample_fun_vec(cuda, kind):
         P = init.shape[0]
         params = rng.uniform(0.05, 1.0, (3, P)).astype(np.float32)
         params /= params.sum(-1, keepdims=True)
+        # the reference's bound ymax = max(c) * n_knots (msplines_jax.py:145-148) only dominates the density for coefficients
+        # that went through remove_bias + the {0:0} boundary conditions, which is how MFlow.sample always calls it
+        # (distributions.py:172-176); raw coefficients put up to 5x more mass at the ends than the bound allows
+        params = bc(rb(torch.from_numpy(params).to(cuda))).cpu().numpy()
         dens = lambda p_, x_: apply_vec(p_, x_)
     else:
         init, apply_vec, _g, sample_vec, knots, bc = BSpline_fun()(0, 6, 23, cached_bases_path_root=None, n_mesh_points=2000)
