@@ -38,6 +38,9 @@ UNIT = "walkers/s"
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures (profiles/)
 TRAFFIC = {
     ("live_simt", 4, 65536): 2376960,        # profiles/r01_live_kernel_d4_lap_ncu_summary.txt (algorithmic: 24 B/walker = 1.57 MB)
+    ("live_tc", 4, 65536): 2564096,          # profiles/r02_live_tc_kernel_d4_lap_ncu_summary.txt (reads only; 0 B written back through DRAM)
+    ("rqs_staged", 32, 1 << 24, False): 6147839000 + 137697792,   # profiles/r02_rqs32_ncu_summary.txt (algorithmic: 392 B x 2^24 = 6.58 GB)
+    ("spline_local", 29, 1 << 24): 2013555000 + 196376576,        # profiles/r02_spline_ncu_summary.txt (algorithmic: 128 B x 2^24 = 2.15 GB)
 }
 
 
@@ -649,8 +652,7 @@ def run_b200(args):
         sweep = {"kernel": "spline_local_kernel<true> (wf_spline_apply_local)", "elements": M, "P": tabs.P, "ms": ms, "parity": par_spline,
                  "elements_per_s": M / (ms * 1e-3),
                  "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
-                              # ncu --set full of this launch (profiles/r01_spline_local_ncu_summary.txt): 2.014 GB read + 0.197 GB written
-                              "traffic": 2210474864, "algorithmic_bytes_per_element": bytes_per_el, "peak_source": hbm_src,
+                              "traffic": TRAFFIC.get(("spline_local", tabs.P, M)), "algorithmic_bytes_per_element": bytes_per_el, "peak_source": hbm_src,
                               "inputs": "2.1 GB per launch (> 126 MB L2)"}}
         del c, xs
 
