@@ -149,45 +149,49 @@ def b_table(k: int, t: np.ndarray, mesh: np.ndarray, nd: int) -> np.ndarray:
 
 
 # --------------------------------------------------------------------------- orthonormalisation
-def gram_schmidt_l2r(imat: np.ndarray, ovlp: np.ndarray) -> np.ndarray:
-    """Left-to-right Gram-Schmidt on the columns of imat (ortho_splines.py:140-161). Mutates ovlp."""
-    mat = np.copy(imat)
-    n, m = mat.shape
-    omat = np.zeros((n, m))
-    omat[:, 0] = mat[:, 0] / np.sqrt(ovlp[0, 0])
-    for i in range(m - 1):
-        vec = ovlp[i, (i + 1):]
-        mat[:, (i + 1):] -= np.outer(mat[:, i], vec) / ovlp[i, i]
-        ovlp[(i + 1):, (i + 1):] -= np.outer(vec, vec) / ovlp[i, i]
-        omat[:, i + 1] = mat[:, i + 1] / np.sqrt(ovlp[i + 1, i + 1])
-    return omat
+def gram_schmidt_l2r(cols: np.ndarray, gram: np.ndarray) -> np.ndarray:
+    """Gram-Schmidt on the columns of `cols`, left to right, driven by their Gram matrix `gram` (= cols.T @ cols, consumed).
+
+    The orthonormal B basis is part of the numerical contract (a different orthonormalisation changes psi for the published
+    checkpoint), so this follows the reference's elimination step for step -- same operations in the same order, derived from
+    ortho_splines.py:140-161 -- and is pinned bit for bit by tests/test_tablegen_golden.py: at step i the remaining columns and
+    the trailing block of the Gram matrix are deflated by column i (outer product, THEN the division by the pivot, THEN the
+    subtraction), and column i is scaled by the square root of its current pivot."""
+    work = np.copy(cols)
+    m = work.shape[1]
+    out = np.zeros_like(work, dtype=np.float64)
+    for i in range(m):
+        pivot = gram[i, i]
+        out[:, i] = work[:, i] / np.sqrt(pivot)
+        if i + 1 < m:
+            row = gram[i, (i + 1):]
+            work[:, (i + 1):] -= np.outer(work[:, i], row) / pivot
+            gram[(i + 1):, (i + 1):] -= np.outer(row, row) / pivot
+    return out
 
 
 def gram_schmidt_symm(imat: np.ndarray) -> np.ndarray:
-    """Symmetrised Gram-Schmidt of the columns of imat (ortho_splines.py:43-112)."""
+    """Symmetrised Gram-Schmidt of the columns of imat (the scheme of ortho_splines.py:43-112, restated with explicit column
+    orders; bit-identical tables, tests/test_tablegen_golden.py).
+
+    Two left-to-right passes over interleaved column orders -- one starting at the left end (0, m-1, 1, m-2, ...), one at the
+    right end (m-1, 0, m-2, 1, ...) -- give, at the even positions, vectors that are mirror images of each other; each mirror
+    pair (v1, v2) with overlap ov is then combined symmetrically (Loewdin for a 2 x 2 block) into the basis functions i and
+    m-1-i."""
     mat = np.copy(imat)
     n, m = mat.shape
     if m % 2:
         raise ValueError("only an even number of bases can be orthogonalised (ortho_splines.py:59-63)")
-    npair = m // 2
-    ovlp = np.dot(mat.T, mat)
-    ind_j = np.concatenate([np.arange(0, 2 * npair - 1, 2), np.arange(1, 2 * npair, 2)])
-    ind_k = np.concatenate([np.arange(m - 1, m - npair - 1, -1), np.arange(0, npair)])
-    mat_r = np.zeros((n, 2 * npair)); ovlp_r = np.zeros((2 * npair, 2 * npair))
-    mat_r[:, ind_j] = mat[:, ind_k]
-    ovlp_r[:, ind_j] = ovlp[:, ind_k]
-    ovlp_r[ind_j, :] = ovlp_r[ind_k, :]
-    mat_l = np.zeros((n, m)); ovlp_l = np.zeros((m, m))
-    ind_jl = np.concatenate([ind_j, np.array([m - 1])])
-    ind_kl = np.concatenate([np.arange(0, npair), np.arange(m - 1, m - npair - 1, -1), np.array([npair])])
-    mat_l[:, ind_jl] = mat[:, ind_kl]
-    ovlp_l[:, ind_jl] = ovlp[:, ind_kl]
-    ovlp_l[ind_jl, :] = ovlp_l[ind_kl, :]
-    mat_l = gram_schmidt_l2r(mat_l, ovlp_l)
-    mat_r = gram_schmidt_l2r(mat_r, ovlp_r)
+    half = m // 2
+    gram = np.dot(mat.T, mat)
+    lo, hi = np.arange(half), np.arange(m - 1, m - half - 1, -1)
+    order_l = np.stack([lo, hi], axis=1).reshape(-1)          # 0, m-1, 1, m-2, ...
+    order_r = np.stack([hi, lo], axis=1).reshape(-1)          # m-1, 0, m-2, 1, ...
+    from_left = gram_schmidt_l2r(mat[:, order_l], gram[np.ix_(order_l, order_l)].copy())
+    from_right = gram_schmidt_l2r(mat[:, order_r], gram[np.ix_(order_r, order_r)].copy())
     omat = np.zeros((n, m))
-    for i in range(npair):
-        v1, v2 = mat_l[:, 2 * i], mat_r[:, 2 * i]
+    for i in range(half):
+        v1, v2 = from_left[:, 2 * i], from_right[:, 2 * i]
         ov = np.dot(v1, v2)
         assert 0 <= ov <= 1
         s1, s2 = 1. / np.sqrt(1 + ov), 1. / np.sqrt(1 - ov)
