@@ -211,6 +211,31 @@ __device__ __forceinline__ void issue_group32(uint32_t d_tmem, uint32_t a_hi, ui
   }
 }
 
+// sigmoid / tanh through ex2.approx.ftz + rcp.approx: __expf carries a denormal fix-up (a compare and two predicated multiplies
+// per call) that the saturating forms below do not need (ex2 -> 0 or inf gives exactly 1 / 0 / +-1)
+__device__ __forceinline__ float ex2_ftz(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float tc_sigmoid(float x) { return __fdividef(1.f, 1.f + ex2_ftz(-1.4426950408889634f * x)); }
+__device__ __forceinline__ float tc_tanh(float x) {
+  const float xc = fminf(fmaxf(x, -15.f), 15.f);
+  return 1.f - __fdividef(2.f, ex2_ftz(2.8853900817779268f * xc) + 1.f);
+}
+// tanh on a 1-register bundle (same algebra as tanh_bundle of live_device.cuh)
+template <int D, bool LAP>
+__device__ __forceinline__ float tc_tanh_bundle(const Ctx<D, LAP>& cx, float a) {
+  if constexpr (LAP) {
+    const float th = tc_tanh(cx.bv(a));
+    const float f1 = 1.f - th * th;
+    const float gg = cx.gsum(a * a);
+    float r = f1 * a;
+    if (cx.is_l) r = fmaf(-2.f * th * f1, gg, r);
+    return cx.is_v ? th : r;
+  } else return tc_tanh(a);
+}
+
 struct ScratchT {
   float* col;
   __device__ __forceinline__ float& operator[](int slot) const { return col[slot * THREADS]; }
@@ -266,6 +291,7 @@ __device__ __forceinline__ void sigmoid_spline_regs(const Ctx<D, LAP>& cx, uint3
   const float Wpre = PREFIX_ONE ? cwq[lo_w] : 0.f;
   // conditioner outputs of this dimension: 8 accumulator columns at a time straight from tensor memory (+ bias on the value
   // lane); the chunk loop stays rolled to keep the kernel inside the instruction cache
+  const float vmask = cx.is_v ? 1.f : 0.f;            // the bias enters the value component only
   uint32_t nxt[8];
   tmem_ld8_issue(tacc, nxt);
   tmem_wait_ld8(nxt);
@@ -275,24 +301,27 @@ __device__ __forceinline__ void sigmoid_spline_regs(const Ctx<D, LAP>& cx, uint3
 #pragma unroll
     for (int t = 0; t < 8; ++t) o8[t] = __uint_as_float(nxt[t]);
     if (c + 1 < WF_MAX_P / 8) tmem_ld8_issue(tacc + (uint32_t)((c + 1) * 8), nxt);      // lands while this chunk is processed
+    // straight-line code for the 8 coefficients of the chunk (no per-coefficient branch: the eight sigmoid chains overlap);
+    // slots q >= P hold exact zeros (zero-padded weights) and are masked to sigmoid(-inf) = 0 with all derivatives 0
 #pragma unroll
     for (int t = 0; t < 8; ++t) {
       const int q = c * 8 + t;
-      if (q < P) {
-        const float oq = cx.is_v ? o8[t] + bias[q] : o8[t];
-        const float ov = cx.bv(oq);
-        const float s = fast_sigmoid(ov);
-        const float d1 = s * (1.f - s);
-        const J sq = cx.unary(J{oq, 0.f, ov}, s, d1, d1 * (1.f - 2.f * s));
-        const float w = wq[q];
-        if (PREFIX_ONE) {
-          if (q == lo_w) PRE = SW;                     // SW holds the bases 0 .. q - 1 here
-        }
-        Ssum.m += sq.m;
-        if constexpr (LAP) Ssum.p += sq.p;
-        axpy(w, sq, SW);
-        S[q] = sq.m;
+      const float oq = fmaf(vmask, bias[q], o8[t]);
+      const float ovr = cx.bv(oq);
+      const float ov = q < P ? ovr : -INFINITY;
+      const float s = tc_sigmoid(ov);
+      const float d1 = s * (1.f - s);
+      const J sq = cx.unary(J{oq, 0.f, ov}, s, d1, d1 * (1.f - 2.f * s));
+      const float w = wq[q];
+      if (PREFIX_ONE) {
+        const bool snap = q == lo_w;                   // SW holds the bases 0 .. q - 1 here
+        PRE.m = snap ? SW.m : PRE.m;
+        if constexpr (LAP) PRE.p = snap ? SW.p : PRE.p;
       }
+      Ssum.m += sq.m;
+      if constexpr (LAP) Ssum.p += sq.p;
+      axpy(w, sq, SW);
+      S[q] = sq.m;
     }
     tmem_wait_ld8(nxt);
   }
@@ -461,7 +490,9 @@ template <int D, bool LAP>
 __global__ void __launch_bounds__(THREADS, 1) live_tc_kernel(const __grid_constant__ LiveParams P, const __grid_constant__ TcExtra X) {
   using C = Ctx<D, LAP>;
   extern __shared__ unsigned char smem_raw[];
-  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // 1024-byte alignment (swizzled MMA operands) by an OFFSET on the shared array: an integer round trip of the pointer would
+  // make every later access a generic LD.E / ST.E (long-scoreboard latency) instead of LDS / STS
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   constexpr int N3 = D * WF_MAX_P;
   constexpr int NETF = net_floats_tc(D);
   constexpr uint32_t W2_BYTES = 2 * W2_PLANE_BYTES, W3_BYTES = 2 * w3_plane_bytes(D), SMALL_BYTES = small_floats(D) * 4;
@@ -601,7 +632,7 @@ __global__ void __launch_bounds__(THREADS, 1) live_tc_kernel(const __grid_consta
           float acc = cx.is_v ? b1[j] : 0.f;
 #pragma unroll
           for (int d = 0; d < D; ++d) acc = fmaf(us[d], W1[d * WF_HIDDEN + j], acc);
-          h[t] = tanh_bundle<D, LAP>(cx, acc);
+          h[t] = tc_tanh_bundle<D, LAP>(cx, acc);
         }
         store_planes8(my_hi, my_lo, (uint32_t)(fbase + c * 8), h);
       }
@@ -639,7 +670,7 @@ __global__ void __launch_bounds__(THREADS, 1) live_tc_kernel(const __grid_consta
 #pragma unroll
           for (int t = 0; t < 8; ++t) {
             const float acc = cx.is_v ? v[t] + b2[fbase + c * 8 + t] : v[t];
-            h[t] = tanh_bundle<D, LAP>(cx, acc);
+            h[t] = tc_tanh_bundle<D, LAP>(cx, acc);
           }
           tmem_wait_ld8(nxt);
           store_planes8(my_hi, my_lo, (uint32_t)(fbase + c * 8), h);
