@@ -218,10 +218,15 @@ __device__ __forceinline__ float ex2_ftz(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-__device__ __forceinline__ float tc_sigmoid(float x) { return __fdividef(1.f, 1.f + ex2_ftz(-1.4426950408889634f * x)); }
+__device__ __forceinline__ float rcp_ftz(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float tc_sigmoid(float x) { return rcp_ftz(1.f + ex2_ftz(-1.4426950408889634f * x)); }
 __device__ __forceinline__ float tc_tanh(float x) {
   const float xc = fminf(fmaxf(x, -15.f), 15.f);
-  return 1.f - __fdividef(2.f, ex2_ftz(2.8853900817779268f * xc) + 1.f);
+  return fmaf(-2.f, rcp_ftz(ex2_ftz(2.8853900817779268f * xc) + 1.f), 1.f);
 }
 // tanh on a 1-register bundle (same algebra as tanh_bundle of live_device.cuh)
 template <int D, bool LAP>
@@ -303,10 +308,12 @@ __device__ __forceinline__ void sigmoid_spline_regs(const Ctx<D, LAP>& cx, uint3
     if (c + 1 < WF_MAX_P / 8) tmem_ld8_issue(tacc + (uint32_t)((c + 1) * 8), nxt);      // lands while this chunk is processed
     // straight-line code for the 8 coefficients of the chunk (no per-coefficient branch: the eight sigmoid chains overlap);
     // slots q >= P hold exact zeros (zero-padded weights) and are masked to sigmoid(-inf) = 0 with all derivatives 0
+    const float4 bA = *reinterpret_cast<const float4*>(bias + c * 8), bB = *reinterpret_cast<const float4*>(bias + c * 8 + 4);
+    const float b8[8] = {bA.x, bA.y, bA.z, bA.w, bB.x, bB.y, bB.z, bB.w};
 #pragma unroll
     for (int t = 0; t < 8; ++t) {
       const int q = c * 8 + t;
-      const float oq = fmaf(vmask, bias[q], o8[t]);
+      const float oq = fmaf(vmask, b8[t], o8[t]);
       const float ovr = cx.bv(oq);
       const float ov = q < P ? ovr : -INFINITY;
       const float s = tc_sigmoid(ov);
@@ -334,7 +341,7 @@ __device__ __forceinline__ void sigmoid_spline_regs(const Ctx<D, LAP>& cx, uint3
     sq.v = cx.bv(sq.m);
     if constexpr (LAP) {
       const float d1 = fmaxf(sq.v * (1.f - sq.v), 1e-30f);
-      sq.p = cx.is_g ? __fdividef((1.f - 2.f * sq.v) * sq.m * sq.m, d1) : 0.f;
+      sq.p = cx.is_g ? (1.f - 2.f * sq.v) * sq.m * sq.m * rcp_ftz(d1) : 0.f;
     } else sq.p = 0.f;
     return sq;
   };
@@ -624,16 +631,24 @@ __global__ void __launch_bounds__(THREADS, 1) live_tc_kernel(const __grid_consta
 
       // ------------------------------------------------ layer 1 (K = D, CUDA cores) -> A planes
 #pragma unroll 1
+      const float vmask = cx.is_v ? 1.f : 0.f;          // biases enter the value component only
       for (int c = 0; c < fw / 8; ++c) {
+        const int j0 = fbase + c * 8;
         float h[8];
-#pragma unroll
-        for (int t = 0; t < 8; ++t) {
-          const int j = fbase + c * 8 + t;
-          float acc = cx.is_v ? b1[j] : 0.f;
-#pragma unroll
-          for (int d = 0; d < D; ++d) acc = fmaf(us[d], W1[d * WF_HIDDEN + j], acc);
-          h[t] = tc_tanh_bundle<D, LAP>(cx, acc);
+        {
+          const float4 ba = *reinterpret_cast<const float4*>(b1 + j0), bb = *reinterpret_cast<const float4*>(b1 + j0 + 4);
+          h[0] = vmask * ba.x; h[1] = vmask * ba.y; h[2] = vmask * ba.z; h[3] = vmask * ba.w;
+          h[4] = vmask * bb.x; h[5] = vmask * bb.y; h[6] = vmask * bb.z; h[7] = vmask * bb.w;
         }
+#pragma unroll
+        for (int d = 0; d < D; ++d) {                   // the same 8 weights for every thread: two broadcast 128-bit loads per input
+          const float4 wa = *reinterpret_cast<const float4*>(W1 + d * WF_HIDDEN + j0);
+          const float4 wb = *reinterpret_cast<const float4*>(W1 + d * WF_HIDDEN + j0 + 4);
+          h[0] = fmaf(us[d], wa.x, h[0]); h[1] = fmaf(us[d], wa.y, h[1]); h[2] = fmaf(us[d], wa.z, h[2]); h[3] = fmaf(us[d], wa.w, h[3]);
+          h[4] = fmaf(us[d], wb.x, h[4]); h[5] = fmaf(us[d], wb.y, h[5]); h[6] = fmaf(us[d], wb.z, h[6]); h[7] = fmaf(us[d], wb.w, h[7]);
+        }
+#pragma unroll
+        for (int t = 0; t < 8; ++t) h[t] = tc_tanh_bundle<D, LAP>(cx, h[t]);
         store_planes8(my_hi, my_lo, (uint32_t)(fbase + c * 8), h);
       }
       tmem_wait_st();
@@ -667,11 +682,10 @@ __global__ void __launch_bounds__(THREADS, 1) live_tc_kernel(const __grid_consta
 #pragma unroll
           for (int t = 0; t < 8; ++t) v[t] = __uint_as_float(nxt[t]);
           if (c + 1 < fw / 8) tmem_ld8_issue(my_acc + (uint32_t)(fbase + (c + 1) * 8), nxt);    // in flight under this chunk's tanh
+          const float4 ba = *reinterpret_cast<const float4*>(b2 + fbase + c * 8), bb = *reinterpret_cast<const float4*>(b2 + fbase + c * 8 + 4);
+          const float b8[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
 #pragma unroll
-          for (int t = 0; t < 8; ++t) {
-            const float acc = cx.is_v ? v[t] + b2[fbase + c * 8 + t] : v[t];
-            h[t] = tc_tanh_bundle<D, LAP>(cx, acc);
-          }
+          for (int t = 0; t < 8; ++t) h[t] = tc_tanh_bundle<D, LAP>(cx, fmaf(vmask, b8[t], v[t]));
           tmem_wait_ld8(nxt);
           store_planes8(my_hi, my_lo, (uint32_t)(fbase + c * 8), h);
         }
