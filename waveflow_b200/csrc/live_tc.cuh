@@ -224,9 +224,17 @@ __device__ __forceinline__ float rcp_ftz(float x) {
   return y;
 }
 __device__ __forceinline__ float tc_sigmoid(float x) { return rcp_ftz(1.f + ex2_ftz(-1.4426950408889634f * x)); }
-__device__ __forceinline__ float tc_tanh(float x) {
-  const float xc = fminf(fmaxf(x, -15.f), 15.f);
-  return fmaf(-2.f, rcp_ftz(ex2_ftz(2.8853900817779268f * xc) + 1.f), 1.f);
+// no clamp needed: ex2 saturates to 0 / inf, rcp(inf) = 0, so the form returns exactly -1 / +1 for large |x|
+__device__ __forceinline__ float tc_tanh(float x) { return fmaf(-2.f, rcp_ftz(ex2_ftz(2.8853900817779268f * x) + 1.f), 1.f); }
+// sum of t over the D gradient lanes of a walker, valid ON THE LAPLACIAN LANE ONLY (the only consumer in the tanh layers).
+// D = 4: a two-step tree over shfl_up plus one hop (3 shuffles, 2 adds) instead of D shuffles and D adds.
+template <int D, bool LAP>
+__device__ __forceinline__ float lap_gsum(const Ctx<D, LAP>& cx, float t) {
+  if constexpr (LAP && D == 4) {
+    const float u = t + __shfl_up_sync(FULL, t, 2);      // lane g4: t4 + t2, lane g3: t3 + t1
+    const float w = u + __shfl_up_sync(FULL, u, 1);      // lane g4: t4 + t2 + t3 + t1
+    return __shfl_up_sync(FULL, w, 1);                   // Laplacian lane = g4 + 1
+  } else return cx.gsum(t);
 }
 // tanh on a 1-register bundle (same algebra as tanh_bundle of live_device.cuh)
 template <int D, bool LAP>
@@ -234,7 +242,7 @@ __device__ __forceinline__ float tc_tanh_bundle(const Ctx<D, LAP>& cx, float a) 
   if constexpr (LAP) {
     const float th = tc_tanh(cx.bv(a));
     const float f1 = 1.f - th * th;
-    const float gg = cx.gsum(a * a);
+    const float gg = lap_gsum<D, LAP>(cx, a * a);
     float r = f1 * a;
     if (cx.is_l) r = fmaf(-2.f * th * f1, gg, r);
     return cx.is_v ? th : r;
@@ -318,7 +326,14 @@ __device__ __forceinline__ void sigmoid_spline_regs(const Ctx<D, LAP>& cx, uint3
       const float ov = q < P ? ovr : -INFINITY;
       const float s = tc_sigmoid(ov);
       const float d1 = s * (1.f - s);
-      const J sq = cx.unary(J{oq, 0.f, ov}, s, d1, d1 * (1.f - 2.f * s));
+      // cx.unary with a zero pending term, written out (the compiler cannot fold f1 * 0)
+      J sq;
+      if constexpr (LAP) {
+        const float dm = d1 * oq;
+        sq.m = cx.is_v ? s : dm;
+        sq.p = cx.is_g ? (1.f - 2.f * s) * dm * oq : 0.f;
+      } else { sq.m = s; sq.p = 0.f; }
+      sq.v = s;
       const float w = wq[q];
       if (PREFIX_ONE) {
         const bool snap = q == lo_w;                   // SW holds the bases 0 .. q - 1 here
