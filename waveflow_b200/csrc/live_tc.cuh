@@ -67,6 +67,26 @@ __device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, u
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
       "}\n" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// The same, executed by a WHOLE (converged) warp with warp-uniform operands: one lane is elected inside.  Issued from a
+// single-lane branch instead, the compiler cannot keep the descriptors in uniform registers and wraps every MMA in an
+// ELECT / R2UR.BROADCAST x4 / BRA.U.ANY loop (~100 cycles per MMA: the 24-MMA groups of this kernel were issue bound).
+__device__ __forceinline__ void umma_tf32_ts_warp(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit_warp(uint64_t* bar) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
+      "}\n" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
@@ -202,9 +222,9 @@ __device__ __forceinline__ void issue_group32(uint32_t d_tmem, uint32_t a_hi, ui
 #pragma unroll 1
   for (int ks = 0; ks < WF_HIDDEN / 8; ++ks) {
     const uint32_t acol = (uint32_t)(ks * 8);
-    umma_tf32_ts(d_tmem, a_hi + acol, dh, idesc, ks != 0 ? 1u : 0u);
-    umma_tf32_ts(d_tmem, a_hi + acol, dl, idesc, 1u);
-    umma_tf32_ts(d_tmem, a_lo + acol, dh, idesc, 1u);
+    umma_tf32_ts_warp(d_tmem, a_hi + acol, dh, idesc, ks != 0 ? 1u : 0u);
+    umma_tf32_ts_warp(d_tmem, a_hi + acol, dl, idesc, 1u);
+    umma_tf32_ts_warp(d_tmem, a_lo + acol, dh, idesc, 1u);
     // next k-step: 32 bytes further inside the 128-byte swizzle span, or the start of the next 32-float k-block
     const uint64_t adv = ((ks & 3) == 3) ? (uint64_t)((N_ROWS * 128 - 96) >> 4) : (uint64_t)(32 >> 4);
     dh += adv; dl += adv;
@@ -546,7 +566,9 @@ __global__ void __launch_bounds__(THREADS, 1) live_tc_kernel(const __grid_consta
   fence_before();
   __syncthreads();
   fence_after();
-  const uint32_t tmem_base = *tmem_ptr;
+  // broadcast from lane 0: tells the compiler these are warp-uniform (the MMA issue below then runs on the uniform datapath)
+  const uint32_t tmem_base = __shfl_sync(FULL, *tmem_ptr, 0);
+  const int warp_u = __shfl_sync(FULL, warp, 0);
   const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
 
   C cx;
@@ -589,8 +611,8 @@ __global__ void __launch_bounds__(THREADS, 1) live_tc_kernel(const __grid_consta
     // finished the previous (DUO) round there -- and slot 1's team must be done with its tile as well
     if (solo && round > 0) __syncthreads();
     const int n_wg = solo ? 4 : 2;
-    const int slot = solo ? 0 : tid / TILE_THREADS;
-    const int wg = solo ? warp >> 2 : (warp >> 2) & 1;   // warpgroup inside the team
+    const int slot = solo ? 0 : warp_u / (TILE_THREADS / 32);
+    const int wg = solo ? warp_u >> 2 : (warp_u >> 2) & 1;   // warpgroup inside the team
     const int team_tid0 = solo ? 0 : slot * TILE_THREADS;
     const int team_threads = solo ? THREADS : TILE_THREADS;
     const bool leader = tid == team_tid0;
@@ -671,11 +693,11 @@ __global__ void __launch_bounds__(THREADS, 1) live_tc_kernel(const __grid_consta
       bar_sync(1 + slot, team_threads);
       // every 32-column group is issued by ONE lane of a different warp: the issue work (24 MMAs per group) is spread
       // instead of serialised in front of one warp's epilogue.  Layer 2: two groups (output units 0..31 / 32..63).
-      if ((warp & 3) == 0 && lane == 0 && (solo ? (wg & 1) == 0 : true)) {
+      if ((warp_u & 3) == 0 && (solo ? (wg & 1) == 0 : true)) {       // a whole warp (warp-uniform branch), one lane elected inside
         const int h = solo ? wg >> 1 : wg;
         fence_after();
         issue_group32<WF_HIDDEN>(dacc + (uint32_t)(h * 32), a_hi, a_lo, w2_s, w2_s + W2_PLANE_BYTES, h * 32);
-        umma_commit(&l2_done[slot * 2 + h]);
+        umma_commit_warp(&l2_done[slot * 2 + h]);
       }
       // the A planes are overwritten below: BOTH halves of layer 2 must have been read by the tensor core
       mbar_wait_guard(&l2_done[slot * 2 + 0], mpar);
@@ -710,12 +732,12 @@ __global__ void __launch_bounds__(THREADS, 1) live_tc_kernel(const __grid_consta
       bar_sync(1 + slot, team_threads);
       {
         // layer 3: one 32-column group per output dimension, issued by warp (d - d_lo) of the warpgroup that owns dimension d
-        const int d_mine = d_lo + (warp & 3);
-        if (lane == 0 && d_mine < d_hi) {
+        const int d_mine = d_lo + (warp_u & 3);
+        if (d_mine < d_hi) {                              // whole warp, one lane elected inside
           fence_after();
           mbar_wait_guard(w3_full, (uint32_t)(g & 1));
           issue_group32<N3>(dacc + (uint32_t)(d_mine * WF_MAX_P), a_hi, a_lo, w3_s, w3_s + w3_plane_bytes(D), d_mine * WF_MAX_P);
-          umma_commit(&l3_done[slot * 4 + d_mine]);
+          umma_commit_warp(&l3_done[slot * 4 + d_mine]);
         }
       }
 
