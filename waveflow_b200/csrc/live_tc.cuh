@@ -213,10 +213,10 @@ __device__ __forceinline__ void mbar_wait_guard(uint64_t* bar, uint32_t parity) 
 //   acc[128 x 32] = A (hi + lo planes in TMEM) x W[rows r0 .. r0 + 31]^T (hi / lo images in shared memory, N_ROWS rows per k-block).
 // The layers are issued in 32-column groups, each committed to its own mbarrier, so that the warpgroup that consumes a group
 // starts its epilogue as soon as THAT group is done instead of waiting for the whole layer.
-template <int N_ROWS>
+template <int N_ROWS, int NCOLS = 32>
 __device__ __forceinline__ void issue_group32(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, const unsigned char* b_hi,
                                               const unsigned char* b_lo, int r0) {
-  constexpr uint32_t idesc = instr_desc_tf32(32);
+  constexpr uint32_t idesc = instr_desc_tf32(NCOLS);
   uint64_t dh = smem_desc_sw128(b_hi + (size_t)r0 * 128), dl = smem_desc_sw128(b_lo + (size_t)r0 * 128);
   // rolled on purpose (code size: the kernel must stay inside the instruction cache); 8 k-steps x 3 MMAs
 #pragma unroll 1
@@ -693,15 +693,17 @@ __global__ void __launch_bounds__(THREADS, 1) live_tc_kernel(const __grid_consta
       bar_sync(1 + slot, team_threads);
       // every 32-column group is issued by ONE lane of a different warp: the issue work (24 MMAs per group) is spread
       // instead of serialised in front of one warp's epilogue.  Layer 2: two groups (output units 0..31 / 32..63).
-      if ((warp_u & 3) == 0 && (solo ? (wg & 1) == 0 : true)) {       // a whole warp (warp-uniform branch), one lane elected inside
-        const int h = solo ? wg >> 1 : wg;
+      // ONE 24-MMA group per layer (N = 64 here), issued by the first warp of the team (whole warp, warp-uniform branch, one lane
+      // elected inside).  A tcgen05.mma of this size costs about the same whatever N <= 128 is, so splitting a layer into
+      // 32- or 16-column groups multiplies the tensor time (measured: 4 x 32 columns 0.926 ms, 8 x 16 columns 0.956 ms per
+      // 65 536 walkers) -- the whole layer in one group is what lets the epilogues start earliest.
+      if (warp_u == (team_tid0 >> 5)) {
         fence_after();
-        issue_group32<WF_HIDDEN>(dacc + (uint32_t)(h * 32), a_hi, a_lo, w2_s, w2_s + W2_PLANE_BYTES, h * 32);
-        umma_commit_warp(&l2_done[slot * 2 + h]);
+        issue_group32<WF_HIDDEN, WF_HIDDEN>(dacc, a_hi, a_lo, w2_s, w2_s + W2_PLANE_BYTES, 0);
+        umma_commit_warp(&l2_done[slot * 2]);
       }
       // the A planes are overwritten below: BOTH halves of layer 2 must have been read by the tensor core
-      mbar_wait_guard(&l2_done[slot * 2 + 0], mpar);
-      mbar_wait_guard(&l2_done[slot * 2 + 1], mpar);
+      mbar_wait_guard(&l2_done[slot * 2], mpar);
       fence_after();
       if (leader) {                                     // the last team to get here refills W2 with the next net
         const int old = atomicAdd(&w_cnt[0], 1);
@@ -732,13 +734,18 @@ __global__ void __launch_bounds__(THREADS, 1) live_tc_kernel(const __grid_consta
       bar_sync(1 + slot, team_threads);
       {
         // layer 3: one 32-column group per output dimension, issued by warp (d - d_lo) of the warpgroup that owns dimension d
-        const int d_mine = d_lo + (warp_u & 3);
-        if (d_mine < d_hi) {                              // whole warp, one lane elected inside
+        if (warp_u == (team_tid0 >> 5)) {                 // layer 3: all D x 32 columns in one group
           fence_after();
           mbar_wait_guard(w3_full, (uint32_t)(g & 1));
-          issue_group32<N3>(dacc + (uint32_t)(d_mine * WF_MAX_P), a_hi, a_lo, w3_s, w3_s + w3_plane_bytes(D), d_mine * WF_MAX_P);
-          umma_commit_warp(&l3_done[slot * 4 + d_mine]);
+          issue_group32<N3, N3>(dacc, a_hi, a_lo, w3_s, w3_s + w3_plane_bytes(D), 0);
+          umma_commit_warp(&l3_done[slot * 4]);
         }
+      }
+      mbar_wait_guard(&l3_done[slot * 4], mpar);
+      fence_after();
+      if (leader) {                                     // W3 is free once the layer-3 groups of ALL teams are done: refill it
+        const int old = atomicAdd(&w_cnt[1], 1);
+        if (old + 1 == cum_teams && g + 1 < g_total) issue_w3(g + 1);
       }
 
       // ------------------------------------------------ layer 3 epilogue: spline glue of this warpgroup's dimensions
@@ -747,8 +754,6 @@ __global__ void __launch_bounds__(THREADS, 1) live_tc_kernel(const __grid_consta
       for (int d = 0; d < D; ++d) ys[d] = 0.f;
 #pragma unroll 1
       for (int d = d_lo; d < d_hi; ++d) {
-        mbar_wait_guard(&l3_done[slot * 4 + d], mpar);
-        fence_after();
         const uint32_t tacc = my_acc + (uint32_t)(d * WF_MAX_P);      // this row's 32 conditioner outputs of dimension d
         const float* b3d = b3 + d * WF_MAX_P;
         float xd = us[0];
@@ -791,12 +796,6 @@ __global__ void __launch_bounds__(THREADS, 1) live_tc_kernel(const __grid_consta
             for (int dd = 0; dd < D; ++dd) lpv[dd] = (d == dd) ? lpd : lpv[dd];
           }
         }
-      }
-      if (leader) {                                     // W3 is free once ALL groups of all teams are done: refill it
-#pragma unroll
-        for (int d = 0; d < D; ++d) mbar_wait_guard(&l3_done[slot * 4 + d], mpar);
-        const int old = atomicAdd(&w_cnt[1], 1);
-        if (old + 1 == cum_teams && g + 1 < g_total) issue_w3(g + 1);
       }
       // ------------------------------------------------ exchange the per-dimension results between the warpgroups of the team
       if (!is_prior) {
