@@ -85,6 +85,47 @@ def test_loss_grad_random_models(cuda, D, coord):
     _compare(_train.unravel(params, g), g_ref)
 
 
+def test_loss_grad_tensor_core_layers(cuda):
+    """Batches of >= 128 x SM-count jet rows run the 64-wide conditioner layers (forward and input adjoints) on tcgen05
+    (csrc/train_tc.cuh, 3xTF32).  3200 walkers = 400 distinct walkers x 8 copies: the batch mean equals the mean over the
+    distinct ones, so the float64 oracle runs on 400 walkers; the same call in 800-walker chunks takes the CUDA-core path."""
+    from waveflow_b200 import _train
+    D = 4
+    m = fx.waveflow_model(D, coord="mean")
+    rng = np.random.default_rng(21)
+    params = fx.random_params(rng, m)
+    p64 = fx.cast_params(params, np.float64)
+    spec = spec_from_live(m)
+    protons = np.zeros((D, 1))
+    x0 = _walkers(rng, 400, D, -6, 6, model=m, params=p64, protons=protons)
+    x = np.tile(x0, (8, 1))
+    assert x.shape[0] * (D + 2) >= 128 * torch.cuda.get_device_properties(cuda).multi_processor_count
+    loss_ref, g_ref = ograd.loss_and_grad(m, p64, x0.astype(np.float64), protons, 0.3)
+    ref = olap.local_energy_bundle(m, p64, x0.astype(np.float64), protons)
+    flat = _train.ravel(fx.cast_params(params, np.float32), cuda)
+    xs = torch.from_numpy(x).to(cuda)
+    sums = torch.zeros(4, dtype=torch.float64, device=cuda)
+    g_tc, out = _train.loss_grad(spec, flat, xs, protons, 0.3, want=("psi", "hpsi", "eloc"), sums=sums)
+    g_cc, out_cc = _train.loss_grad(spec, flat, xs, protons, 0.3, want=("psi", "hpsi", "eloc"), max_chunk=800)
+    assert torch.isfinite(g_tc).all()
+    psi = out["psi"].cpu().numpy()
+    assert np.array_equal(psi[:400], psi[400:800])                      # a row's result does not depend on its tile
+    assert np.abs(psi[:400] - ref["psi"]).max() <= 1e-5 * np.abs(ref["psi"]).max()
+    for key in ("hpsi", "eloc"):
+        e_tc = np.abs(out[key].cpu().numpy()[:400] - ref[key]).max() / np.abs(ref[key]).max()
+        e_cc = np.abs(out_cc[key].cpu().numpy()[:400] - ref[key]).max() / np.abs(ref[key]).max()
+        print(f"{key}: max error / max|ref| tensor-core {e_tc:.2e}, CUDA-core {e_cc:.2e}")
+        # E_loc = H psi / psi: float32 rounding is amplified by 1 / psi at the walkers closest to a node; the 3xTF32 products
+        # (2^-22 per product) may sit a small factor above the CUDA-core path's own rounding there
+        assert e_tc <= (1e-4 if key == "hpsi" else max(1e-4, 4 * e_cc))
+    assert abs(sums.cpu().numpy()[0] / 3200 - loss_ref) <= 1e-4 * max(1.0, abs(loss_ref))
+    w_tc = _compare(_train.unravel(params, g_tc), g_ref)
+    w_cc = _compare(_train.unravel(params, g_cc), g_ref)
+    d = float((g_tc - g_cc).norm() / g_cc.norm())
+    print(f"tensor-core layers: worst block |dg|/|g| vs float64 oracle {w_tc:.2e} (CUDA-core path {w_cc:.2e}), tc vs cc {d:.2e}")
+    assert d <= 1e-3
+
+
 def test_chunked_equals_single_and_sharded(cuda):
     """The call loops over walker chunks sized to the workspace; shards + sum == one call (the multi-GPU reduction)."""
     from waveflow_b200 import _train

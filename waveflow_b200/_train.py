@@ -98,15 +98,18 @@ def loss_grad(spec: _live.LiveSpec, flat: torch.Tensor, x: torch.Tensor, protons
     if N == 0:                                   # empty shard: nothing to launch (a rank may own no walkers)
         return grad, out
     prot = _ffi.host_f32(np.asarray(protons, dtype=np.float32).reshape(-1))
+    need = workspace_floats(spec, N, max_chunk)
     if ws is None:
         ws = _workspace(spec, N, dev, max_chunk)
-    elif ws.numel() < workspace_floats(spec, N, max_chunk) or ws.device != dev or ws.dtype != torch.float32:
+    elif ws.numel() < need or ws.device != dev or ws.dtype != torch.float32:
         raise _ffi.WaveflowB200Error("workspace too small / wrong device or dtype for this batch")
     tabs = _live._tables(spec, dev)
     st = lib.wf_vqmc_loss_grad(C.byref(spec.struct()), C.byref(tabs), ptr(flat), _ffi.np_ptr(prot), int(prot.size), ptr(x), N,
                                float(running_average), ptr(running_average_dev), 1.0 / float(n_total or N),
                                ptr(grad if with_grad else None),
-                               ptr(out.get("psi")), ptr(out.get("hpsi")), ptr(out.get("eloc")), ptr(sums), ptr(ws), ws.numel(),
+                               ptr(out.get("psi")), ptr(out.get("hpsi")), ptr(out.get("eloc")), ptr(sums), ptr(ws), need,   # `need`, not ws.numel():
+                               # the C side sizes its walker chunks from the workspace it is told about, so max_chunk holds
+                               # even when the shared scratch has grown beyond it
                                stream_ptr())
     check(st, "wf_vqmc_loss_grad")
     return grad, out

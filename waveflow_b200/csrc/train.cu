@@ -9,6 +9,7 @@
 //   backward: the same chain in reverse; table derivatives are the next table, order 4 clamps to 3.
 #include <math.h>
 #include "train_jets.cuh"
+#include "train_tc.cuh"
 
 using namespace wf;
 using namespace wf::train;
@@ -798,14 +799,16 @@ int check_model(const wf_live_model* m) {
 
 constexpr int WGRAD_CTAS = 296;
 
-struct Fixed { int64_t wm, fold, partial, total; };
+struct Fixed { int64_t wm, fold, partial, img, total; };
+constexpr int64_t IMG_NET = 2 * ttc::img_floats(1, 64) + ttc::img_floats(1, 128) + ttc::img_floats(2, 64);   // W2, W2^T, W3, W3^T
 Fixed fixed_floats(const wf_live_model* m) {
   Fixed f;
   f.wm = 0;
   for (int i = 0; i < n_nets_of(m); ++i) f.wm += (int64_t)m->D * HID + HID * HID + (int64_t)HID * m->D * net_P(m, i);
   f.fold = 2 * (int64_t)(HID + 1) * ((prior_cols(m) + 3) & ~3);       // folded prior layer (Wf | bf) and its gradient (gWf | gbf)
   f.partial = (int64_t)WGRAD_CTAS * (HID + 1) * MAX_W;
-  f.total = f.wm + f.fold + f.partial;
+  f.img = IMG_NET * n_nets_of(m);                                     // tensor-core operand images of the layer-2 / 3 weights
+  f.total = f.wm + f.fold + f.partial + f.img;
   return f;
 }
 int64_t per_row_floats(const wf_live_model* m) {
@@ -866,6 +869,15 @@ int launch_wgrad_bn(const float* X, const float* dY, float* partial, int grid, i
 
 int launch_wgrad(const float* X, const float* dY, float* partial, float* gW, float* gb, int layer, int D, int64_t R, int Kc, int Nc,
                  int G, cudaStream_t s) {
+  if (ttc::wgrad_tc_ok(R, Kc, Nc)) {             // 64-wide inputs of large batches: tensor cores (train_tc.cuh)
+    int n_cta = 0;
+    const int st = ttc::launch_wgrad_tc(X, dY, partial, R, Nc, G, WGRAD_CTAS, &n_cta, s);
+    if (st != WF_OK) return st;
+    const int tot = (Kc + 1) * Nc;
+    wgrad_reduce_kernel<<<(tot + 31) / 32, 256, 0, s>>>(partial, n_cta, gW, gb, layer, D, Kc, Nc);
+    WF_LAUNCH_CHECK();
+    return WF_OK;
+  }
   const bool small = (R + 127) / 128 < (int64_t)num_sms();
   const int wrows = small ? 16 : 32;
   const int64_t tiles = (R + 4 * wrows - 1) / (4 * wrows);
@@ -907,7 +919,8 @@ int run_chunk(const wf_live_model* m, const wf_live_tables* t, const float* para
   float* gWf = bf + NcFp;                        // gradient of the folded layer, same shapes
   float* gbf = gWf + (int64_t)HID * NcFp;
   float* partial = Wm + fx.wm + fx.fold;
-  float* p = partial + fx.partial;
+  float* img = partial + fx.partial;
+  float* p = img + fx.img;
   auto take = [&](int64_t n) { float* q = p; p += (n + 3) & ~(int64_t)3; return q; };   // keeps every array 16-byte aligned
   float* U[WF_MAX_LAYERS + 2];
   for (int i = 0; i <= nn; ++i) U[i] = take(R * D);
@@ -945,6 +958,38 @@ int run_chunk(const wf_live_model* m, const wf_live_tables* t, const float* para
     fold_prior_kernel<<<((HID + 1) * NcF + 127) / 128, 128, 0, s>>>(W3m[nn - 1], params + off[nn - 1].b3, t->ob_to_b, D, m->P_P, Wf, bf);
     WF_LAUNCH_CHECK();
   }
+  // tensor-core operand images (train_tc.cuh) of the layer-2 / 3 weights and their transposes, once per call
+  const bool tc = ttc::lin_tc_ok(R, HID, HID);
+  float *iW2f[WF_MAX_LAYERS + 1], *iW2b[WF_MAX_LAYERS + 1], *iW3f[WF_MAX_LAYERS + 1], *iW3b[WF_MAX_LAYERS + 1];
+  if (tc) {
+    ttc::PackJobs pj;
+    int nj = 0;
+    auto job = [&](const float* src, float* dst, int Kc, int Nc, int trans) {
+      pj.src[nj] = src; pj.dst[nj] = dst; pj.Kc[nj] = Kc; pj.Nc[nj] = Nc; pj.KP[nj] = ttc::lin_kp(Kc); pj.NT[nj] = ttc::lin_nt(Nc);
+      pj.trans[nj] = trans; ++nj;
+    };
+    for (int i = 0; i < nn; ++i) {
+      float* b = img + IMG_NET * i;
+      iW2f[i] = b; iW2b[i] = b + ttc::img_floats(1, 64); iW3f[i] = iW2b[i] + ttc::img_floats(1, 64); iW3b[i] = iW3f[i] + ttc::img_floats(1, 128);
+      const float* W3 = i < L ? W3m[i] : Wf;
+      const int N3 = i < L ? D * net_P(m, i) : NcF;
+      job(W2m[i], iW2f[i], HID, HID, 0);
+      job(W2m[i], iW2b[i], HID, HID, 1);
+      if (ttc::lin_tc_ok(R, HID, N3)) job(W3, iW3f[i], HID, N3, 0);
+      if (ttc::lin_tc_ok(R, N3, HID)) job(W3, iW3b[i], N3, HID, 1);
+    }
+    ttc::pack_b_kernel<<<dim3(8, nj), 256, 0, s>>>(pj);
+    WF_LAUNCH_CHECK();
+  }
+  // C = A B (+ bias): tensor cores for the 64-wide layers of large batches, linear_kernel otherwise
+  auto lin_fwd = [&](const float* A, const float* B, const float* im, const float* bias, float* C, int Kc, int Nc) {
+    if (tc && ttc::lin_tc_ok(R, Kc, Nc)) return ttc::launch_lin_tc(A, im, bias, C, R, Kc, Nc, G, s);
+    return launch_linear<false, false>(A, B, bias, C, R, Kc, Nc, G, s);
+  };
+  auto lin_bwd = [&](const float* A, const float* B, const float* im, float* C, int Kc, int Nc) {
+    if (tc && ttc::lin_tc_ok(R, Kc, Nc)) return ttc::launch_lin_tc(A, im, nullptr, C, R, Kc, Nc, G, s);
+    return launch_linear<true, false>(A, B, nullptr, C, R, Kc, Nc, G, s);
+  };
 
   HeadArgs ha;
   ha.tab = t->dense_I; ha.N = N; ha.P = m->P_I; ha.T = m->T; ha.reg = m->reg;
@@ -966,10 +1011,10 @@ int run_chunk(const wf_live_model* m, const wf_live_tables* t, const float* para
     int st;
     if ((st = launch_linear<false, false>(U[i], W1m[i], params + off[i].b1, Z1[i], R, D, HID, G, s)) != WF_OK) return st;
     tanh_fwd_kernel<D><<<(int)((nh + eb - 1) / eb), eb, 0, s>>>(Z1[i], H1[i], N);
-    if ((st = launch_linear<false, false>(H1[i], W2m[i], params + off[i].b2, Z2[i], R, HID, HID, G, s)) != WF_OK) return st;
+    if ((st = lin_fwd(H1[i], W2m[i], iW2f[i], params + off[i].b2, Z2[i], HID, HID)) != WF_OK) return st;
     tanh_fwd_kernel<D><<<(int)((nh + eb - 1) / eb), eb, 0, s>>>(Z2[i], H2[i], N);
-    if (i < L) st = launch_linear<false, false>(H2[i], W3m[i], params + off[i].b3, O[i], R, HID, DP, G, s);
-    else st = launch_linear<false, false>(H2[i], Wf, bf, O[i], R, HID, NcF, G, s);          // folded prior layer
+    if (i < L) st = lin_fwd(H2[i], W3m[i], iW3f[i], params + off[i].b3, O[i], HID, DP);
+    else st = lin_fwd(H2[i], Wf, iW3f[i], bf, O[i], HID, NcF);                              // folded prior layer
     if (st != WF_OK) return st;
     if (i < L) {
       ha.O = O[i]; ha.U = U[i];
@@ -1010,14 +1055,14 @@ int run_chunk(const wf_live_model* m, const wf_live_tables* t, const float* para
       if ((st = launch_wgrad(H2[i], Obar, partial, gWf, gbf, 0, D, R, HID, NcF, G, s)) != WF_OK) return st;
       unfold_prior_grad_kernel<<<((HID + 1) * DP + 127) / 128, 128, 0, s>>>(gWf, gbf, t->ob_to_b, D, P, grad + off[i].W3, grad + off[i].b3);
       WF_LAUNCH_CHECK();
-      if ((st = launch_linear<true, false>(Obar, Wf, nullptr, HbA, R, NcF, HID, G, s)) != WF_OK) return st;
+      if ((st = lin_bwd(Obar, Wf, iW3b[i], HbA, NcF, HID)) != WF_OK) return st;
     } else {
       if ((st = launch_wgrad(H2[i], Obar, partial, grad + off[i].W3, grad + off[i].b3, 3, D, R, HID, DP, G, s)) != WF_OK) return st;
-      if ((st = launch_linear<true, false>(Obar, W3m[i], nullptr, HbA, R, DP, HID, G, s)) != WF_OK) return st;
+      if ((st = lin_bwd(Obar, W3m[i], iW3b[i], HbA, DP, HID)) != WF_OK) return st;
     }
     tanh_bwd_kernel<D><<<(int)((nh + eb - 1) / eb), eb, 0, s>>>(Z2[i], HbA, N);
     if ((st = launch_wgrad(H1[i], HbA, partial, grad + off[i].W2, grad + off[i].b2, 2, D, R, HID, HID, G, s)) != WF_OK) return st;
-    if ((st = launch_linear<true, false>(HbA, W2m[i], nullptr, HbB, R, HID, HID, G, s)) != WF_OK) return st;
+    if ((st = lin_bwd(HbA, W2m[i], iW2b[i], HbB, HID, HID)) != WF_OK) return st;
     tanh_bwd_kernel<D><<<(int)((nh + eb - 1) / eb), eb, 0, s>>>(Z1[i], HbB, N);
     if ((st = launch_wgrad(U[i], HbB, partial, grad + off[i].W1, grad + off[i].b1, 1, D, R, D, HID, G, s)) != WF_OK) return st;
     if (i > 0 && (st = launch_linear<true, true>(HbB, W1m[i], nullptr, Ucur, R, HID, D, G, s)) != WF_OK) return st;
