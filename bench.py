@@ -803,7 +803,9 @@ def run_b200(args):
         ms = train_ms
         tfl = 3.0 * flops_per_walker(D) * int(x_train.shape[0]) / (ms * 1e-3) / 1e12          # forward + ~2x for the reverse pass
         train = {"api": "vqmc.train_step_efficient(epoch, psi, h_fn, opt_update, opt_state, params, batch, running_average)",
-                 "kernels": "wf_vqmc_loss_grad (layer-wise jets: linear / tanh / spline-head kernels, forward + reverse) + wf_adam_step",
+                 "kernels": "wf_vqmc_loss_grad (layer-wise jets; the 64-wide conditioner layers, their input adjoints and all weight gradients on "
+                            "tcgen05 3xTF32 -- csrc/train_tc.cuh: lin_tc_kernel, wgrad_tc_kernel; tanh / spline-head kernels on CUDA cores; "
+                            "forward + reverse) + wf_adam_step",
                  "walkers_total": n_train, "walkers_per_gpu": int(x_train.shape[0]), "ms_per_step": ms,
                  "walkers_per_s": n_train / (ms * 1e-3), "loss_after_13_steps": train_loss, "cross_n_checksum": train_check,
                  "walker_set": "the workload's 65536 walkers filtered to |psi| > 1e-4 max|psi| (identical on every rank and for every N)",
@@ -812,7 +814,7 @@ def run_b200(args):
                      ("one peer-memory kernel (wf_p2p_allreduce_vec) inside the CUDA graph of the step" if gx is not None
                       else "two NCCL all-reduces between eagerly launched kernels")),
                  "algorithmic_tflops_per_gpu": tfl, "frac_of_measured_fp32_fma": tfl / fp32_peak,
-                 "gpu_launches_per_step": 76 * ((int(x_train.shape[0]) + 65535) // 65536) + 1}
+                 "gpu_launches_per_step": 77 * ((int(x_train.shape[0]) + 65535) // 65536) + 1}
         if world == 1:
             # the reference's own training configuration (BASELINE configs[1]): He, batch 256 -- launch-bound, CUDA-graph replay
             from waveflow_b200 import _train

@@ -200,6 +200,46 @@ __global__ void __launch_bounds__(LIN_THREADS) linear_kernel(const float* __rest
   }
 }
 
+// C[R][NOUT] += A[R][64] * W^T, W given as [NOUT][64] (the input adjoint of the first layer: NOUT = D).  HBM bound on A:
+// 16 lanes per row, each one 16-byte unit of the row against the matching weight columns, then a butterfly over the 16 lanes.
+template <int NOUT>
+__global__ void __launch_bounds__(256) dgrad_narrow_kernel(const float* __restrict__ A, const float* __restrict__ W, float* __restrict__ C,
+                                                           int64_t R) {
+  __shared__ float4 Ws[NOUT][16];
+  if (threadIdx.x < NOUT * 16) Ws[threadIdx.x / 16][threadIdx.x % 16] = reinterpret_cast<const float4*>(W)[threadIdx.x];
+  __syncthreads();
+  const int c = threadIdx.x & 15;
+  const int64_t rows_per_pass = (int64_t)gridDim.x * 16;
+  for (int64_t row0 = (int64_t)blockIdx.x * 16; row0 < R; row0 += rows_per_pass) {       // uniform trip count per CTA
+    const int64_t row = row0 + (threadIdx.x >> 4);
+    const bool ok = row < R;
+    const float4 a = ok ? __ldg(reinterpret_cast<const float4*>(A + row * HID) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float p[NOUT];
+#pragma unroll
+    for (int o = 0; o < NOUT; ++o) {
+      const float4 w = Ws[o][c];
+      p[o] = fmaf(a.x, w.x, fmaf(a.y, w.y, fmaf(a.z, w.z, a.w * w.w)));
+    }
+#pragma unroll
+    for (int m = 8; m >= 1; m >>= 1)
+#pragma unroll
+      for (int o = 0; o < NOUT; ++o) p[o] += __shfl_xor_sync(0xffffffffu, p[o], m);
+    if (ok && c == 0) {
+#pragma unroll
+      for (int o = 0; o < NOUT; ++o) C[row * NOUT + o] += p[o];
+    }
+  }
+}
+int launch_dgrad_narrow(const float* A, const float* W, float* C, int64_t R, int nout, cudaStream_t s) {
+  const int64_t want = (R + 15) / 16;
+  const int grid = (int)(want < 8 * (int64_t)num_sms() ? want : 8 * (int64_t)num_sms());
+  if (nout == 2) dgrad_narrow_kernel<2><<<grid, 256, 0, s>>>(A, W, C, R);
+  else if (nout == 3) dgrad_narrow_kernel<3><<<grid, 256, 0, s>>>(A, W, C, R);
+  else dgrad_narrow_kernel<4><<<grid, 256, 0, s>>>(A, W, C, R);
+  WF_LAUNCH_CHECK();
+  return WF_OK;
+}
+
 // partial[cta][Kc + 1][Nc] = sum over the CTA's rows of X[r][k] * dY[r][n]; row Kc = sum over the value rows (bias gradient).
 // Each slice accumulates an 8 (k) x 8 (n) block per thread over its own 16-row chunks; the slices are summed through
 // shared memory in a fixed order at the end.
@@ -871,7 +911,7 @@ int launch_wgrad(const float* X, const float* dY, float* partial, float* gW, flo
                  int G, cudaStream_t s) {
   if (ttc::wgrad_tc_ok(R, Kc, Nc)) {             // 64-wide inputs of large batches: tensor cores (train_tc.cuh)
     int n_cta = 0;
-    const int st = ttc::launch_wgrad_tc(X, dY, partial, R, Nc, G, WGRAD_CTAS, &n_cta, s);
+    const int st = ttc::launch_wgrad_tc(X, dY, partial, R, Kc, Nc, G, WGRAD_CTAS, &n_cta, s);
     if (st != WF_OK) return st;
     const int tot = (Kc + 1) * Nc;
     wgrad_reduce_kernel<<<(tot + 31) / 32, 256, 0, s>>>(partial, n_cta, gW, gb, layer, D, Kc, Nc);
@@ -1065,7 +1105,7 @@ int run_chunk(const wf_live_model* m, const wf_live_tables* t, const float* para
     if ((st = lin_bwd(HbA, W2m[i], iW2b[i], HbB, HID, HID)) != WF_OK) return st;
     tanh_bwd_kernel<D><<<(int)((nh + eb - 1) / eb), eb, 0, s>>>(Z1[i], HbB, N);
     if ((st = launch_wgrad(U[i], HbB, partial, grad + off[i].W1, grad + off[i].b1, 1, D, R, D, HID, G, s)) != WF_OK) return st;
-    if (i > 0 && (st = launch_linear<true, true>(HbB, W1m[i], nullptr, Ucur, R, HID, D, G, s)) != WF_OK) return st;
+    if (i > 0 && (st = launch_dgrad_narrow(HbB, W1m[i], Ucur, R, D, s)) != WF_OK) return st;
     WF_LAUNCH_CHECK();
     cur ^= 1;
   }

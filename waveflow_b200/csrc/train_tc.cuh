@@ -44,6 +44,25 @@ __device__ __forceinline__ void umma_tf32_ss_warp(uint32_t d_tmem, uint64_t a_de
       "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
       "}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// round-to-nearest (ties away) to TF32 on the integer pipe: cvt.rna.tf32.f32 issues on the quarter-rate XU pipe, and the operand
+// staging of these kernels converts every element once
+__device__ __forceinline__ float tf32_rna_i(float a) { return __uint_as_float((__float_as_uint(a) + 0x1000u) & 0xFFFFE000u); }
+// mbarrier wait for the warp-specialised pipelines below: a failed try_wait backs off with nanosleep, so that the roles that
+// are ahead (producer, MMA issuer, the faster team) do not flood the shared-memory pipe with SYNCS polls while the others work
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
+  uint32_t done = 0;
+  for (uint32_t spin = 0; ; ++spin) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    if (done) break;
+    __nanosleep(40);
+    if (spin > (1u << 24)) __trap();
+  }
+}
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // ---------------------------------------------------------------------------------------------- weight images
@@ -64,7 +83,7 @@ __global__ void pack_b_kernel(const __grid_constant__ PackJobs jobs) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int n = trans ? i / (KP * 64) : i % NT, k = trans ? i % (KP * 64) : i / NT;      // coalesced on the source side
     const float v = (n < Nc && k < Kc) ? (trans ? B[(int64_t)n * Kc + k] : B[(int64_t)k * Nc + n]) : 0.f;
-    const float hi = tf32_rn(v), lo = v - hi;
+    const float hi = tf32_rn(v), lo = tf32_rn(v - hi);
     const int kp = k >> 6, kl = k & 63, kb = kl >> 5, kk = kl & 31;
     const int plane = NT * 64;                                                             // floats per plane
     const int off = kp * 2 * plane + kb * NT * 32 + n * 32 + ((((kk >> 2) ^ (n & 7)) << 2) | (kk & 3));
@@ -135,7 +154,7 @@ lin_tc_kernel(const float* __restrict__ A, const float* __restrict__ Bimg, const
         const int u = ttid + TEAM * j, row = u >> 4, c = u & 15;
         const float4 v = raw[j];
         float4 hi, lo;
-        hi.x = tf32_rna(v.x); hi.y = tf32_rna(v.y); hi.z = tf32_rna(v.z); hi.w = tf32_rna(v.w);
+        hi.x = tf32_rna_i(v.x); hi.y = tf32_rna_i(v.y); hi.z = tf32_rna_i(v.z); hi.w = tf32_rna_i(v.w);
         lo.x = v.x - hi.x; lo.y = v.y - hi.y; lo.z = v.z - hi.z; lo.w = v.w - hi.w;
         const int off = (c >> 3) * (128 * 128) + row * 128 + (((c & 7) ^ (row & 7)) << 4);
         *reinterpret_cast<float4*>(As + off) = hi;
@@ -168,7 +187,7 @@ lin_tc_kernel(const float* __restrict__ A, const float* __restrict__ Bimg, const
       fence_after();
     }
     // ---- epilogue: accumulator rows -> (+ bias on value rows) -> staging -> coalesced stores
-    const float vmask = ((r0 + ttid) % G) == 0 ? 1.f : 0.f;
+    const float vmask = (((uint32_t)(r0 % G) + (uint32_t)ttid) % (uint32_t)G) == 0 ? 1.f : 0.f;
 #pragma unroll 1
     for (int h = 0; h < HALVES; ++h) {
 #pragma unroll
@@ -232,45 +251,52 @@ inline int launch_lin_tc(const float* A, const float* img, const float* bias, fl
 }
 
 // ---------------------------------------------------------------------------------------------- dW = X^T dY (+ bias gradient)
-//   wgrad_tc_kernel:  partial[cta][k][n] = sum over the CTA's rows of X[r][k] dY[r][n]  (k < 64),
-//                     partial[cta][64][n] = sum over its value rows (r % G == 0) of dY[r][n]
+//   wgrad_tc_kernel:  partial[cta][k][n] = sum over the CTA's rows of X[r][k] dY[r][n]  (k < Kc, Kc = 64 or a multiple of 4 below),
+//                     partial[cta][Kc][n] = sum over its value rows (r % G == 0) of dY[r][n]
 // The reduction runs over ROWS, so both MMA operands have to be row-contiguous ("K-major" with K = rows) while the arrays
 // in HBM are feature-contiguous.  The transposition costs nothing extra:
-//   * a producer thread streams 64-row sub-tiles of X and dY, as they lie in HBM, into a 3-stage shared-memory ring
-//     (two cp.async.bulk per sub-tile, 46 KB, up to 138 KB in flight per SM);
-//   * "A team" (4 warps, thread n owns output column n = TMEM lane n) reads COLUMN n of the dY sub-tile (consecutive
+//   * a producer thread streams 32-row sub-tiles of X and dY, as they lie in HBM, into a shared-memory ring of up to 8
+//     stages (two cp.async.bulk per sub-tile; ~160 KB in flight per SM -- with 3 stages of 64 rows the kernel was bound by
+//     the round trip of the ring, not by HBM);
+//   * "A team" (8 warps, thread n owns output column n = TMEM lane n, two warps per lane quarter) reads COLUMN n of the dY sub-tile (consecutive
 //     lanes -> consecutive floats: no bank conflicts), splits it into TF32 hi / lo planes and writes them with
 //     tcgen05.st into tensor memory: the A operand of the .ts MMA form (lane = M index, one column per row r);
 //   * "B team" (4 warps, thread (k, half)) reads column k of the X sub-tile and writes row k of the K-major
 //     SWIZZLE_128B image (the XOR swizzle makes the row-per-lane 128-bit stores conflict free); image row 64 is the
 //     value-row indicator, so the bias gradient falls out of the same MMAs as output column 64;
-//   * one warp issues 2 x 4 x 3 tcgen05.mma (M = 128, N = 80, K = 8, 3xTF32) per sub-tile into ONE accumulator
-//     D[n][k] (80 TMEM columns) that lives across all sub-tiles of the CTA; operands are double buffered and handed
+//   * one warp issues 4 x 3 tcgen05.mma (M = 128, N = 80, K = 8, 3xTF32) per sub-tile into ONE accumulator
+//     D[n][k] (80 TMEM columns) that lives across all sub-tiles of the CTA; operands are triple buffered and handed
 //     over with mbarriers (tcgen05.commit frees a stage), so loads, transposition and MMAs of neighbouring sub-tiles overlap.
 // The per-CTA partial sums are then added in a fixed order by wgrad_reduce_kernel: deterministic gradients.
-constexpr int WG_ROWS = 64, WG_STAGES = 3, WG_NB = 80;
-constexpr int WG_X_BYTES = WG_ROWS * 64 * 4, WG_Y_BYTES = WG_ROWS * 128 * 4, WG_RAW = WG_X_BYTES + WG_Y_BYTES;
-constexpr int WG_BPLANE = 2 * WG_NB * 128, WG_BSTAGE = 2 * WG_BPLANE;
-constexpr int WG_SMEM = 1024 + WG_STAGES * WG_RAW + 2 * WG_BSTAGE + 256;
-constexpr int WG_THREADS = 320;
+constexpr int WG_ROWS = 32;                     // rows per sub-tile = one 32-float k-block
+constexpr int WG_MAX_STAGES = 8;                // raw ring (as many as fit: 7 at Kc = 64, Nc = 116)
+constexpr int WG_OPS = 3;                       // operand stages (A planes in TMEM, B image in shared memory)
+constexpr int WG_NB = 80;                       // image rows: 64 input features + value-row indicator, padded to N % 16 == 0
+constexpr int WG_BPLANE = WG_NB * 128, WG_BSTAGE = 2 * WG_BPLANE;
+constexpr int WG_SMEM = 227 * 1024;
+constexpr int WG_RING = WG_SMEM - 1024 - WG_OPS * WG_BSTAGE - 512;
+constexpr int WG_THREADS = 448;              // 8 A-team warps, 4 B-team warps, producer, MMA issuer
+__host__ __device__ inline int wg_stage_bytes(int Kc, int Nc) { return (WG_ROWS * (Kc + Nc) * 4 + 127) & ~127; }
 
 __global__ void __launch_bounds__(WG_THREADS, 1)
-wgrad_tc_kernel(const float* __restrict__ X, const float* __restrict__ dY, float* __restrict__ partial, int64_t R, int Nc, int G) {
+wgrad_tc_kernel(const float* __restrict__ X, const float* __restrict__ dY, float* __restrict__ partial, int64_t R, int Kc, int Nc, int G) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* sm = smem_raw + ((1024 - (smem_u32(smem_raw) & 1023)) & 1023);
-  unsigned char* Bimg = sm;                                        // [2 stages][hi | lo][2 k-blocks][80 rows][128 B]
-  unsigned char* raw = sm + 2 * WG_BSTAGE;                         // [3 stages][X 16 KB | dY 32 KB]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(raw + WG_STAGES * WG_RAW);
-  uint64_t *raw_full = bars, *raw_empty = bars + 3, *ops_full = bars + 6, *ops_empty = bars + 8, *done = bars + 10;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  unsigned char* Bimg = sm;                                        // [WG_OPS][hi | lo][80 rows][128 B]
+  unsigned char* raw = sm + WG_OPS * WG_BSTAGE;                    // [S][X rows | dY rows]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(raw + WG_RING);
+  uint64_t *raw_full = bars, *raw_empty = bars + 8, *ops_full = bars + 16, *ops_empty = bars + 20, *done = bars + 24;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 26);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int stage_bytes = wg_stage_bytes(Kc, Nc), x_bytes = WG_ROWS * Kc * 4;
+  const int S = min(WG_MAX_STAGES, WG_RING / stage_bytes);
 
-  for (int i = tid; i < 2 * WG_BSTAGE / 16; i += WG_THREADS) reinterpret_cast<float4*>(Bimg)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = tid; i < WG_OPS * WG_BSTAGE / 16; i += WG_THREADS) reinterpret_cast<float4*>(Bimg)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   fence_proxy_async_smem();
   if (warp == 0) tmem_alloc(tmem_slot, 512);
   if (tid == 0) {
-    for (int i = 0; i < 3; ++i) { mbar_init(&raw_full[i], 1); mbar_init(&raw_empty[i], 8); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&ops_full[i], 8); mbar_init(&ops_empty[i], 1); }
+    for (int i = 0; i < WG_MAX_STAGES; ++i) { mbar_init(&raw_full[i], 1); mbar_init(&raw_empty[i], 12); }
+    for (int i = 0; i < WG_OPS; ++i) { mbar_init(&ops_full[i], 12); mbar_init(&ops_empty[i], 1); }
     mbar_init(done, 1);
     mbar_fence_init();
   }
@@ -278,126 +304,149 @@ wgrad_tc_kernel(const float* __restrict__ X, const float* __restrict__ dY, float
   __syncthreads();
   fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t d_tmem = tmem_base + 256;
+  const uint32_t d_tmem = tmem_base + 256;                         // accumulator D[n][k]: 80 columns
   const int64_t n_sub = (R + WG_ROWS - 1) / WG_ROWS;
   const int n_it = (int)((n_sub - blockIdx.x + gridDim.x - 1) / gridDim.x);        // sub-tiles of this CTA (>= 1)
 
-  if (warp == 8) {
-    // ---- producer
+  if (warp == 12) {
+    // ---- producer: two bulk copies per sub-tile, S sub-tiles in flight
     if (lane == 0) {
+      int s = 0; uint32_t ph = 0;
       for (int it = 0; it < n_it; ++it) {
-        const int s = it % WG_STAGES;
         const int64_t sub = blockIdx.x + (int64_t)it * gridDim.x;
         const int rows = (int)min((int64_t)WG_ROWS, R - sub * WG_ROWS);
-        if (it >= WG_STAGES) mbar_wait_guard(&raw_empty[s], (uint32_t)((it / WG_STAGES - 1) & 1));
-        const uint32_t bx = (uint32_t)rows * 256u, by = (uint32_t)rows * (uint32_t)Nc * 4u;
+        if (it >= S) mbar_wait_backoff(&raw_empty[s], ph ^ 1);
+        const uint32_t bx = (uint32_t)rows * (uint32_t)Kc * 4u, by = (uint32_t)rows * (uint32_t)Nc * 4u;
         mbar_expect_tx(&raw_full[s], bx + by);
-        bulk_g2s(raw + s * WG_RAW, X + sub * WG_ROWS * 64, bx, &raw_full[s]);
-        bulk_g2s(raw + s * WG_RAW + WG_X_BYTES, dY + sub * WG_ROWS * Nc, by, &raw_full[s]);
+        bulk_g2s(raw + s * stage_bytes, X + sub * WG_ROWS * Kc, bx, &raw_full[s]);
+        bulk_g2s(raw + s * stage_bytes + x_bytes, dY + sub * WG_ROWS * Nc, by, &raw_full[s]);
+        if (++s == S) { s = 0; ph ^= 1; }
       }
     }
-  } else if (warp == 9) {
-    // ---- MMA issue
+  } else if (warp == 13) {
+    // ---- MMA issue: 4 k-steps x 3 per sub-tile into the CTA-lifetime accumulator
     constexpr uint32_t idesc = instr_desc_tf32(WG_NB);
+    int st = 0; uint32_t ph = 0;
     for (int it = 0; it < n_it; ++it) {
-      const int st = it & 1;
-      mbar_wait_guard(&ops_full[st], (uint32_t)((it >> 1) & 1));
+      mbar_wait_backoff(&ops_full[st], ph);
       fence_after();
-      const uint32_t a_hi = tmem_base + (uint32_t)(st * 128), a_lo = a_hi + 64;
+      const uint32_t a_hi = tmem_base + (uint32_t)(st * 64), a_lo = a_hi + 32;
       uint64_t bh = smem_desc_sw128(Bimg + st * WG_BSTAGE), bl = smem_desc_sw128(Bimg + st * WG_BSTAGE + WG_BPLANE);
-#pragma unroll 1
-      for (int ks = 0; ks < 8; ++ks) {
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
         const uint32_t acol = (uint32_t)(ks * 8);
         umma_tf32_ts_warp(d_tmem, a_hi + acol, bh, idesc, (it | ks) != 0 ? 1u : 0u);
         umma_tf32_ts_warp(d_tmem, a_hi + acol, bl, idesc, 1u);
         umma_tf32_ts_warp(d_tmem, a_lo + acol, bh, idesc, 1u);
-        const uint64_t adv = (ks & 3) == 3 ? (uint64_t)((WG_NB * 128 - 96) >> 4) : 2ull;
-        bh += adv; bl += adv;
+        bh += 2; bl += 2;                                          // 32 bytes further inside the 128-byte swizzle span
       }
       umma_commit_warp(&ops_empty[st]);
+      if (++st == WG_OPS) { st = 0; ph ^= 1; }
     }
     umma_commit_warp(done);
-  } else if (warp < 4) {
-    // ---- A team: column n of dY -> tensor memory (hi | lo), lane n
-    const int n = tid;
-    const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
+  } else if (warp < 8) {
+    // ---- A team: column n of dY -> tensor memory (hi | lo), lane n.  Two warps per lane quarter (rows 0..15 / 16..31 of the
+    // sub-tile): with one warp per scheduler the dependent cvt / sub chains were the bottleneck of the whole kernel.
+    const int q = warp & 3, c = warp >> 2, n = 32 * q + lane;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
     const bool live = n < Nc;
+    int s = 0, st = 0; uint32_t ph = 0, pho = 0;
     for (int it = 0; it < n_it; ++it) {
-      const int s = it % WG_STAGES, st = it & 1;
       const int64_t sub = blockIdx.x + (int64_t)it * gridDim.x;
       const int rows = (int)min((int64_t)WG_ROWS, R - sub * WG_ROWS);
-      mbar_wait_guard(&raw_full[s], (uint32_t)((it / WG_STAGES) & 1));
-      if (it >= 2) { mbar_wait_guard(&ops_empty[st], (uint32_t)(((it >> 1) - 1) & 1)); fence_after(); }
-      const float* y = reinterpret_cast<const float*>(raw + s * WG_RAW + WG_X_BYTES) + (live ? n : 0);
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t hi[16], lo[16];
+      mbar_wait_backoff(&raw_full[s], ph);
+      if (it >= WG_OPS) { mbar_wait_backoff(&ops_empty[st], pho ^ 1); fence_after(); }
+      const float* y = reinterpret_cast<const float*>(raw + s * stage_bytes + x_bytes) + (live ? n : 0) + 16 * c * Nc;
+      uint32_t hi[16], lo[16];
+      if (live && rows == WG_ROWS) {
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          const int r = 16 * c + j;
-          const float v = (live && r < rows) ? y[r * Nc] : 0.f;
-          const float h = tf32_rna(v);
+          const float v = y[j * Nc];
+          const float h = tf32_rna_i(v);
           hi[j] = __float_as_uint(h);
           lo[j] = __float_as_uint(v - h);
         }
-        tmem_st16(lane_addr + (uint32_t)(st * 128 + 16 * c), hi);
-        tmem_st16(lane_addr + (uint32_t)(st * 128 + 64 + 16 * c), lo);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float v = (live && 16 * c + j < rows) ? y[j * Nc] : 0.f;
+          const float h = tf32_rna_i(v);
+          hi[j] = __float_as_uint(h);
+          lo[j] = __float_as_uint(v - h);
+        }
       }
+      tmem_st16(lane_addr + (uint32_t)(st * 64 + 16 * c), hi);
+      tmem_st16(lane_addr + (uint32_t)(st * 64 + 32 + 16 * c), lo);
       tmem_wait_st();
       fence_before();
       __syncwarp();
       if (lane == 0) { mbar_arrive(&ops_full[st]); mbar_arrive(&raw_empty[s]); }
+      if (++s == S) { s = 0; ph ^= 1; }
+      if (++st == WG_OPS) { st = 0; pho ^= 1; }
     }
+    if (c == 0) {
     // ---- accumulator -> partial[cta][k][n]
-    mbar_wait_guard(done, 0);
+    mbar_wait_backoff(done, 0);
     fence_after();
-    float* out = partial + (int64_t)blockIdx.x * 65 * Nc;
+    float* out = partial + (int64_t)blockIdx.x * (Kc + 1) * Nc;
 #pragma unroll 1
-    for (int c = 0; c < 5; ++c) {
+    for (int cc = 0; cc < 5; ++cc) {
       float v[16];
-      tmem_ld16(lane_addr + (uint32_t)(256 + 16 * c), v);
+      tmem_ld16(lane_addr + (uint32_t)(256 + 16 * cc), v);
       if (live) {
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          const int k = 16 * c + j;
-          if (k <= 64) out[k * Nc + n] = v[j];
+          const int k = 16 * cc + j;
+          if (k < Kc) out[k * Nc + n] = v[j];
+          else if (k == 64) out[Kc * Nc + n] = v[j];
         }
       }
     }
+    }
   } else {
-    // ---- B team: column k of X -> row k of the K-major image (hi | lo); row 64 = value-row indicator
-    const int t = tid - 128, k = t & 63, kb = t >> 6;
+    // ---- B team: column k of X -> row k of the K-major image (hi | lo), 16 rows per thread; image row 64 = value-row indicator
+    const int t = tid - 256, k = t & 63, half = t >> 6;
+    int s = 0, st = 0; uint32_t ph = 0, pho = 0;
+    // (first row of the sub-tile) mod G, advanced per iteration in 32-bit arithmetic (a 64-bit modulo per sub-tile on the
+    // critical path of this warp used to cost more than the transposition itself)
+    uint32_t rem = (uint32_t)(((int64_t)blockIdx.x * WG_ROWS) % G);
+    const uint32_t rem_step = (uint32_t)(((int64_t)gridDim.x * WG_ROWS) % G);
     for (int it = 0; it < n_it; ++it) {
-      const int s = it % WG_STAGES, st = it & 1;
       const int64_t sub = blockIdx.x + (int64_t)it * gridDim.x;
       const int rows = (int)min((int64_t)WG_ROWS, R - sub * WG_ROWS);
-      mbar_wait_guard(&raw_full[s], (uint32_t)((it / WG_STAGES) & 1));
-      if (it >= 2) mbar_wait_guard(&ops_empty[st], (uint32_t)(((it >> 1) - 1) & 1));
-      const float* x = reinterpret_cast<const float*>(raw + s * WG_RAW) + k;
-      unsigned char* img = Bimg + st * WG_BSTAGE + kb * (WG_NB * 128);
+      mbar_wait_backoff(&raw_full[s], ph);
+      if (it >= WG_OPS) mbar_wait_backoff(&ops_empty[st], pho ^ 1);
+      const float* x = reinterpret_cast<const float*>(raw + s * stage_bytes) + k;
+      unsigned char* img = Bimg + st * WG_BSTAGE;
+      if (k < Kc) {                                     // image rows Kc .. 63 stay zero (narrow first layer)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float v[4];
+        for (int jj = 0; jj < 4; ++jj) {
+          const int j = 4 * half + jj;
+          float v[4];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int r = 32 * kb + 4 * j + e;
-          v[e] = r < rows ? x[r * 64] : 0.f;
+          for (int e = 0; e < 4; ++e) {
+            const int r = 4 * j + e;
+            v[e] = r < rows ? x[r * Kc] : 0.f;
+          }
+          float4 hi, lo;
+          hi.x = tf32_rna_i(v[0]); hi.y = tf32_rna_i(v[1]); hi.z = tf32_rna_i(v[2]); hi.w = tf32_rna_i(v[3]);
+          lo.x = v[0] - hi.x; lo.y = v[1] - hi.y; lo.z = v[2] - hi.z; lo.w = v[3] - hi.w;
+          const int off = k * 128 + ((j ^ (k & 7)) << 4);
+          *reinterpret_cast<float4*>(img + off) = hi;
+          *reinterpret_cast<float4*>(img + WG_BPLANE + off) = lo;
         }
-        float4 hi, lo;
-        hi.x = tf32_rna(v[0]); hi.y = tf32_rna(v[1]); hi.z = tf32_rna(v[2]); hi.w = tf32_rna(v[3]);
-        lo.x = v[0] - hi.x; lo.y = v[1] - hi.y; lo.z = v[2] - hi.z; lo.w = v[3] - hi.w;
-        const int off = k * 128 + ((j ^ (k & 7)) << 4);
-        *reinterpret_cast<float4*>(img + off) = hi;
-        *reinterpret_cast<float4*>(img + WG_BPLANE + off) = lo;
       }
-      if (t < 64) {
+      if (t < WG_ROWS) {
         const int r = t;
-        const float ind = (r < rows && ((sub * WG_ROWS + r) % G) == 0) ? 1.f : 0.f;
-        *reinterpret_cast<float*>(Bimg + st * WG_BSTAGE + (r >> 5) * (WG_NB * 128) + 64 * 128 + (((r & 31) >> 2) << 4) + ((r & 3) << 2)) = ind;
+        const float ind = (r < rows && ((rem + (uint32_t)r) % (uint32_t)G) == 0) ? 1.f : 0.f;
+        *reinterpret_cast<float*>(img + 64 * 128 + ((r >> 2) << 4) + ((r & 3) << 2)) = ind;
       }
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) { mbar_arrive(&ops_full[st]); mbar_arrive(&raw_empty[s]); }
+      if (++s == S) { s = 0; ph ^= 1; }
+      if (++st == WG_OPS) { st = 0; pho ^= 1; }
+      rem = (rem + rem_step) % (uint32_t)G;
     }
   }
   fence_before();
@@ -405,10 +454,13 @@ wgrad_tc_kernel(const float* __restrict__ X, const float* __restrict__ dY, float
   if (warp == 0) tmem_dealloc(tmem_base, 512);
 }
 
-inline bool wgrad_tc_ok(int64_t R, int Kc, int Nc) { return R >= (int64_t)128 * num_sms() && Kc == 64 && (Nc & 3) == 0 && Nc >= 4 && Nc <= 128; }
+inline bool wgrad_tc_ok(int64_t R, int Kc, int Nc) {
+  return R >= (int64_t)128 * num_sms() && Kc >= 4 && Kc <= 64 && (Kc & 3) == 0 && (Nc & 3) == 0 && Nc >= 4 && Nc <= 128;
+}
 
 // grid (= number of partial blocks written) is returned through *n_cta
-inline int launch_wgrad_tc(const float* X, const float* dY, float* partial, int64_t R, int Nc, int G, int max_cta, int* n_cta, cudaStream_t s) {
+inline int launch_wgrad_tc(const float* X, const float* dY, float* partial, int64_t R, int Kc, int Nc, int G, int max_cta, int* n_cta,
+                           cudaStream_t s) {
   static bool attr[WF_MAX_DEVICES] = {};
   const int dev = current_device();
   if (!attr[dev]) {
@@ -418,7 +470,7 @@ inline int launch_wgrad_tc(const float* X, const float* dY, float* partial, int6
   const int64_t n_sub = (R + WG_ROWS - 1) / WG_ROWS;
   int grid = (int)(n_sub < num_sms() ? n_sub : num_sms());
   if (grid > max_cta) grid = max_cta;
-  wgrad_tc_kernel<<<grid, WG_THREADS, WG_SMEM, s>>>(X, dY, partial, R, Nc, G);
+  wgrad_tc_kernel<<<grid, WG_THREADS, WG_SMEM, s>>>(X, dY, partial, R, Kc, Nc, G);
   WF_LAUNCH_CHECK();
   *n_cta = grid;
   return WF_OK;
