@@ -490,6 +490,54 @@ __device__ __forceinline__ Jet<D> sig_jet(const Jet<D>& o) {
   return junary(o, g.s, g.d1, g.d2);
 }
 
+// Rows of a walker's conditioner output as they lie in HBM: lane q reads / writes the D consecutive floats of coefficient q
+// (all dimensions at once: one 128-bit access per jet row at D = 4, fully coalesced across the warp).  The head kernels used to
+// run one warp per (walker, dimension) with 4-byte accesses at a stride of D floats -- a quarter of every sector used per
+// request, and they were bound by those requests, not by their warp all-reduces.
+template <int D>
+__device__ __forceinline__ void rows_load(const float* __restrict__ base, int64_t n, int width, int lane, bool act, float (&o)[D + 2][D]) {
+#pragma unroll
+  for (int c = 0; c < D + 2; ++c) {
+    const float* p = base + (n * (D + 2) + c) * (int64_t)width + lane * D;
+    if constexpr (D == 4) {
+      const float4 v = act ? __ldg(reinterpret_cast<const float4*>(p)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      o[c][0] = v.x; o[c][1] = v.y; o[c][2] = v.z; o[c][3] = v.w;
+    } else {
+#pragma unroll
+      for (int dd = 0; dd < D; ++dd) o[c][dd] = act ? __ldg(p + dd) : 0.f;
+    }
+  }
+}
+template <int D>
+__device__ __forceinline__ void rows_store(float* __restrict__ base, int64_t n, int width, int lane, const float (&o)[D + 2][D]) {
+#pragma unroll
+  for (int c = 0; c < D + 2; ++c) {
+    float* p = base + (n * (D + 2) + c) * (int64_t)width + lane * D;
+    if constexpr (D == 4) {
+      *reinterpret_cast<float4*>(p) = make_float4(o[c][0], o[c][1], o[c][2], o[c][3]);
+    } else {
+#pragma unroll
+      for (int dd = 0; dd < D; ++dd) p[dd] = o[c][dd];
+    }
+  }
+}
+template <int D>
+__device__ __forceinline__ Jet<D> rows_jet(const float (&o)[D + 2][D], int d) {
+  Jet<D> j;
+  j.v = o[0][d];
+#pragma unroll
+  for (int i = 0; i < D; ++i) j.g[i] = o[1 + i][d];
+  j.l = o[D + 1][d];
+  return j;
+}
+template <int D>
+__device__ __forceinline__ void rows_put(float (&o)[D + 2][D], int d, const Jet<D>& j) {
+  o[0][d] = j.v;
+#pragma unroll
+  for (int i = 0; i < D; ++i) o[1 + i][d] = j.g[i];
+  o[D + 1][d] = j.l;
+}
+
 // ---- IMADE head (made.py:66-81)
 struct HeadArgs {
   const float* O;      // [R][D*P] conditioner output jets
@@ -511,11 +559,10 @@ struct ImadeLane {
 
 // everything the forward pass of one (walker, dimension) produces, per lane
 template <int D>
-__device__ __forceinline__ void imade_lane_fwd(const HeadArgs& a, int64_t n, int d, int lane, ImadeLane<D>& L) {
-  const int DP = D * a.P;
+__device__ __forceinline__ void imade_lane_fwd(const HeadArgs& a, int64_t n, int d, int lane, const Jet<D>& o, ImadeLane<D>& L) {
   L.act = lane < a.P;
   L.wq = L.act ? a.wq[lane] : 0.f;
-  L.o = L.act ? jload<D>(a.O, n, DP, lane * D + d) : jzero<D>();
+  L.o = o;                                             // zero on the padding lanes (rows_load)
   L.s = L.act ? sig_jet(L.o) : jzero<D>();
   L.S1 = warp_sum(L.s);
   L.r1 = jrecip(L.S1);
@@ -538,20 +585,24 @@ __device__ __forceinline__ void imade_lane_fwd(const HeadArgs& a, int64_t n, int
   L.dy.v += LOG_TOL;
 }
 
-// Y [R][D] receives y at the REVERSED column (the Reverse layer, bijections.py:317-347); LDC [R][D] the log-det terms
+// One WARP per walker, lane q owns coefficient q (P <= 32); the D dimensions are processed one after the other on the rows
+// loaded once.  Y [R][D] receives y at the REVERSED column (the Reverse layer, bijections.py:317-347); LDC [R][D] the log-det terms
 template <int D>
 __global__ void __launch_bounds__(HEAD_THREADS) imade_fwd_kernel(const __grid_constant__ HeadArgs a, float* __restrict__ Y,
                                                                  float* __restrict__ LDC) {
-  const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t n = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
-  if (w >= a.N * D) return;
-  const int64_t n = w / D;
-  const int d = (int)(w % D);
-  ImadeLane<D> L;
-  imade_lane_fwd<D>(a, n, d, lane, L);
-  if (lane == 0) {
-    jstore<D>(Y, n, D, D - 1 - d, L.y);
-    jstore<D>(LDC, n, D, d, jlog(L.dy));
+  if (n >= a.N) return;
+  float o[D + 2][D];
+  rows_load<D>(a.O, n, D * a.P, lane, lane < a.P, o);
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    ImadeLane<D> L;
+    imade_lane_fwd<D>(a, n, d, lane, rows_jet<D>(o, d), L);
+    if (lane == 0) {
+      jstore<D>(Y, n, D, D - 1 - d, L.y);
+      jstore<D>(LDC, n, D, d, jlog(L.dy));
+    }
   }
 }
 
@@ -560,49 +611,53 @@ template <int D>
 __global__ void __launch_bounds__(HEAD_THREADS) imade_bwd_kernel(const __grid_constant__ HeadArgs a, const float* __restrict__ Ybar,
                                                                  const float* __restrict__ LDbar, float* __restrict__ Obar,
                                                                  float* __restrict__ Ubar) {
-  const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t n = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
-  if (w >= a.N * D) return;
-  const int64_t n = w / D;
-  const int d = (int)(w % D);
-  ImadeLane<D> L;
-  imade_lane_fwd<D>(a, n, d, lane, L);
-  const Jet<D> ybar = jload<D>(Ybar, n, D, D - 1 - d);
+  if (n >= a.N) return;
+  float o[D + 2][D], ob[D + 2][D];
+  rows_load<D>(a.O, n, D * a.P, lane, lane < a.P, o);
   const Jet<D> lbar = jload<D>(LDbar, n, 1, 0);
-  Jet<D> dybar = jzero<D>();
-  jlog_bwd(L.dy, lbar, dybar);
-  Jet<D> cbar = jzero<D>(), B0bar = jzero<D>(), B1bar = jzero<D>(), ub = jzero<D>();
-  jmul_bwd(L.B0, ybar, cbar);
-  jmul_bwd(L.B1, dybar, cbar);
-  jmul_bwd(L.c, ybar, B0bar);
-  jmul_bwd(L.c, dybar, B1bar);
-  junary_bwd(L.u, L.f.f[1], L.f.f[2], L.f.f[3], B0bar, ub);
-  junary_bwd(L.u, L.f.f[2], L.f.f[3], L.f.f[3], B1bar, ub);   // table order 4 clamps to 3 (quirk Q5)
-  const Jet<D> ubar = warp_sum(ub);
-  Jet<D> bbar = jzero<D>(), r2b = jzero<D>();
-  jmul_bwd(L.r2, cbar, bbar);
-  jmul_bwd(L.b, cbar, r2b);
-  const Jet<D> r2bar = warp_sum(r2b);
-  Jet<D> S2bar = jzero<D>();
-  jrecip_bwd(L.S2, r2bar, S2bar);
-  Jet<D> sbar = jzero<D>(), r1b = jzero<D>();
-  if (L.wq != 0.f) {
-    jacc(bbar, S2bar);
-    const Jet<D> abar = jscale(bbar, L.wq);
-    jmul_bwd(L.r1, abar, sbar);
-    jmul_bwd(L.s, abar, r1b);
-  }
-  const Jet<D> r1bar = warp_sum(r1b);
-  Jet<D> S1bar = jzero<D>();
-  jrecip_bwd(L.S1, r1bar, S1bar);
-  if (L.act) {
-    jacc(sbar, S1bar);
-    const Sig g = sigmoid_derivs(L.o.v);
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    ImadeLane<D> L;
+    imade_lane_fwd<D>(a, n, d, lane, rows_jet<D>(o, d), L);
+    const Jet<D> ybar = jload<D>(Ybar, n, D, D - 1 - d);
+    Jet<D> dybar = jzero<D>();
+    jlog_bwd(L.dy, lbar, dybar);
+    Jet<D> cbar = jzero<D>(), B0bar = jzero<D>(), B1bar = jzero<D>(), ub = jzero<D>();
+    jmul_bwd(L.B0, ybar, cbar);
+    jmul_bwd(L.B1, dybar, cbar);
+    jmul_bwd(L.c, ybar, B0bar);
+    jmul_bwd(L.c, dybar, B1bar);
+    junary_bwd(L.u, L.f.f[1], L.f.f[2], L.f.f[3], B0bar, ub);
+    junary_bwd(L.u, L.f.f[2], L.f.f[3], L.f.f[3], B1bar, ub);   // table order 4 clamps to 3 (quirk Q5)
+    const Jet<D> ubar = warp_sum(ub);
+    Jet<D> bbar = jzero<D>(), r2b = jzero<D>();
+    jmul_bwd(L.r2, cbar, bbar);
+    jmul_bwd(L.b, cbar, r2b);
+    const Jet<D> r2bar = warp_sum(r2b);
+    Jet<D> S2bar = jzero<D>();
+    jrecip_bwd(L.S2, r2bar, S2bar);
+    Jet<D> sbar = jzero<D>(), r1b = jzero<D>();
+    if (L.wq != 0.f) {
+      jacc(bbar, S2bar);
+      const Jet<D> abar = jscale(bbar, L.wq);
+      jmul_bwd(L.r1, abar, sbar);
+      jmul_bwd(L.s, abar, r1b);
+    }
+    const Jet<D> r1bar = warp_sum(r1b);
+    Jet<D> S1bar = jzero<D>();
+    jrecip_bwd(L.S1, r1bar, S1bar);
     Jet<D> obar = jzero<D>();
-    junary_bwd(L.o, g.d1, g.d2, g.d3, sbar, obar);
-    jstore<D>(Obar, n, D * a.P, lane * D + d, obar);
+    if (L.act) {
+      jacc(sbar, S1bar);
+      const Sig g = sigmoid_derivs(L.o.v);
+      junary_bwd(L.o, g.d1, g.d2, g.d3, sbar, obar);
+    }
+    rows_put<D>(ob, d, obar);
+    if (lane == 0) jstore<D>(Ubar, n, D, d, ubar);
   }
-  if (lane == 0) jstore<D>(Ubar, n, D, d, ubar);
+  if (lane < a.P) rows_store<D>(Obar, n, D * a.P, lane, ob);
 }
 
 // ---- prior head (wavefunctions.py:54-71)
@@ -1041,7 +1096,8 @@ int run_chunk(const wf_live_model* m, const wf_live_tables* t, const float* para
 
   const int eb = 256;
   const int64_t nh = N * HID, nd = N * D;
-  const int hb = (int)((nd * 32 + HEAD_THREADS - 1) / HEAD_THREADS);   // one warp per (walker, dimension)
+  const int hb = (int)((nd * 32 + HEAD_THREADS - 1) / HEAD_THREADS);   // prior head: one warp per (walker, dimension)
+  const int hbw = (int)((N * 32 + HEAD_THREADS - 1) / HEAD_THREADS);   // IMADE heads: one warp per walker
 
   // ---------------- forward
   box_kernel<D><<<(int)((N + 127) / 128), 128, 0, s>>>(x, N, m->box, m->coord_mean, U[0], LDbox);
@@ -1058,7 +1114,7 @@ int run_chunk(const wf_live_model* m, const wf_live_tables* t, const float* para
     if (st != WF_OK) return st;
     if (i < L) {
       ha.O = O[i]; ha.U = U[i];
-      imade_fwd_kernel<D><<<hb, HEAD_THREADS, 0, s>>>(ha, U[i + 1], LDC + (int64_t)i * R * D);
+      imade_fwd_kernel<D><<<hbw, HEAD_THREADS, 0, s>>>(ha, U[i + 1], LDC + (int64_t)i * R * D);
     } else {
       pa.O = O[i]; pa.U = U[i];
       prior_fwd_kernel<D><<<hb, HEAD_THREADS, 0, s>>>(pa, PHI);
@@ -1085,7 +1141,7 @@ int run_chunk(const wf_live_model* m, const wf_live_tables* t, const float* para
       prior_bwd_kernel<D><<<hb, HEAD_THREADS, 0, s>>>(pa, PHIbar, Obar, Ucur);
     } else {
       ha.O = O[i]; ha.U = U[i];
-      imade_bwd_kernel<D><<<hb, HEAD_THREADS, 0, s>>>(ha, Ub[cur ^ 1], LDbar, Obar, Ucur);
+      imade_bwd_kernel<D><<<hbw, HEAD_THREADS, 0, s>>>(ha, Ub[cur ^ 1], LDbar, Obar, Ucur);
     }
     WF_LAUNCH_CHECK();
     int st;
