@@ -547,7 +547,43 @@ struct HeadArgs {
   int P, T;
   float reg;
   float wq[WF_MAX_P];  // remove_bias scale with the boundary constraints folded in (0 at constrained ends)
+  float* sav;          // [N][D][sav_floats<D>]: S1, S2, dy of the forward pass -- the reverse kernel reloads these three sums over
+                       // coefficients (18 floats per walker and dimension at D = 4) instead of repeating four of its seven warp all-reduces
 };
+template <int D> constexpr int sav_floats() { return (3 * (D + 2) + 3) & ~3; }
+template <int D>
+__device__ __forceinline__ void sav_put(float (&v)[sav_floats<D>()], int k, const Jet<D>& j) {
+  v[k * (D + 2)] = j.v;
+#pragma unroll
+  for (int i = 0; i < D; ++i) v[k * (D + 2) + 1 + i] = j.g[i];
+  v[k * (D + 2) + D + 1] = j.l;
+}
+template <int D>
+__device__ __forceinline__ Jet<D> sav_get(const float (&v)[sav_floats<D>()], int k) {
+  Jet<D> j;
+  j.v = v[k * (D + 2)];
+#pragma unroll
+  for (int i = 0; i < D; ++i) j.g[i] = v[k * (D + 2) + 1 + i];
+  j.l = v[k * (D + 2) + D + 1];
+  return j;
+}
+template <int D>
+__device__ __forceinline__ void sav_store(float* __restrict__ p, const Jet<D>& a, const Jet<D>& b, const Jet<D>& c) {
+  float v[sav_floats<D>()] = {};
+  sav_put<D>(v, 0, a); sav_put<D>(v, 1, b); sav_put<D>(v, 2, c);
+#pragma unroll
+  for (int k = 0; k < sav_floats<D>() / 4; ++k) reinterpret_cast<float4*>(p)[k] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+}
+template <int D>
+__device__ __forceinline__ void sav_load(const float* __restrict__ p, Jet<D>& a, Jet<D>& b, Jet<D>& c) {
+  float v[sav_floats<D>()];
+#pragma unroll
+  for (int k = 0; k < sav_floats<D>() / 4; ++k) {
+    const float4 q = __ldg(reinterpret_cast<const float4*>(p) + k);
+    v[4 * k] = q.x; v[4 * k + 1] = q.y; v[4 * k + 2] = q.z; v[4 * k + 3] = q.w;
+  }
+  a = sav_get<D>(v, 0); b = sav_get<D>(v, 1); c = sav_get<D>(v, 2);
+}
 
 template <int D>
 struct ImadeLane {
@@ -558,13 +594,14 @@ struct ImadeLane {
 };
 
 // everything the forward pass of one (walker, dimension) produces, per lane
-template <int D>
+template <int D, bool RELOAD>
 __device__ __forceinline__ void imade_lane_fwd(const HeadArgs& a, int64_t n, int d, int lane, const Jet<D>& o, ImadeLane<D>& L) {
   L.act = lane < a.P;
   L.wq = L.act ? a.wq[lane] : 0.f;
   L.o = o;                                             // zero on the padding lanes (rows_load)
   L.s = L.act ? sig_jet(L.o) : jzero<D>();
-  L.S1 = warp_sum(L.s);
+  if (RELOAD) sav_load<D>(a.sav + (n * D + d) * sav_floats<D>(), L.S1, L.S2, L.dy);
+  else L.S1 = warp_sum(L.s);
   L.r1 = jrecip(L.S1);
   L.b = jzero<D>();
   if (L.wq != 0.f) {
@@ -572,7 +609,7 @@ __device__ __forceinline__ void imade_lane_fwd(const HeadArgs& a, int64_t n, int
     L.b.v += a.reg;
     L.b = jscale(L.b, L.wq);
   }
-  L.S2 = warp_sum(L.b);
+  if (!RELOAD) L.S2 = warp_sum(L.b);
   L.r2 = jrecip(L.S2);
   L.c = jmul(L.b, L.r2);
   L.u = jload<D>(a.U, n, D, d);
@@ -580,9 +617,11 @@ __device__ __forceinline__ void imade_lane_fwd(const HeadArgs& a, int64_t n, int
   L.f = basis4(a.tab, ni, (float)(a.T - 1), lane);     // padded table columns (lane >= P) are zero
   L.B0 = junary(L.u, L.f.f[0], L.f.f[1], L.f.f[2]);
   L.B1 = junary(L.u, L.f.f[1], L.f.f[2], L.f.f[3]);
-  L.y = warp_sum(jmul(L.c, L.B0));
-  L.dy = warp_sum(jmul(L.c, L.B1));
-  L.dy.v += LOG_TOL;
+  if (!RELOAD) {                                                   // y itself is not needed by the reverse pass
+    L.y = warp_sum(jmul(L.c, L.B0));
+    L.dy = warp_sum(jmul(L.c, L.B1));
+    L.dy.v += LOG_TOL;
+  }
 }
 
 // One WARP per walker, lane q owns coefficient q (P <= 32); the D dimensions are processed one after the other on the rows
@@ -598,17 +637,18 @@ __global__ void __launch_bounds__(HEAD_THREADS) imade_fwd_kernel(const __grid_co
 #pragma unroll
   for (int d = 0; d < D; ++d) {
     ImadeLane<D> L;
-    imade_lane_fwd<D>(a, n, d, lane, rows_jet<D>(o, d), L);
+    imade_lane_fwd<D, false>(a, n, d, lane, rows_jet<D>(o, d), L);
     if (lane == 0) {
       jstore<D>(Y, n, D, D - 1 - d, L.y);
       jstore<D>(LDC, n, D, d, jlog(L.dy));
+      if (a.sav) sav_store<D>(a.sav + (n * D + d) * sav_floats<D>(), L.S1, L.S2, L.dy);
     }
   }
 }
 
 // Ybar [R][D]: adjoint of the NEXT layer's input (so y_d's adjoint sits at column D-1-d); LDbar [R]: adjoint of log|det|
 template <int D>
-__global__ void __launch_bounds__(HEAD_THREADS) imade_bwd_kernel(const __grid_constant__ HeadArgs a, const float* __restrict__ Ybar,
+__global__ void __launch_bounds__(HEAD_THREADS, 4) imade_bwd_kernel(const __grid_constant__ HeadArgs a, const float* __restrict__ Ybar,
                                                                  const float* __restrict__ LDbar, float* __restrict__ Obar,
                                                                  float* __restrict__ Ubar) {
   const int64_t n = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -620,7 +660,7 @@ __global__ void __launch_bounds__(HEAD_THREADS) imade_bwd_kernel(const __grid_co
 #pragma unroll
   for (int d = 0; d < D; ++d) {
     ImadeLane<D> L;
-    imade_lane_fwd<D>(a, n, d, lane, rows_jet<D>(o, d), L);
+    imade_lane_fwd<D, true>(a, n, d, lane, rows_jet<D>(o, d), L);
     const Jet<D> ybar = jload<D>(Ybar, n, D, D - 1 - d);
     Jet<D> dybar = jzero<D>();
     jlog_bwd(L.dy, lbar, dybar);
@@ -909,7 +949,8 @@ Fixed fixed_floats(const wf_live_model* m) {
 int64_t per_row_floats(const wf_live_model* m) {
   const int D = m->D, nn = n_nets_of(m), DPm = max_DP(m);
   // U[nn+1], per net Z1 H1 Z2 H2 O, LDbox, LDC[L], PHI, PHIbar, LDbar, Obar, HbarA, HbarB, Ubar x2
-  return (int64_t)(nn + 1) * D + (int64_t)nn * (4 * HID + DPm) + 1 + (int64_t)m->n_layers * D + 2 * D + 1 + DPm + 2 * HID + 2 * D;
+  return (int64_t)(nn + 1) * D + (int64_t)nn * (4 * HID + DPm) + 1 + (int64_t)m->n_layers * D + 2 * D + 1 + DPm + 2 * HID + 2 * D +
+         4 * (int64_t)m->n_layers * D;                              // + the saved head sums S1, S2, dy per flow layer (>= D sav_floats / G)
 }
 
 int smem_linear(int Kc, int BN, int lrows) {
@@ -1030,6 +1071,7 @@ int run_chunk(const wf_live_model* m, const wf_live_tables* t, const float* para
   float* HbA = take(R * HID);
   float* HbB = take(R * HID);
   float* Ub[2] = {take(R * D), take(R * D)};
+  float* SAV = take((int64_t)L * N * D * sav_floats<D>());
 
   // masked weights (model_factory.py:31-33)
   NetOff off[WF_MAX_LAYERS + 1];
@@ -1113,7 +1155,7 @@ int run_chunk(const wf_live_model* m, const wf_live_tables* t, const float* para
     else st = lin_fwd(H2[i], Wf, iW3f[i], bf, O[i], HID, NcF);                              // folded prior layer
     if (st != WF_OK) return st;
     if (i < L) {
-      ha.O = O[i]; ha.U = U[i];
+      ha.O = O[i]; ha.U = U[i]; ha.sav = grad ? SAV + (int64_t)i * N * D * sav_floats<D>() : nullptr;
       imade_fwd_kernel<D><<<hbw, HEAD_THREADS, 0, s>>>(ha, U[i + 1], LDC + (int64_t)i * R * D);
     } else {
       pa.O = O[i]; pa.U = U[i];
@@ -1140,7 +1182,7 @@ int run_chunk(const wf_live_model* m, const wf_live_tables* t, const float* para
       pa.O = O[i]; pa.U = U[i];
       prior_bwd_kernel<D><<<hb, HEAD_THREADS, 0, s>>>(pa, PHIbar, Obar, Ucur);
     } else {
-      ha.O = O[i]; ha.U = U[i];
+      ha.O = O[i]; ha.U = U[i]; ha.sav = SAV + (int64_t)i * N * D * sav_floats<D>();
       imade_bwd_kernel<D><<<hbw, HEAD_THREADS, 0, s>>>(ha, Ub[cur ^ 1], LDbar, Obar, Ucur);
     }
     WF_LAUNCH_CHECK();
