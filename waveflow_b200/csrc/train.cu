@@ -406,6 +406,115 @@ __global__ void tanh_bwd_kernel(const float* __restrict__ Z, float* __restrict__
   jstore<D>(Hbar, n, HID, c, zb);
 }
 
+// ---- first conditioner layer, fused: Z1 = U W1 + b1 (K = D: no GEMM to speak of) and H1 = tanh(Z1) in one pass, and in
+// reverse Zbar1 = tanh'(Z1; Hbar1) (in place) together with the input adjoint Ubar += Zbar1 W1^T.  16 lanes per walker, 4 hidden
+// features each: every thread holds all G jet components of its features, so the tanh jet needs no exchange; rows are written
+// with 128-bit coalesced stores.  Replaces linear_kernel + tanh_fwd_kernel and tanh_bwd_kernel + dgrad_narrow_kernel.
+template <int D>
+__global__ void __launch_bounds__(256) layer1_fwd_kernel(const float* __restrict__ U, const float* __restrict__ W1, const float* __restrict__ b1,
+                                                         float* __restrict__ Z, float* __restrict__ Hh, int64_t N) {
+  constexpr int G = D + 2;
+  __shared__ float4 Ws[D][16];
+  __shared__ float4 bs[16];
+  if (threadIdx.x < D * 16) Ws[threadIdx.x / 16][threadIdx.x % 16] = make_float4(W1[4 * threadIdx.x], W1[4 * threadIdx.x + 1], W1[4 * threadIdx.x + 2], W1[4 * threadIdx.x + 3]);
+  if (threadIdx.x < 16) bs[threadIdx.x] = make_float4(b1[4 * threadIdx.x], b1[4 * threadIdx.x + 1], b1[4 * threadIdx.x + 2], b1[4 * threadIdx.x + 3]);
+  __syncthreads();
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t n = i >> 4;
+  const int q = (int)(i & 15);
+  if (n >= N) return;
+  float z[G][4];
+#pragma unroll
+  for (int c = 0; c < G; ++c) {
+    float4 acc = c == 0 ? bs[q] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+      const float u = __ldg(U + (n * G + c) * D + k);
+      const float4 w = Ws[k][q];
+      acc.x = fmaf(u, w.x, acc.x); acc.y = fmaf(u, w.y, acc.y); acc.z = fmaf(u, w.z, acc.z); acc.w = fmaf(u, w.w, acc.w);
+    }
+    z[c][0] = acc.x; z[c][1] = acc.y; z[c][2] = acc.z; z[c][3] = acc.w;
+    *reinterpret_cast<float4*>(Z + (n * G + c) * HID + 4 * q) = acc;
+  }
+  float h[G][4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    Jet<D> zj;
+    zj.v = z[0][j];
+#pragma unroll
+    for (int g = 0; g < D; ++g) zj.g[g] = z[1 + g][j];
+    zj.l = z[D + 1][j];
+    const float t = tanhf(zj.v), d1 = 1.f - t * t;
+    const Jet<D> hj = junary(zj, t, d1, -2.f * t * d1);
+    h[0][j] = hj.v;
+#pragma unroll
+    for (int g = 0; g < D; ++g) h[1 + g][j] = hj.g[g];
+    h[D + 1][j] = hj.l;
+  }
+#pragma unroll
+  for (int c = 0; c < G; ++c) *reinterpret_cast<float4*>(Hh + (n * G + c) * HID + 4 * q) = make_float4(h[c][0], h[c][1], h[c][2], h[c][3]);
+}
+
+// Hbar -> Zbar in place; Ubar[R][D] += Zbar W1^T when Ubar != nullptr (W1 [D][64])
+template <int D>
+__global__ void __launch_bounds__(256) layer1_bwd_kernel(const float* __restrict__ Z, float* __restrict__ Hbar, const float* __restrict__ W1,
+                                                         float* __restrict__ Ubar, int64_t N) {
+  constexpr int G = D + 2;
+  __shared__ float4 Ws[D][16];
+  if (threadIdx.x < D * 16) Ws[threadIdx.x / 16][threadIdx.x % 16] = make_float4(W1[4 * threadIdx.x], W1[4 * threadIdx.x + 1], W1[4 * threadIdx.x + 2], W1[4 * threadIdx.x + 3]);
+  __syncthreads();
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t n = i >> 4;                           // N is padded to whole warps by the launch: every lane takes part in the shuffles
+  const int q = (int)(i & 15);
+  const bool ok = n < N;
+  float z[G][4], ob[G][4], zb[G][4];
+#pragma unroll
+  for (int c = 0; c < G; ++c) {
+    const float4 a = ok ? __ldg(reinterpret_cast<const float4*>(Z + (n * G + c) * HID) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 b = ok ? *(reinterpret_cast<const float4*>(Hbar + (n * G + c) * HID) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+    z[c][0] = a.x; z[c][1] = a.y; z[c][2] = a.z; z[c][3] = a.w;
+    ob[c][0] = b.x; ob[c][1] = b.y; ob[c][2] = b.z; ob[c][3] = b.w;
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    Jet<D> zj, oj;
+    zj.v = z[0][j]; oj.v = ob[0][j];
+#pragma unroll
+    for (int g = 0; g < D; ++g) { zj.g[g] = z[1 + g][j]; oj.g[g] = ob[1 + g][j]; }
+    zj.l = z[D + 1][j]; oj.l = ob[D + 1][j];
+    const float t = tanhf(zj.v), d1 = 1.f - t * t, d2 = -2.f * t * d1, d3 = -2.f * d1 * d1 - 2.f * t * d2;
+    Jet<D> r = jzero<D>();
+    junary_bwd(zj, d1, d2, d3, oj, r);
+    zb[0][j] = r.v;
+#pragma unroll
+    for (int g = 0; g < D; ++g) zb[1 + g][j] = r.g[g];
+    zb[D + 1][j] = r.l;
+  }
+  if (ok) {
+#pragma unroll
+    for (int c = 0; c < G; ++c) *(reinterpret_cast<float4*>(Hbar + (n * G + c) * HID) + q) = make_float4(zb[c][0], zb[c][1], zb[c][2], zb[c][3]);
+  }
+  if (Ubar) {
+#pragma unroll
+    for (int c = 0; c < G; ++c) {
+      float p[D];
+#pragma unroll
+      for (int o = 0; o < D; ++o) {
+        const float4 w = Ws[o][q];
+        p[o] = fmaf(zb[c][0], w.x, fmaf(zb[c][1], w.y, fmaf(zb[c][2], w.z, zb[c][3] * w.w)));
+      }
+#pragma unroll
+      for (int m = 8; m >= 1; m >>= 1)
+#pragma unroll
+        for (int o = 0; o < D; ++o) p[o] += __shfl_xor_sync(0xffffffffu, p[o], m);
+      if (ok && q == 0) {
+#pragma unroll
+        for (int o = 0; o < D; ++o) Ubar[(n * G + c) * D + o] += p[o];
+      }
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------- box transform (made.py:108-183)
 template <int D>
 __global__ void box_kernel(const float* __restrict__ x, int64_t N, float L, int coord_mean, float* __restrict__ U,
@@ -1147,8 +1256,7 @@ int run_chunk(const wf_live_model* m, const wf_live_tables* t, const float* para
   for (int i = 0; i < nn; ++i) {
     const int P = net_P(m, i), DP = D * P;
     int st;
-    if ((st = launch_linear<false, false>(U[i], W1m[i], params + off[i].b1, Z1[i], R, D, HID, G, s)) != WF_OK) return st;
-    tanh_fwd_kernel<D><<<(int)((nh + eb - 1) / eb), eb, 0, s>>>(Z1[i], H1[i], N);
+    layer1_fwd_kernel<D><<<(int)((N * 16 + 255) / 256), 256, 0, s>>>(U[i], W1m[i], params + off[i].b1, Z1[i], H1[i], N);
     if ((st = lin_fwd(H1[i], W2m[i], iW2f[i], params + off[i].b2, Z2[i], HID, HID)) != WF_OK) return st;
     tanh_fwd_kernel<D><<<(int)((nh + eb - 1) / eb), eb, 0, s>>>(Z2[i], H2[i], N);
     if (i < L) st = lin_fwd(H2[i], W3m[i], iW3f[i], params + off[i].b3, O[i], HID, DP);
@@ -1201,9 +1309,8 @@ int run_chunk(const wf_live_model* m, const wf_live_tables* t, const float* para
     tanh_bwd_kernel<D><<<(int)((nh + eb - 1) / eb), eb, 0, s>>>(Z2[i], HbA, N);
     if ((st = launch_wgrad(H1[i], HbA, partial, grad + off[i].W2, grad + off[i].b2, 2, D, R, HID, HID, G, s)) != WF_OK) return st;
     if ((st = lin_bwd(HbA, W2m[i], iW2b[i], HbB, HID, HID)) != WF_OK) return st;
-    tanh_bwd_kernel<D><<<(int)((nh + eb - 1) / eb), eb, 0, s>>>(Z1[i], HbB, N);
+    layer1_bwd_kernel<D><<<(int)((N * 16 + 255) / 256), 256, 0, s>>>(Z1[i], HbB, W1m[i], i > 0 ? Ucur : nullptr, N);
     if ((st = launch_wgrad(U[i], HbB, partial, grad + off[i].W1, grad + off[i].b1, 1, D, R, D, HID, G, s)) != WF_OK) return st;
-    if (i > 0 && (st = launch_dgrad_narrow(HbB, W1m[i], Ucur, R, D, s)) != WF_OK) return st;
     WF_LAUNCH_CHECK();
     cur ^= 1;
   }
