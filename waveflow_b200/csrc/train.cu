@@ -828,13 +828,13 @@ struct PriorLane {
 };
 
 template <int D>
-__device__ __forceinline__ void prior_lane_fwd(const PriorArgs& a, int64_t n, int d, int lane, PriorLane<D>& L) {
+__device__ __forceinline__ void prior_lane_fwd(const PriorArgs& a, int64_t n, int d, int lane, const Jet<D>& cpre, PriorLane<D>& L) {
   const int P = a.P, NcF = D * P + D;
   // O is the FOLDED third layer: column q*D + d = c'_q (un-normalised B coefficients), column D*P + d = sum_p o_p, whose sign
   // the conditioner's own normalisation leaves behind (model_factory.py:69-70; the L2 normalisations cancel its magnitude)
   const float sv = a.O[n * (D + 2) * (int64_t)NcF + D * P + d];
   L.sign = sv < 0.f ? -1.f : 1.f;
-  L.cpre = lane < P ? jload<D>(a.O, n, NcF, lane * D + d) : jzero<D>();
+  L.cpre = cpre;                                       // zero on the padding lanes (rows_load)
   L.S = warp_sum(jmul(L.cpre, L.cpre));
   L.nrm = jrsqrt(L.S);
   L.c = jmul(L.cpre, L.nrm);
@@ -850,54 +850,62 @@ __device__ __forceinline__ void prior_lane_fwd(const PriorArgs& a, int64_t n, in
   L.phi = jscale(warp_sum(jmul(L.c, L.B0)), L.scale);
 }
 
+// one warp per walker, as the IMADE heads
 template <int D>
 __global__ void __launch_bounds__(HEAD_THREADS) prior_fwd_kernel(const __grid_constant__ PriorArgs a, float* __restrict__ PHI) {
-  const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t n = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
-  if (w >= a.N * D) return;
-  const int64_t n = w / D;
-  const int d = (int)(w % D);
-  PriorLane<D> L;
-  prior_lane_fwd<D>(a, n, d, lane, L);
-  if (lane == 0) jstore<D>(PHI, n, D, d, L.phi);
+  if (n >= a.N) return;
+  float o[D + 2][D];
+  rows_load<D>(a.O, n, D * a.P + D, lane, lane < a.P, o);
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    PriorLane<D> L;
+    prior_lane_fwd<D>(a, n, d, lane, rows_jet<D>(o, d), L);
+    if (lane == 0) jstore<D>(PHI, n, D, d, L.phi);
+  }
 }
 
 template <int D>
 __global__ void __launch_bounds__(HEAD_THREADS) prior_bwd_kernel(const __grid_constant__ PriorArgs a, const float* __restrict__ PHIbar,
                                                                  float* __restrict__ Obar, float* __restrict__ Ubar) {
-  const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t n = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
-  if (w >= a.N * D) return;
-  const int64_t n = w / D;
-  const int d = (int)(w % D);
+  if (n >= a.N) return;
   const int P = a.P, NcF = D * P + D;
-  PriorLane<D> L;
-  prior_lane_fwd<D>(a, n, d, lane, L);
-  const Jet<D> phibar = jscale(jload<D>(PHIbar, n, D, d), L.scale);
-  Jet<D> cbar = jzero<D>(), B0bar = jzero<D>(), ub = jzero<D>();
-  jmul_bwd(L.B0, phibar, cbar);
-  jmul_bwd(L.c, phibar, B0bar);
-  junary_bwd(L.uc, L.f.f[1], L.f.f[2], L.f.f[3], B0bar, ub);
-  Jet<D> ucbar = warp_sum(ub);
-  Jet<D> cb = jzero<D>(), nb = jzero<D>();
-  jmul_bwd(L.nrm, cbar, cb);
-  jmul_bwd(L.cpre, cbar, nb);
-  const Jet<D> nbar = warp_sum(nb);
-  Jet<D> Sbar = jzero<D>();
-  jrsqrt_bwd(L.S, nbar, Sbar);
-  Jet<D> t = jzero<D>();
-  jmul_bwd(L.cpre, Sbar, t);            // d(c*c) = 2 * (one-sided adjoint)
-  jaxpy(cb, 2.f, t);
-  if (lane < P) jstore<D>(Obar, n, NcF, lane * D + d, cb);                 // adjoint of c'_q
-  if (lane == 0) {
-    jstore<D>(Obar, n, NcF, D * P + d, jzero<D>());                         // the sign column has no gradient
-    if (!L.inside) {
-      const float keep = (L.uraw == L.uc.v) ? ucbar.v : 0.f;   // clip passes the gradient only where it did not clamp
-      ucbar = jzero<D>();
-      ucbar.v = keep;
+  float o[D + 2][D], ob[D + 2][D];
+  rows_load<D>(a.O, n, NcF, lane, lane < P, o);
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    PriorLane<D> L;
+    prior_lane_fwd<D>(a, n, d, lane, rows_jet<D>(o, d), L);
+    const Jet<D> phibar = jscale(jload<D>(PHIbar, n, D, d), L.scale);
+    Jet<D> cbar = jzero<D>(), B0bar = jzero<D>(), ub = jzero<D>();
+    jmul_bwd(L.B0, phibar, cbar);
+    jmul_bwd(L.c, phibar, B0bar);
+    junary_bwd(L.uc, L.f.f[1], L.f.f[2], L.f.f[3], B0bar, ub);
+    Jet<D> ucbar = warp_sum(ub);
+    Jet<D> cb = jzero<D>(), nb = jzero<D>();
+    jmul_bwd(L.nrm, cbar, cb);
+    jmul_bwd(L.cpre, cbar, nb);
+    const Jet<D> nbar = warp_sum(nb);
+    Jet<D> Sbar = jzero<D>();
+    jrsqrt_bwd(L.S, nbar, Sbar);
+    Jet<D> t = jzero<D>();
+    jmul_bwd(L.cpre, Sbar, t);            // d(c*c) = 2 * (one-sided adjoint)
+    jaxpy(cb, 2.f, t);
+    rows_put<D>(ob, d, cb);               // adjoint of c'_q
+    if (lane == 0) {
+      jstore<D>(Obar, n, NcF, D * P + d, jzero<D>());                       // the sign column has no gradient
+      if (!L.inside) {
+        const float keep = (L.uraw == L.uc.v) ? ucbar.v : 0.f;   // clip passes the gradient only where it did not clamp
+        ucbar = jzero<D>();
+        ucbar.v = keep;
+      }
+      jstore<D>(Ubar, n, D, d, ucbar);
     }
-    jstore<D>(Ubar, n, D, d, ucbar);
   }
+  if (lane < P) rows_store<D>(Obar, n, NcF, lane, ob);
 }
 
 // ---------------------------------------------------------------------------------------------- psi, H psi, E_loc and the adjoint seeds
@@ -1247,8 +1255,7 @@ int run_chunk(const wf_live_model* m, const wf_live_tables* t, const float* para
 
   const int eb = 256;
   const int64_t nh = N * HID, nd = N * D;
-  const int hb = (int)((nd * 32 + HEAD_THREADS - 1) / HEAD_THREADS);   // prior head: one warp per (walker, dimension)
-  const int hbw = (int)((N * 32 + HEAD_THREADS - 1) / HEAD_THREADS);   // IMADE heads: one warp per walker
+  const int hbw = (int)((N * 32 + HEAD_THREADS - 1) / HEAD_THREADS);   // spline heads: one warp per walker
 
   // ---------------- forward
   box_kernel<D><<<(int)((N + 127) / 128), 128, 0, s>>>(x, N, m->box, m->coord_mean, U[0], LDbox);
@@ -1267,7 +1274,7 @@ int run_chunk(const wf_live_model* m, const wf_live_tables* t, const float* para
       imade_fwd_kernel<D><<<hbw, HEAD_THREADS, 0, s>>>(ha, U[i + 1], LDC + (int64_t)i * R * D);
     } else {
       pa.O = O[i]; pa.U = U[i];
-      prior_fwd_kernel<D><<<hb, HEAD_THREADS, 0, s>>>(pa, PHI);
+      prior_fwd_kernel<D><<<hbw, HEAD_THREADS, 0, s>>>(pa, PHI);
     }
     WF_LAUNCH_CHECK();
   }
@@ -1288,7 +1295,7 @@ int run_chunk(const wf_live_model* m, const wf_live_tables* t, const float* para
     float* Ucur = Ub[cur];
     if (i == L) {
       pa.O = O[i]; pa.U = U[i];
-      prior_bwd_kernel<D><<<hb, HEAD_THREADS, 0, s>>>(pa, PHIbar, Obar, Ucur);
+      prior_bwd_kernel<D><<<hbw, HEAD_THREADS, 0, s>>>(pa, PHIbar, Obar, Ucur);
     } else {
       ha.O = O[i]; ha.U = U[i]; ha.sav = SAV + (int64_t)i * N * D * sav_floats<D>();
       imade_bwd_kernel<D><<<hbw, HEAD_THREADS, 0, s>>>(ha, Ub[cur ^ 1], LDbar, Obar, Ucur);
