@@ -814,7 +814,7 @@ def run_b200(args):
                      ("one peer-memory kernel (wf_p2p_allreduce_vec) inside the CUDA graph of the step" if gx is not None
                       else "two NCCL all-reduces between eagerly launched kernels")),
                  "algorithmic_tflops_per_gpu": tfl, "frac_of_measured_fp32_fma": tfl / fp32_peak,
-                 "gpu_launches_per_step": 77 * ((int(x_train.shape[0]) + 65535) // 65536) + 1}
+                 "gpu_launches_per_step": 70 * ((int(x_train.shape[0]) + 65535) // 65536) + 1}
         if world == 1:
             # the reference's own training configuration (BASELINE configs[1]): He, batch 256 -- launch-bound, CUDA-graph replay
             from waveflow_b200 import _train

@@ -109,9 +109,11 @@ lin_tc_kernel(const float* __restrict__ A, const float* __restrict__ Bimg, const
   float* bias_s = reinterpret_cast<float*>(Bs + BB + TEAMS * A_TEAM);           // [NT]
   uint64_t* bars = reinterpret_cast<uint64_t*>(Bs + BB + TEAMS * A_TEAM + 512);  // [0] weights, [1 + team] MMAs done
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  volatile uint32_t* turn = tmem_slot + 1;                   // ticket of the team whose MMAs go next (see below)
 
   if (tid < 32) tmem_alloc(tmem_slot, TMEM_COLS);
   if (tid == 0) {
+    *turn = 0;
     mbar_init(&bars[0], 1);
     for (int i = 0; i < TEAMS; ++i) mbar_init(&bars[1 + i], 1);
     mbar_fence_init();
@@ -143,9 +145,12 @@ lin_tc_kernel(const float* __restrict__ A, const float* __restrict__ Bimg, const
   if (tile < n_tiles) load(tile, 0);
   bool first = true;
   uint32_t par = 0;
-  for (; tile < n_tiles; tile += stride) {
+  int it = 0;
+  for (; tile < n_tiles; tile += stride, ++it) {
     const int64_t r0 = tile * 128;
     const int rows = (int)min((int64_t)128, R - r0);
+    // teams of this CTA that have a tile in this round (only the last round can be short)
+    const int m_round = (int)min((int64_t)TEAMS, n_tiles - ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * TEAMS);
 #pragma unroll 1
     for (int kp = 0; kp < KP; ++kp) {
       // ---- split + stage the operand image of this k-part
@@ -164,6 +169,16 @@ lin_tc_kernel(const float* __restrict__ A, const float* __restrict__ Bimg, const
       bar_sync(1 + team, TEAM);
       if (tw == 0) {
         if (first) mbar_wait_guard(&bars[0], 0);              // weight image landed
+        // The teams take turns on the tensor pipe.  Left alone they run in LOCKSTEP (a clock64 timeline of one CTA,
+        // profiles/r02_train_lin_tc_timeline.txt: all three stage, issue, read TMEM and store at the same time; every phase is
+        // bound by a resource they then share -- shared-memory bandwidth, the MMA queue, TMEM reads, the store path -- and a
+        // round of three tiles takes the SUM of the contended phases, 13.5 k cycles).  Issuing the 24 MMAs of one team as one
+        // block, in ticket order, lets the first team leave the MMA phase after a third of the time: -10 % per layer.
+        // (Making the staging and epilogue phases exclusive as well was slower: alone they are latency bound.)
+        const uint32_t ticket = (uint32_t)((it * KP) * TEAMS + kp * m_round + team);
+        if ((ttid & 31) == 0)
+          while (*turn != ticket) __nanosleep(20);
+        __syncwarp();
         fence_after();
         uint64_t ah = smem_desc_sw128(As), al = smem_desc_sw128(As + A_PLANE);
         uint64_t bh = smem_desc_sw128(Bs + kp * (NT * 512)), bl = smem_desc_sw128(Bs + kp * (NT * 512) + NT * 256);
@@ -177,6 +192,7 @@ lin_tc_kernel(const float* __restrict__ A, const float* __restrict__ Bimg, const
           ah += aadv; al += aadv; bh += badv; bl += badv;
         }
         umma_commit_warp(&bars[1 + team]);
+        if ((ttid & 31) == 0) *turn = ticket + 1;
       }
       first = false;
       // ---- the next loads fly under the MMAs and the epilogue
