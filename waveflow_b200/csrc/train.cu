@@ -698,6 +698,7 @@ template <int D>
 struct ImadeLane {
   Jet<D> o, s, S1, r1, b, S2, r2, c, u, B0, B1, y, dy;
   Basis4 f;
+  Sig sg;               // sigmoid and its derivatives at o.v (the reverse pass reuses them)
   float wq;
   bool act;
 };
@@ -708,7 +709,8 @@ __device__ __forceinline__ void imade_lane_fwd(const HeadArgs& a, int64_t n, int
   L.act = lane < a.P;
   L.wq = L.act ? a.wq[lane] : 0.f;
   L.o = o;                                             // zero on the padding lanes (rows_load)
-  L.s = L.act ? sig_jet(L.o) : jzero<D>();
+  L.sg = sigmoid_derivs(L.o.v);
+  L.s = L.act ? junary(L.o, L.sg.s, L.sg.d1, L.sg.d2) : jzero<D>();
   if (RELOAD) sav_load<D>(a.sav + (n * D + d) * sav_floats<D>(), L.S1, L.S2, L.dy);
   else L.S1 = warp_sum(L.s);
   L.r1 = jrecip(L.S1);
@@ -800,8 +802,7 @@ __global__ void __launch_bounds__(HEAD_THREADS, 4) imade_bwd_kernel(const __grid
     Jet<D> obar = jzero<D>();
     if (L.act) {
       jacc(sbar, S1bar);
-      const Sig g = sigmoid_derivs(L.o.v);
-      junary_bwd(L.o, g.d1, g.d2, g.d3, sbar, obar);
+      junary_bwd(L.o, L.sg.d1, L.sg.d2, L.sg.d3, sbar, obar);
     }
     rows_put<D>(ob, d, obar);
     if (lane == 0) jstore<D>(Ubar, n, D, d, ubar);
