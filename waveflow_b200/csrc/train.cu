@@ -200,46 +200,6 @@ __global__ void __launch_bounds__(LIN_THREADS) linear_kernel(const float* __rest
   }
 }
 
-// C[R][NOUT] += A[R][64] * W^T, W given as [NOUT][64] (the input adjoint of the first layer: NOUT = D).  HBM bound on A:
-// 16 lanes per row, each one 16-byte unit of the row against the matching weight columns, then a butterfly over the 16 lanes.
-template <int NOUT>
-__global__ void __launch_bounds__(256) dgrad_narrow_kernel(const float* __restrict__ A, const float* __restrict__ W, float* __restrict__ C,
-                                                           int64_t R) {
-  __shared__ float4 Ws[NOUT][16];
-  if (threadIdx.x < NOUT * 16) Ws[threadIdx.x / 16][threadIdx.x % 16] = reinterpret_cast<const float4*>(W)[threadIdx.x];
-  __syncthreads();
-  const int c = threadIdx.x & 15;
-  const int64_t rows_per_pass = (int64_t)gridDim.x * 16;
-  for (int64_t row0 = (int64_t)blockIdx.x * 16; row0 < R; row0 += rows_per_pass) {       // uniform trip count per CTA
-    const int64_t row = row0 + (threadIdx.x >> 4);
-    const bool ok = row < R;
-    const float4 a = ok ? __ldg(reinterpret_cast<const float4*>(A + row * HID) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-    float p[NOUT];
-#pragma unroll
-    for (int o = 0; o < NOUT; ++o) {
-      const float4 w = Ws[o][c];
-      p[o] = fmaf(a.x, w.x, fmaf(a.y, w.y, fmaf(a.z, w.z, a.w * w.w)));
-    }
-#pragma unroll
-    for (int m = 8; m >= 1; m >>= 1)
-#pragma unroll
-      for (int o = 0; o < NOUT; ++o) p[o] += __shfl_xor_sync(0xffffffffu, p[o], m);
-    if (ok && c == 0) {
-#pragma unroll
-      for (int o = 0; o < NOUT; ++o) C[row * NOUT + o] += p[o];
-    }
-  }
-}
-int launch_dgrad_narrow(const float* A, const float* W, float* C, int64_t R, int nout, cudaStream_t s) {
-  const int64_t want = (R + 15) / 16;
-  const int grid = (int)(want < 8 * (int64_t)num_sms() ? want : 8 * (int64_t)num_sms());
-  if (nout == 2) dgrad_narrow_kernel<2><<<grid, 256, 0, s>>>(A, W, C, R);
-  else if (nout == 3) dgrad_narrow_kernel<3><<<grid, 256, 0, s>>>(A, W, C, R);
-  else dgrad_narrow_kernel<4><<<grid, 256, 0, s>>>(A, W, C, R);
-  WF_LAUNCH_CHECK();
-  return WF_OK;
-}
-
 // partial[cta][Kc + 1][Nc] = sum over the CTA's rows of X[r][k] * dY[r][n]; row Kc = sum over the value rows (bias gradient).
 // Each slice accumulates an 8 (k) x 8 (n) block per thread over its own 16-row chunks; the slices are summed through
 // shared memory in a fixed order at the end.
@@ -364,8 +324,19 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
   const int tot = (Kc + 1) * Nc;
   const int i = blockIdx.x * 32 + ii;
   float s = 0.f;
-  if (i < tot)
-    for (int c = ci; c < n_cta; c += 8) s += partial[(int64_t)c * tot + i];
+  if (i < tot) {
+    // four independent chains: the loop is a chain of dependent L2 loads otherwise (9 us per layer for 148 partial blocks)
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    int c = ci;
+    for (; c + 24 < n_cta; c += 32) {
+      s0 += partial[(int64_t)c * tot + i];
+      s1 += partial[(int64_t)(c + 8) * tot + i];
+      s2 += partial[(int64_t)(c + 16) * tot + i];
+      s3 += partial[(int64_t)(c + 24) * tot + i];
+    }
+    for (; c < n_cta; c += 8) s0 += partial[(int64_t)c * tot + i];
+    s = (s0 + s1) + (s2 + s3);
+  }
   red[ci][ii] = s;
   __syncthreads();
   if (ci == 0 && i < tot) {
@@ -409,7 +380,7 @@ __global__ void tanh_bwd_kernel(const float* __restrict__ Z, float* __restrict__
 // ---- first conditioner layer, fused: Z1 = U W1 + b1 (K = D: no GEMM to speak of) and H1 = tanh(Z1) in one pass, and in
 // reverse Zbar1 = tanh'(Z1; Hbar1) (in place) together with the input adjoint Ubar += Zbar1 W1^T.  16 lanes per walker, 4 hidden
 // features each: every thread holds all G jet components of its features, so the tanh jet needs no exchange; rows are written
-// with 128-bit coalesced stores.  Replaces linear_kernel + tanh_fwd_kernel and tanh_bwd_kernel + dgrad_narrow_kernel.
+// with 128-bit coalesced stores.  Replaces linear_kernel + tanh_fwd_kernel and tanh_bwd_kernel + a separate 64 -> D product.
 template <int D>
 __global__ void __launch_bounds__(256) layer1_fwd_kernel(const float* __restrict__ U, const float* __restrict__ W1, const float* __restrict__ b1,
                                                          float* __restrict__ Z, float* __restrict__ Hh, int64_t N) {
