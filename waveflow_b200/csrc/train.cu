@@ -1129,6 +1129,28 @@ void fill_wq_I(const wf_live_model* m, float* w) {
   w[0] = 0.f; w[P - 1] = 0.f;
 }
 
+// The weight gradients are off the critical path of the reverse pass (the adjoint chain head -> layer 3 -> tanh -> layer 2 ->
+// layer 1 -> next head never reads them), so they run on a second stream, forked and joined with events -- which a CUDA-graph
+// capture of the calling stream records as plain dependencies.  For large batches every kernel fills the GPU and nothing is
+// gained; for the shards of a multi-GPU step (6 k walkers per GPU at 8 GPUs) the step is a chain of 70 short kernels, and the
+// 24 weight-gradient launches overlap the chain.
+struct SideStream {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[6 * (WF_MAX_LAYERS + 1)] = {};
+  bool ok = false;
+};
+SideStream* side_stream() {
+  static SideStream ss[WF_MAX_DEVICES];
+  SideStream* a = &ss[current_device()];
+  if (!a->ok) {
+    if (cudaStreamCreateWithFlags(&a->stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    for (auto& e : a->ev)
+      if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    a->ok = true;
+  }
+  return a;
+}
+
 template <int D>
 int run_chunk(const wf_live_model* m, const wf_live_tables* t, const float* params, const float* protons, int n_protons,
               const float* x, int64_t N, float running_average, const float* ra_dev, float inv_n, float* grad, float* psi, float* hpsi,
@@ -1261,10 +1283,20 @@ int run_chunk(const wf_live_model* m, const wf_live_tables* t, const float* para
   if (!grad) return WF_OK;
 
   // ---------------- backward
+  SideStream* sd = side_stream();
+  if (!sd) return (int)cudaErrorUnknown;
+  cudaStream_t s2 = sd->stream;
+  int ne = 0;
+  // fork: s2 continues after everything issued on s so far; done: an event on s2 that s has to wait for later
+  auto fork = [&]() { cudaEvent_t e = sd->ev[ne++]; WF_CUDA(cudaEventRecord(e, s)); WF_CUDA(cudaStreamWaitEvent(s2, e, 0)); return WF_OK; };
+  auto done = [&](cudaEvent_t* out) { cudaEvent_t e = sd->ev[ne++]; WF_CUDA(cudaEventRecord(e, s2)); *out = e; return WF_OK; };
+  cudaEvent_t free_Obar = nullptr, free_HbA = nullptr, free_HbB = nullptr;      // s2 has finished reading the buffer (previous net)
   int cur = 0;
   for (int i = nn - 1; i >= 0; --i) {
     const int P = net_P(m, i), DP = D * P;
     float* Ucur = Ub[cur];
+    int st;
+    if (free_Obar) WF_CUDA(cudaStreamWaitEvent(s, free_Obar, 0));
     if (i == L) {
       pa.O = O[i]; pa.U = U[i];
       prior_bwd_kernel<D><<<hbw, HEAD_THREADS, 0, s>>>(pa, PHIbar, Obar, Ucur);
@@ -1273,26 +1305,39 @@ int run_chunk(const wf_live_model* m, const wf_live_tables* t, const float* para
       imade_bwd_kernel<D><<<hbw, HEAD_THREADS, 0, s>>>(ha, Ub[cur ^ 1], LDbar, Obar, Ucur);
     }
     WF_LAUNCH_CHECK();
-    int st;
+    // ---- layer 3: weight gradient on s2, input adjoint on s
+    if ((st = fork()) != WF_OK) return st;
     if (i == L) {
       // folded prior layer: gradient w.r.t. (Wf | bf) without a mask, then mapped back to (W3 | b3) through F^T and the MADE mask
-      WF_CUDA(cudaMemsetAsync(gWf, 0, sizeof(float) * (size_t)(HID + 1) * NcFp, s));   // gWf | gbf
-      if ((st = launch_wgrad(H2[i], Obar, partial, gWf, gbf, 0, D, R, HID, NcF, G, s)) != WF_OK) return st;
-      unfold_prior_grad_kernel<<<((HID + 1) * DP + 127) / 128, 128, 0, s>>>(gWf, gbf, t->ob_to_b, D, P, grad + off[i].W3, grad + off[i].b3);
+      WF_CUDA(cudaMemsetAsync(gWf, 0, sizeof(float) * (size_t)(HID + 1) * NcFp, s2));   // gWf | gbf
+      if ((st = launch_wgrad(H2[i], Obar, partial, gWf, gbf, 0, D, R, HID, NcF, G, s2)) != WF_OK) return st;
+      unfold_prior_grad_kernel<<<((HID + 1) * DP + 127) / 128, 128, 0, s2>>>(gWf, gbf, t->ob_to_b, D, P, grad + off[i].W3, grad + off[i].b3);
       WF_LAUNCH_CHECK();
-      if ((st = lin_bwd(Obar, Wf, iW3b[i], HbA, NcF, HID)) != WF_OK) return st;
     } else {
-      if ((st = launch_wgrad(H2[i], Obar, partial, grad + off[i].W3, grad + off[i].b3, 3, D, R, HID, DP, G, s)) != WF_OK) return st;
-      if ((st = lin_bwd(Obar, W3m[i], iW3b[i], HbA, DP, HID)) != WF_OK) return st;
+      if ((st = launch_wgrad(H2[i], Obar, partial, grad + off[i].W3, grad + off[i].b3, 3, D, R, HID, DP, G, s2)) != WF_OK) return st;
     }
+    if ((st = done(&free_Obar)) != WF_OK) return st;
+    if (free_HbA) WF_CUDA(cudaStreamWaitEvent(s, free_HbA, 0));
+    if (i == L) st = lin_bwd(Obar, Wf, iW3b[i], HbA, NcF, HID);
+    else st = lin_bwd(Obar, W3m[i], iW3b[i], HbA, DP, HID);
+    if (st != WF_OK) return st;
     tanh_bwd_kernel<D><<<(int)((nh + eb - 1) / eb), eb, 0, s>>>(Z2[i], HbA, N);
-    if ((st = launch_wgrad(H1[i], HbA, partial, grad + off[i].W2, grad + off[i].b2, 2, D, R, HID, HID, G, s)) != WF_OK) return st;
+    WF_LAUNCH_CHECK();
+    // ---- layer 2
+    if ((st = fork()) != WF_OK) return st;
+    if ((st = launch_wgrad(H1[i], HbA, partial, grad + off[i].W2, grad + off[i].b2, 2, D, R, HID, HID, G, s2)) != WF_OK) return st;
+    if ((st = done(&free_HbA)) != WF_OK) return st;
+    if (free_HbB) WF_CUDA(cudaStreamWaitEvent(s, free_HbB, 0));
     if ((st = lin_bwd(HbA, W2m[i], iW2b[i], HbB, HID, HID)) != WF_OK) return st;
     layer1_bwd_kernel<D><<<(int)((N * 16 + 255) / 256), 256, 0, s>>>(Z1[i], HbB, W1m[i], i > 0 ? Ucur : nullptr, N);
-    if ((st = launch_wgrad(U[i], HbB, partial, grad + off[i].W1, grad + off[i].b1, 1, D, R, D, HID, G, s)) != WF_OK) return st;
     WF_LAUNCH_CHECK();
+    // ---- layer 1
+    if ((st = fork()) != WF_OK) return st;
+    if ((st = launch_wgrad(U[i], HbB, partial, grad + off[i].W1, grad + off[i].b1, 1, D, R, D, HID, G, s2)) != WF_OK) return st;
+    if ((st = done(&free_HbB)) != WF_OK) return st;
     cur ^= 1;
   }
+  if (free_HbB) WF_CUDA(cudaStreamWaitEvent(s, free_HbB, 0));       // join: s2 is in order, its last event covers everything on it
   return WF_OK;
 }
 
