@@ -300,7 +300,12 @@ int64_t wf_vqmc_grad_workspace_floats(const wf_live_model* model_host, int64_t w
  * inv_n_total = 1 / (number of walkers over all ranks).  psi, hpsi, eloc [N] nullable; sums (nullable, double[4]) +=
  * {sum E, sum E^2, count, sum psi^2}.  The call loops over chunks sized to the workspace; deterministic summation.
  * running_average_dev (nullable, device float[1]) overrides running_average: the call then has no host-side inputs that
- * change from step to step, so a captured CUDA graph of it can be replayed. */
+ * change from step to step, so a captured CUDA graph of it can be replayed.
+ * Execution: chunks of >= 128 x SM-count jet rows (N (D+2)) run the 64-wide conditioner layers, their input adjoints and the
+ * weight gradients on tcgen05 (3xTF32, csrc/train_tc.cuh), smaller ones on CUDA-core GEMMs; a row's result does not depend on the
+ * chunking.  The weight-gradient kernels are issued on an internal second stream of the device, forked from and joined back into
+ * `stream` with events: everything is complete in `stream` order when the call returns, and a stream capture of `stream` records
+ * the whole call.  One call at a time per device (the second stream and the workspace are not re-entrant). */
 int wf_vqmc_loss_grad(const wf_live_model* model_host, const wf_live_tables* tables_host, const float* params,
                       const float* protons_host, int n_protons, const float* x, int64_t N, float running_average,
                       const float* running_average_dev, float inv_n_total, float* grad, float* psi, float* hpsi, float* eloc,
