@@ -245,6 +245,42 @@ def test_graphed_step_equals_eager_step(cuda):
     assert torch.allclose(res[0][0], res[1][0], rtol=1e-5, atol=1e-7)
 
 
+def test_graph_capture_of_the_tensor_core_path(cuda):
+    """A stream capture of wf_vqmc_loss_grad records the whole call -- including the weight-gradient kernels it issues on its internal
+    second stream (fork / join with events) -- and the replay is bit-identical to the eager call (deterministic summation)."""
+    from waveflow_b200 import _train
+    D = 4
+    m = fx.waveflow_model(D, coord="mean")
+    rng = np.random.default_rng(33)
+    spec = spec_from_live(m)
+    flat = _train.ravel(fx.cast_params(fx.random_params(rng, m), np.float32), cuda)
+    n = 3400                                             # 20 400 jet rows: the tcgen05 layers
+    x = torch.from_numpy(np.sort(rng.uniform(-5, 5, (n, D)), -1).astype(np.float32)).to(cuda)
+    prot = np.zeros((D, 1))
+    ws = torch.empty(_train.workspace_floats(spec, n, n), dtype=torch.float32, device=cuda)
+    g_eager = torch.zeros_like(flat)
+    s_eager = torch.zeros(4, dtype=torch.float64, device=cuda)
+    _train.loss_grad(spec, flat, x, prot, 0.3, grad=g_eager, sums=s_eager, ws=ws)
+    g = torch.zeros_like(flat)
+    sums = torch.zeros(4, dtype=torch.float64, device=cuda)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        _train.loss_grad(spec, flat, x, prot, 0.3, grad=g, sums=sums, ws=ws)
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        _train.loss_grad(spec, flat, x, prot, 0.3, grad=g, sums=sums, ws=ws)
+    for _ in range(3):
+        g.zero_(); sums.zero_()
+        graph.replay()
+    torch.cuda.synchronize()
+    assert torch.isfinite(g).all() and float(g.abs().max()) > 0
+    assert torch.equal(g, g_eager)
+    assert torch.allclose(sums, s_eager, rtol=1e-12, atol=0)     # block sums are added with float64 atomics: order-dependent last bits
+
+
 def test_loss_grad_edge_cases(cuda):
     """Empty and single-walker batches, forward-only mode, and a model outside the supported set."""
     from waveflow_b200 import _train
