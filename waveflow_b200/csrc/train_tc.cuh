@@ -1,11 +1,12 @@
 // Tensor-core GEMMs of the training step (train.cu): the conditioner layers of the layer-wise jet formulation are plain
 // [rows, K] x [K, N] products over rows = (walker, jet component), HBM bound once the FLOPs are off the CUDA cores
-// (200 B of traffic per row and 64-wide layer against 16 kFLOP).
+// (512 B of traffic per row of a 64-wide layer against 8 kFLOP).  Reference: the stax.serial(Dense, Tanh, Dense, Tanh, Dense)
+// conditioners of model_factory.py:21-35 under value_and_grad(loss_fn_efficient), vqmc.py:193-221.
 //
 //   lin_tc_kernel<KP, NT>:  C[R][Nc] = A[R][Kc] * B (+ bias on the value rows),  Kc <= 64 KP,  Nc <= NT
 //
-// One CTA per SM, split into independent TEAMS of 128 threads (one tile of 128 rows each, out of phase with one another so
-// that one team's global loads overlap another's MMAs and stores).  Per tile and 64-wide k-part a team
+// One CTA per SM, split into independent TEAMS of 128 threads (one tile of 128 rows each; they take turns on the tensor pipe,
+// see the ticket in the kernel).  Per tile and 64-wide k-part a team
 //   * reads its rows with coalesced 128-bit loads (thread t owns 16-byte unit t + 128 j of the row-major tile),
 //   * splits every value into two TF32-exact planes (hi = rna(a), lo = a - hi) and stores them as the K-major
 //     SWIZZLE_128B operand image the tensor core reads (row r of k-block b at b 16 KB + r 128 B, 16-byte units XOR (r & 7);
