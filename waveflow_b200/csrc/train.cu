@@ -1248,7 +1248,7 @@ int run_chunk(const wf_live_model* m, const wf_live_tables* t, const float* para
   pa.cons_hi = m->coord_mean ? D - 1 : D;
 
   const int eb = 256;
-  const int64_t nh = N * HID, nd = N * D;
+  const int64_t nh = N * HID;
   const int hbw = (int)((N * 32 + HEAD_THREADS - 1) / HEAD_THREADS);   // spline heads: one warp per walker
 
   // ---------------- forward
