@@ -4,9 +4,13 @@ Line-by-line numpy restatement of flows/bijections/neural_splines.py (vendored, 
 uses the removed jax.ops API), including its quirks: softmax/softplus applied twice by the
 coupling layer (Q7), `+1e-6` on the last knot in searchsorted, identity tails.
 
-PARITY UNPINNED: the reference has no runnable test or golden vector for this path (its only test,
-tests/test_bijections.py:136-138, imports a non-existent package).  Pins available: the bijectivity
-property (inverse(direct(x)) == x) and the analytic derivative check in tests/test_oracle_rqs.py.
+PINNED BY THE REFERENCE'S OWN SOURCE: the reference holds no runnable test or golden vector for this path (its only test,
+tests/test_bijections.py:136-138, imports a non-existent package) and JAX cannot be installed here, but the file needs array
+primitives only: tests/golden/make_rqs_golden.py executes the unmodified neural_splines.py on a numpy stand-in for its jax
+imports (float32 "x64 disabled" dtype rules) and stores inputs, layer weights, bin indices, knots and outputs in
+tests/golden/ref_rqs_vectors.npz.  tests/test_rqs_reference_vectors.py: every bin index equal (forward and inverse), knots within
+a few float32 ulp (> 50 % bit-identical), values float32-grade, coupling layer to 4e-6.  What the stand-in cannot reproduce is
+XLA's own float32 exp and reduction order.  Further pins: bijectivity and the analytic derivative check in tests/test_oracle_rqs.py.
 """
 from __future__ import annotations
 

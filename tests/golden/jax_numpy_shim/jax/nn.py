@@ -1,0 +1,15 @@
+"""jax.nn.softmax / softplus / relu as JAX defines them (jax/_src/nn/functions.py), on numpy float32."""
+import numpy as _np
+
+
+def softmax(x, axis=-1):
+    unnormalized = _np.exp(x - x.max(axis=axis, keepdims=True))
+    return unnormalized / unnormalized.sum(axis=axis, keepdims=True)
+
+
+def softplus(x):
+    return _np.logaddexp(x, _np.zeros((), dtype=x.dtype))
+
+
+def relu(x):
+    return _np.maximum(x, _np.zeros((), dtype=x.dtype))

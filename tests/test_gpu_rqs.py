@@ -120,3 +120,25 @@ def test_rqs_argument_errors(cuda):
     out, lad = unconstrained_RQS(torch.zeros(0, device=cuda), torch.zeros(0, 8, device=cuda), torch.zeros(0, 8, device=cuda),
                                  torch.zeros(0, 7, device=cuda))
     assert out.shape == (0,)
+
+
+@pytest.mark.parametrize("tag", ["op_k8", "op_k32", "op_k32_mild", "op_k5"])
+def test_rqs_against_vectors_from_the_reference_source(cuda, tag):
+    """wf_rqs_apply against tests/golden/ref_rqs_vectors.npz -- inputs, bin indices and outputs produced by the reference's own
+    neural_splines.py executed on a numpy stand-in for its jax imports (tests/golden/make_rqs_golden.py).  Exact-bin mode: every
+    bin index the reference computed, forward and inverse; values float32-grade with the reference vector as the yardstick."""
+    from pathlib import Path
+    G = np.load(Path(__file__).resolve().parent / "golden" / "ref_rqs_vectors.npz")
+    uw, uh, ud, B = G[tag + "_uw"], G[tag + "_uh"], G[tag + "_ud"], float(G[tag + "_B"])
+    d64 = lambda a: a.astype(np.float64)
+    for inverse, xin, ins, bk, yk, lk in ((False, G[tag + "_x"], G[tag + "_inside"], "_bins_fwd", "_y", "_ld"),
+                                          (True, G[tag + "_y"], G[tag + "_inside_inv"], "_bins_inv", "_xi", "_ldi")):
+        out, lad, bins = _run(cuda, xin, uw, uh, ud, inverse, B, exact_bins=True)
+        assert np.array_equal(bins[ins], G[tag + bk]), (tag, inverse, int((bins[ins] != G[tag + bk]).sum()))
+        assert np.all(bins[~ins] == -1) and np.array_equal(out[~ins], xin[~ins]) and np.all(lad[~ins] == 0)
+        o64, l64 = orqs.unconstrained_rqs(d64(xin), d64(uw), d64(uh), d64(ud), inverse, B)
+        assert_fp32_grade(out[ins], o64[ins], G[tag + yk][ins], 1e-5, B, f"rqs vs reference source {tag} inv={inverse} outputs")
+        assert_fp32_grade(lad[ins], l64[ins], G[tag + lk][ins], 1e-5, 1.0, f"rqs vs reference source {tag} inv={inverse} logabsdet",
+                          max_slack=8.0)
+        _, _, fast = _run(cuda, xin, uw, uh, ud, inverse, B)
+        assert np.mean(fast[ins] != G[tag + bk]) < 2e-3          # default (ex2.approx) path: may differ only next to a knot
