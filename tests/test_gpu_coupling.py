@@ -111,3 +111,29 @@ def test_tc_coupling_flow_config5(cuda):
     # chunked execution (workspace smaller than the batch) gives identical results
     y2, ld2 = coupling_flow_tc(w, L, torch.from_numpy(x).to(cuda), B, chunk_rows=256)
     assert torch.equal(y, y2) and torch.equal(ld, ld2)
+
+
+@pytest.mark.parametrize("tag", ["cpl_d2", "cpl_d8"])
+def test_coupling_layer_against_vectors_from_the_reference_source(cuda, tag):
+    """The fused coupling kernel against NeuralSplineCoupling.direct_fun / inverse_fun of the reference's own neural_splines.py
+    (executed on a numpy stand-in for its jax imports, tests/golden/make_rqs_golden.py), with the weights that layer created."""
+    from pathlib import Path
+    from waveflow_b200.flows.neural_splines import coupling_flow
+    G = np.load(Path(__file__).resolve().parent / "golden" / "ref_rqs_vectors.npz")
+    f = lambda w: [(G[f"{tag}_{w}_W{i}"], G[f"{tag}_{w}_b{i}"]) for i in range(3)]
+    K, B, hidden = int(G[tag + "_K"]), float(G[tag + "_B"]), int(G[tag + "_hidden"])
+    layers = [(f("f1"), f("f2"))]
+    tl = [(_to_stax(f("f1"), cuda), _to_stax(f("f2"), cuda))]
+    l64 = [tuple([(W.astype(np.float64), b.astype(np.float64)) for W, b in net] for net in layers[0])]
+    x = G[tag + "_x"]
+    y, ld = coupling_flow(tl, torch.from_numpy(x).to(cuda), K, B, hidden)
+    ry, rld = orqs.coupling_flow_direct(l64, x.astype(np.float64), K, B)
+    assert_fp32_grade(y.cpu().numpy(), ry, G[tag + "_y"], 1e-5, B, f"coupling vs reference source {tag} outputs", max_slack=8.0)
+    assert_fp32_grade(ld.cpu().numpy(), rld, G[tag + "_ld"], 1e-5, 1.0, f"coupling vs reference source {tag} log_det", max_slack=8.0)
+    assert np.abs(y.cpu().numpy() - G[tag + "_y"]).max() <= 2e-5 * B
+    yin = G[tag + "_y"]
+    xi, ldi = coupling_flow(tl, torch.from_numpy(yin).to(cuda), K, B, hidden, inverse=True)
+    rx, rldi = orqs.coupling_flow_inverse(l64, yin.astype(np.float64), K, B)
+    assert_fp32_grade(xi.cpu().numpy(), rx, G[tag + "_xi"], 1e-5, B, f"coupling vs reference source {tag} inverse", max_slack=8.0)
+    assert_fp32_grade(ldi.cpu().numpy(), rldi, G[tag + "_ldi"], 1e-5, 1.0, f"coupling vs reference source {tag} inverse log_det",
+                      max_slack=8.0)
