@@ -6,8 +6,11 @@ square-normalised Waveflow wavefunction.  Each function cites the reference line
 (paths relative to /root/reference/waveflow).  ``dtype`` selects float32 (the reference's default,
 JAX x64 disabled) or float64 (used as the high-precision yardstick in parity tests).
 
-Pinned by: tests/golden/ref_tables_deg5_k16.npz (shipped basis tables, bit-exact) and
-tests/golden/he_checkpoint_epoch100000.npz (published parameters + psi grids) -- see tests/test_oracle_golden.py.
+Pinned by: tests/golden/ref_tables_deg5_k16.npz (shipped basis tables, bit-exact), tests/golden/he_checkpoint_epoch100000.npz
+(published parameters + psi grids) -- see tests/test_oracle_golden.py -- and, for the spline operators (remove_bias,
+enforce_boundary_conditions, apply / apply_grad, bisection), tests/golden/ref_spline_vectors.npz: outputs of the reference's OWN
+isplines_jax.py / bsplines_jax.py / helpers.binary_search executed on a numpy stand-in for jax (tests/golden/make_spline_golden.py),
+reproduced bit for bit in float32 (tests/test_spline_reference_vectors.py).
 """
 from __future__ import annotations
 

@@ -13,3 +13,11 @@ def softplus(x):
 
 def relu(x):
     return _np.maximum(x, _np.zeros((), dtype=x.dtype))
+
+
+def one_hot(i, n, dtype=_np.float32):
+    return (_np.arange(n) == i).astype(dtype)
+
+
+def sigmoid(x):
+    return 1 / (1 + _np.exp(-x))

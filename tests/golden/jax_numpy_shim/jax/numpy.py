@@ -1,6 +1,8 @@
 """jax.numpy on numpy with JAX's default (x64 disabled) dtype canonicalisation: float64 -> float32 on the way in and out."""
 import numpy as _np
 
+from ._core import JArr as _JArr, jarr as _jarr
+
 float32 = _np.float32
 int32 = _np.int32
 newaxis = None
@@ -16,7 +18,9 @@ def _canon(x):
     if isinstance(x, _np.floating):
         return _np.float32(x)
     if isinstance(x, _np.ndarray) and x.dtype == _np.float64:
-        return x.astype(_np.float32)
+        return _jarr(x.astype(_np.float32))
+    if isinstance(x, _np.ndarray):
+        return _jarr(x)
     if isinstance(x, (list, tuple)) and x and all(isinstance(v, _np.ndarray) for v in x):
         return type(x)(_canon(v) for v in x)
     return x
@@ -33,11 +37,11 @@ def _wrap(fn):
 
 
 def zeros(shape, dtype=None):
-    return _np.zeros(shape, dtype=_np.float32 if dtype is None else dtype)
+    return _jarr(_np.zeros(shape, dtype=_np.float32 if dtype is None else dtype))
 
 
 def ones(shape, dtype=None):
-    return _np.ones(shape, dtype=_np.float32 if dtype is None else dtype)
+    return _jarr(_np.ones(shape, dtype=_np.float32 if dtype is None else dtype))
 
 
 def array(x, dtype=None):

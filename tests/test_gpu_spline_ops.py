@@ -200,3 +200,30 @@ def test_empty_and_ragged_batches(cuda):
         if M:
             ref = live.spline_apply(tabs.tab32, c, x, 0)
             assert relerr(v.cpu().numpy(), ref, 1.0) < 1e-6
+
+
+def test_spline_operators_against_vectors_from_the_reference_source(cuda):
+    """The C-ABI spline operators (through the ISpline_fun / BSpline_fun mirrors) against tests/golden/ref_spline_vectors.npz:
+    outputs of the reference's own isplines_jax.py / bsplines_jax.py / helpers.binary_search executed on a numpy stand-in for
+    jax (tests/golden/make_spline_golden.py) on the reference's shipped tables (degree 5, 16 internal knots)."""
+    from pathlib import Path
+    from waveflow_b200.splines.factories import BSpline_fun, ISpline_fun
+    G = np.load(Path(__file__).resolve().parent / "golden" / "ref_spline_vectors.npz")
+    k, n, T, tol = int(G["k"]), int(G["n_internal"]), int(G["T"]), float(G["tol"])
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(cuda)
+    _, apply_v, apply_g, reverse_v, _, enforce_bc, remove_bias = ISpline_fun()(
+        0, k, n, zero_border=False, n_mesh_points=T, cached_bases_path_root=None, reverse_fun_tol=tol,
+        constraints_dict_left={0: 0.0}, constraints_dict_right={0: 1.0})
+    assert relerr(remove_bias(t(G["raw"])).cpu().numpy(), G["remove_bias"], 1.0) < 5e-7
+    assert relerr(enforce_bc(t(G["remove_bias"])).cpu().numpy(), G["enforce_bc"], np.abs(G["enforce_bc"]).max()) < 2e-6
+    c = t(G["enforce_bc"])
+    assert relerr(apply_v(c, t(G["x"])).cpu().numpy(), G["apply"], 1.0) < 1e-6
+    assert relerr(apply_g(c, t(G["x"])).cpu().numpy(), G["apply_grad"], np.abs(G["apply_grad"]).max()) < 1e-6
+    xr = reverse_v(c, t(G["apply"])).cpu().numpy()
+    assert np.mean(xr == G["reverse"]) > 0.98 and np.abs(xr - G["reverse"]).max() <= 2 * tol
+    _, b_apply, b_grad, _, _, b_bc = BSpline_fun()(0, k, n, n_mesh_points=T, cached_bases_path_root=None,
+                                                  constraints_dict_left={0: 0, 2: 0}, constraints_dict_right={0: 0})
+    assert relerr(b_bc(t(G["B_raw"])).cpu().numpy(), G["B_enforce_bc"], np.abs(G["B_enforce_bc"]).max()) < 2e-6
+    cb = t(G["B_enforce_bc"])
+    assert relerr(b_apply(cb, t(G["B_x"])).cpu().numpy(), G["B_apply"], np.abs(G["B_apply"]).max()) < 3e-6
+    assert relerr(b_grad(cb, t(G["B_x"])).cpu().numpy(), G["B_apply_grad"], np.abs(G["B_apply_grad"]).max()) < 3e-6
