@@ -12,9 +12,12 @@ of lookup(nd) w.r.t. its argument is lookup(nd+1), and table index 4 clamps to 3
 quirk Q5) -- the parameter gradient is the only place that clamp is reachable.
 
 ``loss_and_grad`` takes three reverse passes through oracle/laplacian.py::autograd_psi_lap in float64.
-Parity unpinned by the reference (no stored gradients anywhere); the pins are the oracle chain
-psi-KAT -> two agreeing Laplacian oracles -> this function, plus a finite-difference check of the surrogate on the
-parameters whose gradient does not pass through a table argument (tests/test_oracle_golden.py).
+PINNED BY THE REFERENCE'S OWN SOURCE: no gradients are stored anywhere upstream, but
+tests/golden/make_energy_golden.py evaluates the unmodified vqmc.loss_fn_efficient -- including the estimator it registers with
+custom_jvp -- on parameters seeded with dual numbers (numpy stand-in for jax, float64): the loss value and <grad loss, v> for two
+random parameter directions v agree with ``loss_and_grad`` to 1e-12 (tests/test_energy_reference_vectors.py).  Further pins:
+the chain psi-KAT -> Laplacian oracles -> this function, and a finite-difference check of the surrogate on the parameters
+whose gradient does not pass through a table argument (tests/test_oracle_golden.py).
 """
 from __future__ import annotations
 

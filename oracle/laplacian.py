@@ -10,8 +10,13 @@ table lookup through its custom_jvp: d/dx lookup(nd) := lookup(nd+1) (splines/is
 * ``local_energy_autograd`` torch float64 double reverse-mode autodiff of the restated psi, where the table lookup
   is an autograd.Function whose backward is the lookup in table nd+1 (what jax.hessian sees).
 
-Parity unpinned by the reference (no stored H psi anywhere): these two agreeing with each other, the
-psi KAT, and the published energy plateau are the pins.
+PINNED BY THE REFERENCE'S OWN SOURCE: the reference stores no H psi anywhere and JAX cannot be installed here,
+but tests/golden/make_energy_golden.py executes the unmodified model_factory -> wavefunctions.Waveflow -> flows -> isplines_jax /
+bsplines_jax -> utils/physics.construct_hamiltonian_function on a numpy stand-in for jax (float64): jax.hessian becomes forward
+over forward mode with nested, level-tagged dual numbers carried through the reference's own arithmetic, and every table lookup
+on a dual number applies the custom_jvp rule the reference registered, at both levels.  Both restatements reproduce the stored
+psi / log_pdf / H psi to 1e-12 for a D = 2 ('mean' coordinates) and a D = 3 ('first') model (tests/test_energy_reference_vectors.py).
+Further pins: the two restatements agree with each other, the psi KAT, the published energy plateau.
 """
 from __future__ import annotations
 

@@ -1,6 +1,11 @@
 """Array wrapper with jax's functional `.at[...]` updates, a one-level dual number for `grad` of scalar functions, and the
 function transformations the reference's spline modules use (jit, vmap, grad, custom_jvp).  Test infrastructure (see README.md)."""
+import math as _math
+import os as _os
+
 import numpy as _np
+
+X64 = _os.environ.get("JAX_SHIM_X64", "0") == "1"        # float64 everywhere (jax_enable_x64): used for the local-energy vectors
 
 
 class _At:
@@ -19,9 +24,9 @@ class _At:
 
             @staticmethod
             def add(v):
-                out = _np.array(arr, copy=True).view(JArr)
-                out[idx] += v
-                return out
+                out = _np.array(arr, copy=True)
+                out[idx] = out[idx] + v
+                return out.view(JArr)
 
         return _Upd
 
@@ -35,6 +40,12 @@ class JArr(_np.ndarray):
     def at(self):
         return _At(self)
 
+    # jax arrays are immutable: `a += b` rebinds the name to a new array (and may change its dtype)
+    def __iadd__(self, o): return self + o
+    def __isub__(self, o): return self - o
+    def __imul__(self, o): return self * o
+    def __itruediv__(self, o): return self / o
+
     def __array_ufunc__(self, ufunc, method, *inputs, out=None, **kwargs):
         args = [i.view(_np.ndarray) if isinstance(i, JArr) else i for i in inputs]
         if out is not None:
@@ -45,7 +56,7 @@ class JArr(_np.ndarray):
 
         def fix(r):
             r = _np.asarray(r)
-            if r.dtype == _np.float64:
+            if r.dtype == _np.float64 and not X64:
                 r = r.astype(_np.float32)
             return r.view(JArr)
         return tuple(fix(r) for r in res) if isinstance(res, tuple) else fix(res)
@@ -55,43 +66,148 @@ def jarr(x):
     return x.view(JArr) if isinstance(x, _np.ndarray) and not isinstance(x, JArr) else x
 
 
+def _unbox(a):
+    """0-d object arrays (what vmap hands out) -> the element itself."""
+    if isinstance(a, _np.ndarray) and a.dtype == object and a.ndim == 0:
+        return a.item()
+    return a
+
+
+def _f(name, v):
+    """elementary function on a plain number or a (nested) Dual"""
+    return getattr(v, name)() if isinstance(v, Dual) else getattr(_math, name)(float(v))
+
+
+_TAG = [0]
+
+
+def new_tag():
+    _TAG[0] += 1
+    return _TAG[0]
+
+
 class Dual:
-    """value + tangent of a scalar (first-order forward mode): what `grad(f, argnums)` of a scalar function needs."""
+    """value + tangent along ONE direction (forward mode), with a TAG that names the differentiation level it belongs to.
+    Components may be Duals of lower tags, which nests the modes (forward over forward: second derivatives).  In a binary
+    operation the operand of the lower tag is a constant with respect to the higher one (no perturbation confusion: the
+    `grad` inside the reference's apply_fun_vec_grad runs under the outer levels of `hessian`).  Arithmetic and the elementary
+    functions are generic over the nesting; a `custom_jvp` function called on a Dual applies the rule the reference registered."""
     __array_ufunc__ = None          # numpy scalars / arrays defer to the reflected operators below
+    __array_priority__ = 1000
 
-    def __init__(self, v, t):
-        self.v, self.t = v, t
+    def __init__(self, v, t, tag):
+        self.v, self.t, self.tag = v, t, tag
 
-    @staticmethod
-    def _vt(o):
-        return (o.v, o.t) if isinstance(o, Dual) else (o, 0.0)
+    def _vt(self, o):
+        """(value, tangent) of the other operand AT THIS LEVEL, or None if the other operand lives on a higher level."""
+        o = _unbox(o)
+        if isinstance(o, Dual):
+            if o.tag == self.tag:
+                return o.v, o.t
+            if o.tag > self.tag:
+                return None
+        return o, 0.0
 
     def __add__(self, o):
-        v, t = Dual._vt(o)
-        return Dual(self.v + v, self.t + t)
+        vt = self._vt(o)
+        if vt is None:
+            return _unbox(o).__radd__(self)
+        return Dual(self.v + vt[0], self.t + vt[1], self.tag)
 
     __radd__ = __add__
 
     def __sub__(self, o):
-        v, t = Dual._vt(o)
-        return Dual(self.v - v, self.t - t)
+        vt = self._vt(o)
+        if vt is None:
+            return _unbox(o).__rsub__(self)
+        return Dual(self.v - vt[0], self.t - vt[1], self.tag)
 
     def __rsub__(self, o):
-        v, t = Dual._vt(o)
-        return Dual(v - self.v, t - self.t)
+        vt = self._vt(o)
+        if vt is None:
+            return _unbox(o).__sub__(self)
+        return Dual(vt[0] - self.v, vt[1] - self.t, self.tag)
 
     def __mul__(self, o):
-        v, t = Dual._vt(o)
-        return Dual(self.v * v, self.t * v + self.v * t)
+        vt = self._vt(o)
+        if vt is None:
+            return _unbox(o).__rmul__(self)
+        v, t = vt
+        return Dual(self.v * v, self.t * v + self.v * t, self.tag)
 
     __rmul__ = __mul__
 
     def __truediv__(self, o):
-        v, t = Dual._vt(o)
-        return Dual(self.v / v, (self.t * v - self.v * t) / (v * v))
+        vt = self._vt(o)
+        if vt is None:
+            return _unbox(o).__rtruediv__(self)
+        v, t = vt
+        return Dual(self.v / v, (self.t * v - self.v * t) / (v * v), self.tag)
+
+    def __rtruediv__(self, o):
+        vt = self._vt(o)
+        if vt is None:
+            return _unbox(o).__truediv__(self)
+        v, t = vt
+        return Dual(v / self.v, (t * self.v - v * self.t) / (self.v * self.v), self.tag)
 
     def __neg__(self):
-        return Dual(-self.v, -self.t)
+        return Dual(-self.v, -self.t, self.tag)
+
+    def __pos__(self):
+        return self
+
+    def __abs__(self):
+        return self if self >= 0 else -self
+
+    def __pow__(self, n):
+        if isinstance(n, (int, _np.integer)) and n >= 0:
+            out = 1.0
+            for _ in range(int(n)):
+                out = out * self
+            return out
+        if float(n) == 0.5:
+            return self.sqrt()
+        return (self.log() * float(n)).exp()
+
+    # comparisons act on the primal value (the branch taken), as in jax
+    def _p(self):
+        v = self.v
+        while isinstance(v, Dual):
+            v = v.v
+        return v
+
+    @staticmethod
+    def _pv(o):
+        o = _unbox(o)
+        return o._p() if isinstance(o, Dual) else o
+
+    def __lt__(self, o): return self._p() < Dual._pv(o)
+    def __le__(self, o): return self._p() <= Dual._pv(o)
+    def __gt__(self, o): return self._p() > Dual._pv(o)
+    def __ge__(self, o): return self._p() >= Dual._pv(o)
+    def __eq__(self, o): return self._p() == Dual._pv(o)
+    def __ne__(self, o): return self._p() != Dual._pv(o)
+    __hash__ = None
+
+    # numpy ufuncs on object arrays call the method of the same name
+    def exp(self):
+        e = _f("exp", self.v)
+        return Dual(e, e * self.t, self.tag)
+
+    def log(self):
+        return Dual(_f("log", self.v), self.t / self.v, self.tag)
+
+    def sqrt(self):
+        r = _f("sqrt", self.v)
+        return Dual(r, self.t / (2.0 * r), self.tag)
+
+    def tanh(self):
+        th = _f("tanh", self.v)
+        return Dual(th, (1.0 - th * th) * self.t, self.tag)
+
+    def conjugate(self):
+        return self
 
 
 def jit(fn=None, **kwargs):
@@ -117,9 +233,11 @@ def grad(fn, argnums=0):
     def g(*args):
         a = list(args)
         x = a[argnums]
-        a[argnums] = Dual(x, _np.float32(1.0))
-        out = fn(*a)
-        return out.t if isinstance(out, Dual) else _np.float32(0.0) * x
+        x = _unbox(x)
+        tag = new_tag()
+        a[argnums] = Dual(x, 1.0 if X64 else _np.float32(1.0), tag)
+        out = _unbox(fn(*a))
+        return out.t if isinstance(out, Dual) and out.tag == tag else (0.0 if X64 else _np.float32(0.0)) * x
     return g
 
 
@@ -138,17 +256,84 @@ class custom_jvp:
         import inspect
         bound = inspect.signature(self.fn).bind(*args, **kwargs)      # as jax does: defaults and keywords become positional
         bound.apply_defaults()
-        args = tuple(bound.arguments.values())
-        if any(isinstance(a, Dual) for a in args):
-            primals = tuple(a.v if isinstance(a, Dual) else a for a in args)
-            tangents = tuple(a.t if isinstance(a, Dual) else 0.0 for a in args)
+        args = tuple(_unbox(a) for a in bound.arguments.values())
+        if any(isinstance(a, _np.ndarray) and a.dtype == object for a in args):
+            return self._call_arrays(args)
+        tags = [a.tag for a in args if isinstance(a, Dual)]
+        if tags:
+            tag = max(tags)                              # differentiate the outermost level; lower levels ride along as values
+            top = lambda a: isinstance(a, Dual) and a.tag == tag
+            primals = tuple(a.v if top(a) else a for a in args)
+            tangents = tuple(a.t if top(a) else 0.0 for a in args)
             out, t = self.rule(primals, tangents)
-            return Dual(out, t)
+            return Dual(out, t, tag)
         return self.fn(*args)
 
 
-def hessian(*a, **k):
-    raise NotImplementedError("second-order transformations are outside this stand-in")
+def _custom_jvp_call_arrays(self, args):
+    """array arguments holding Duals (the loss estimator of vqmc.py): the rule sees primal and tangent ARRAYS of the top level"""
+    flat = [e for a in args if isinstance(a, _np.ndarray) and a.dtype == object for e in a.reshape(-1) if isinstance(e, Dual)]
+    if not flat:
+        return self.fn(*args)
+    tag = max(e.tag for e in flat)
+    top = lambda e: isinstance(e, Dual) and e.tag == tag
+
+    def split(a):
+        if isinstance(a, _np.ndarray) and a.dtype == object:
+            p = _np.empty(a.shape, dtype=object)
+            t = _np.empty(a.shape, dtype=object)
+            for idx in _np.ndindex(a.shape):
+                e = a[idx]
+                p[idx], t[idx] = (e.v, e.t) if top(e) else (e, 0.0)
+            return p.view(JArr), t.view(JArr)
+        return a, (_np.zeros_like(a) if isinstance(a, _np.ndarray) else 0.0)
+
+    pt = [split(a) for a in args]
+    out, tan = self.rule(tuple(p for p, _ in pt), tuple(t for _, t in pt))
+    out, tan = _np.asarray(out, dtype=object), _np.asarray(tan, dtype=object)
+    res = _np.empty(out.shape, dtype=object)
+    for idx in _np.ndindex(out.shape):
+        res[idx] = Dual(out[idx], tan[idx], tag)
+    return res.view(JArr)
+
+
+custom_jvp._call_arrays = _custom_jvp_call_arrays
+
+
+def value_and_grad(*a, **k):
+    raise NotImplementedError("reverse mode is outside this stand-in (directional derivatives: seed the parameters with Duals)")
+
+
+def tree_map(f, tree):
+    if isinstance(tree, (tuple, list)):
+        return type(tree)(tree_map(f, t) for t in tree)
+    return f(tree)
+
+
+def hessian(fn, argnums=0):
+    """jax.hessian for a vector argument: H[..., i, j] = d2 out / dx_i dx_j by forward over forward mode (nested Duals): the
+    outer level carries e_j, the inner one e_i; custom_jvp rules are applied at both levels, as jacfwd(jacfwd) would."""
+    def h(*args):
+        x = _np.asarray(args[argnums])
+        D = x.shape[0]
+        t1, t2 = new_tag(), new_tag()
+        rows = []
+        for i in range(D):
+            cols = []
+            for j in range(D):
+                xo = _np.empty(D, dtype=object)
+                for k in range(D):
+                    xo[k] = Dual(Dual(x[k].item(), 1.0 if k == i else 0.0, t1), Dual(1.0 if k == j else 0.0, 0.0, t1), t2)
+                a = list(args)
+                a[argnums] = xo.view(JArr)
+                out = _np.asarray(fn(*a), dtype=object).reshape(-1)
+                cols.append([o.t.t if isinstance(o, Dual) and o.tag == t2 and isinstance(o.t, Dual) and o.t.tag == t1 else 0.0
+                             for o in out])
+            rows.append(cols)
+        plain = not any(isinstance(e, Dual) for r in rows for c in r for e in c)
+        H = _np.array(rows, dtype=_np.float64 if plain else object)      # [i, j, out] (Duals of lower levels stay objects)
+        return jarr(_np.moveaxis(H, -1, 0))                               # [out, i, j]
+    return h
 
 
 class _Config:

@@ -1,1 +1,1 @@
-from . import stax  # noqa: F401
+from . import stax, optimizers  # noqa: F401

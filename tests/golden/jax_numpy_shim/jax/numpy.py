@@ -1,7 +1,7 @@
 """jax.numpy on numpy with JAX's default (x64 disabled) dtype canonicalisation: float64 -> float32 on the way in and out."""
 import numpy as _np
 
-from ._core import JArr as _JArr, jarr as _jarr
+from ._core import JArr as _JArr, jarr as _jarr, X64 as _X64
 
 float32 = _np.float32
 int32 = _np.int32
@@ -11,6 +11,8 @@ ndarray = _np.ndarray
 
 
 def _canon(x):
+    if _X64:
+        return _jarr(x) if isinstance(x, _np.ndarray) else x
     if isinstance(x, (bool, int, _np.integer, _np.bool_)):
         return x
     if isinstance(x, float):
@@ -36,12 +38,15 @@ def _wrap(fn):
     return f
 
 
+_DEFAULT = _np.float64 if _X64 else _np.float32
+
+
 def zeros(shape, dtype=None):
-    return _jarr(_np.zeros(shape, dtype=_np.float32 if dtype is None else dtype))
+    return _jarr(_np.zeros(shape, dtype=_DEFAULT if dtype is None else dtype))
 
 
 def ones(shape, dtype=None):
-    return _jarr(_np.ones(shape, dtype=_np.float32 if dtype is None else dtype))
+    return _jarr(_np.ones(shape, dtype=_DEFAULT if dtype is None else dtype))
 
 
 def array(x, dtype=None):

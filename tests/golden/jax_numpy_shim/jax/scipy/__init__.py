@@ -1,1 +1,1 @@
-from . import special  # noqa: F401
+from . import special, linalg, stats  # noqa: F401
