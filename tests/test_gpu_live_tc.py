@@ -144,3 +144,22 @@ def test_tc_he_checkpoint_psi_kat(cuda):
     tc = _live.forward(spec, w, torch.from_numpy(x).to(cuda), want=("psi",), mode="tc")["psi"].cpu().numpy()
     r64 = live.psi(m, params, x.astype(np.float64))
     assert np.abs(tc - r64).max() <= 2e-5 * np.abs(r64).max()
+
+
+@pytest.mark.parametrize("mode", ["tc", "simt"])
+def test_mflow_logpdf_against_vectors_from_the_reference_source(cuda, mode):
+    """BASELINE configs[0]: the fused forward kernels (both weight layouts) against MFlow.log_pdf of the reference's own source
+    files executed on a numpy stand-in for jax (tests/golden/make_mflow_golden.py): float64 vector as the truth, the reference's
+    float32 vector as the yardstick."""
+    from waveflow_b200 import _live
+    from tests.test_mflow_reference_vectors import G, mflow_model, mflow_params
+    m = mflow_model(np.float64)
+    spec = spec_from_live(m)
+    w = _pack(spec, mflow_params(np.float32), cuda)
+    x = G["f32_x"]
+    assert np.array_equal(x.astype(np.float64).astype(np.float32), x) and np.abs(G["f64_x"] - x).max() < 1e-7
+    out = _live.forward(spec, w, torch.from_numpy(x).to(cuda), want=("logpdf", "u"), mode=mode)
+    # the float64 vector was evaluated at the float64 inputs (x rounded to float32 moves log_pdf by < 1e-6): truth at x itself
+    r64 = live.log_pdf(m, mflow_params(np.float64), x.astype(np.float64))
+    assert_fp32_grade(out["logpdf"].cpu().numpy(), r64, G["f32_logpdf"], 1e-5, 1.0, f"{mode} MFlow.log_pdf vs reference source")
+    assert np.abs(out["u"].cpu().numpy() - G["f32_u"]).max() <= 2e-6
