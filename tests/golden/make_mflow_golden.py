@@ -61,7 +61,27 @@ def run(mode):
     x = rng.uniform(0.02, 0.98, (256, D))
     x = x.astype(np.float32) if mode == "f32" else x
     lp, u = log_pdf(params, x, return_sample=True)
-    out = {"x": np.asarray(x), "logpdf": np.asarray(lp), "u": np.asarray(u), "treedef": np.array(json.dumps(structure(params))),
+    # the inverse direction (sampling path) of the same flow: Serial(IMADE, Reverse).inverse_fun -- IMADE's inverse is the vmapped
+    # bisection of helpers.binary_search and conditions on its INPUT -- rebuilt with the rng MFlow handed down
+    from jax import random
+    _, trng = random.split(21)
+    tparams, _direct, inverse = flows.Serial(*(flows.IMADE(get_masked_transform(), spline_degree=k_i, n_internal_knots=n_i,
+                                                          spline_regularization=reg, reverse_fun_tol=1e-6), flows.Reverse()) * L)(trng, D)
+    assert all(np.array_equal(a, b) for a, b in zip(leaves(tparams), leaves(params[0])))
+    import jax.numpy as jnp                                     # (the stand-in) arrays with jax's functional .at[] updates
+    x_back = np.asarray(inverse(tparams, jnp.asarray(np.asarray(u)))[0])
+    # box transform, both coordinate types, both directions (made.py:108-190; reverse_fun_mean is quirk Q2)
+    box = {}
+    for coord, Db, Lb in (("mean", 2, 4.0), ("first", 3, 5.0)):
+        _, bdirect, breverse = flows.BoxTransformLayer(Lb, xu_coord_type=coord)(0, Db)
+        xb = np.sort(rng.uniform(-0.9 * Lb, 0.9 * Lb, (64, Db)), axis=-1)
+        xb = xb.astype(np.float32) if mode == "f32" else xb
+        ub, ldb = bdirect((), jnp.asarray(xb))
+        box[f"box_{coord}_x"], box[f"box_{coord}_u"], box[f"box_{coord}_ld"] = np.asarray(xb), np.asarray(ub), np.asarray(ldb)
+        box[f"box_{coord}_back"] = np.asarray(breverse((), jnp.asarray(np.asarray(ub)))[0])
+        box[f"box_{coord}_L"] = np.float64(Lb)
+    out = {"x": np.asarray(x), "logpdf": np.asarray(lp), "u": np.asarray(u), "x_back": x_back, **box,
+           "treedef": np.array(json.dumps(structure(params))),
            "cfg": np.array(json.dumps(dict(D=D, L=L, k_i=k_i, n_i=n_i, reg=reg, k_p=k_p, n_p=n_p)))}
     for i, leaf in enumerate(leaves(params)):
         out[f"param{i:03d}"] = leaf
