@@ -15,7 +15,7 @@ but tests/golden/make_energy_golden.py executes the unmodified model_factory -> 
 bsplines_jax -> utils/physics.construct_hamiltonian_function on a numpy stand-in for jax (float64): jax.hessian becomes forward
 over forward mode with nested, level-tagged dual numbers carried through the reference's own arithmetic, and every table lookup
 on a dual number applies the custom_jvp rule the reference registered, at both levels.  Both restatements reproduce the stored
-psi / log_pdf / H psi to 1e-12 for a D = 2 ('mean' coordinates) and a D = 3 ('first') model (tests/test_energy_reference_vectors.py).
+psi / log_pdf / H psi to 1e-12 for a D = 2 ('mean' coordinates), a D = 3 ('first') and a three-layer D = 4 ('mean') model (tests/test_energy_reference_vectors.py).
 Further pins: the two restatements agree with each other, the psi KAT, the published energy plateau.
 """
 from __future__ import annotations

@@ -59,7 +59,8 @@ def main():
     from waveflow.utils import physics
 
     out = {}
-    for tag, D, layers, coord, box, n in (("d2_mean", 2, 1, "mean", 4.0, 10), ("d3_first", 3, 1, "first", 5.0, 4)):
+    for tag, D, layers, coord, box, n in (("d2_mean", 2, 1, "mean", 4.0, 10), ("d3_first", 3, 1, "first", 5.0, 4),
+                                          ("d4_mean_l3", 4, 3, "mean", 10.0, 2)):       # the bench's D, depth and box
         init = model_factory.get_waveflow_model(D, base_spline_degree=5, i_spline_degree=5, n_prior_internal_knots=16,
                                                 n_i_internal_knots=16, n_flow_layers=layers, box_size=box, xu_coord_type=coord)
         params, psi, log_pdf, sample = init(3 + D, D)

@@ -40,7 +40,7 @@ def _leaves(t, out):
     return out
 
 
-@pytest.mark.parametrize("tag", ["d2_mean", "d3_first"])
+@pytest.mark.parametrize("tag", ["d2_mean", "d3_first", "d4_mean_l3"])
 def test_psi_logpdf_and_local_energy_equal_the_reference_source(tag):
     """psi, log_pdf and H psi = -1/2 trace(hessian(psi)) + V psi: both restatements of oracle/laplacian.py (forward-Laplacian
     bundles, torch double autograd) against the reference's own code -- float64, 1e-12."""
