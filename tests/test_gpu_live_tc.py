@@ -163,3 +163,29 @@ def test_mflow_logpdf_against_vectors_from_the_reference_source(cuda, mode):
     r64 = live.log_pdf(m, mflow_params(np.float64), x.astype(np.float64))
     assert_fp32_grade(out["logpdf"].cpu().numpy(), r64, G["f32_logpdf"], 1e-5, 1.0, f"{mode} MFlow.log_pdf vs reference source")
     assert np.abs(out["u"].cpu().numpy() - G["f32_u"]).max() <= 2e-6
+
+
+@pytest.mark.parametrize("tag", ["d2_mean", "d3_first", "d4_mean_l3"])
+def test_local_energy_against_vectors_from_the_reference_source(cuda, tag):
+    """wf_local_energy (tensor-core and CUDA-core kernels) against psi and H psi produced by the reference's own model_factory /
+    wavefunctions / flows / splines / physics.construct_hamiltonian_function (jax.hessian with the registered custom_jvp rules),
+    executed in float64 on the numpy stand-in for jax (tests/golden/make_energy_golden.py)."""
+    from waveflow_b200 import _live
+    from tests.test_energy_reference_vectors import G, _model
+    m, params, D = _model(tag)
+    spec = spec_from_live(m)
+    w = _pack(spec, fx.cast_params(params, np.float32), cuda)
+    x = G[tag + "_x"].astype(np.float32)
+    ref = olap.local_energy_bundle(m, params, x.astype(np.float64), np.zeros((D, 1)))      # == the reference vectors at float64 x
+    assert np.abs(ref["hpsi"] - G[tag + "_hpsi"]).max() <= 1e-5 * np.abs(G[tag + "_hpsi"]).max()   # float32 rounding of x only
+    # yardstick: the reference's arithmetic in float32 (the vectorised CPU port of the same formulas)
+    r32 = fast_cpu.FastLocalEnergy(m.cast(np.float32), params, np.zeros((D, 1)), dtype=torch.float32)(x)
+    for mode in ("tc", "simt"):
+        out = _live.local_energy(spec, w, torch.from_numpy(x).to(cuda), np.zeros((D, 1)), want=("psi", "hpsi"), mode=mode)
+        for key, tol in (("psi", 2e-5), ("hpsi", 2e-4)):
+            got, gold = out[key].cpu().numpy().astype(np.float64), G[tag + "_" + key]
+            scale = np.abs(gold).max()
+            e32 = np.abs(np.asarray(r32[key], dtype=np.float64) - gold).max()
+            err = np.abs(got - gold).max()
+            print(f"{tag} {mode} {key}: max error / max|ref| = {err / scale:.2e} (float32 CPU arithmetic {e32 / scale:.2e})")
+            assert err <= max(tol * scale, 4 * e32 + 1e-6 * scale), (mode, key, err / scale, e32 / scale)
