@@ -15,7 +15,8 @@ quirk Q5) -- the parameter gradient is the only place that clamp is reachable.
 PINNED BY THE REFERENCE'S OWN SOURCE: no gradients are stored anywhere upstream, but
 tests/golden/make_energy_golden.py evaluates the unmodified vqmc.loss_fn_efficient -- including the estimator it registers with
 custom_jvp -- on parameters seeded with dual numbers (numpy stand-in for jax, float64): the loss value and <grad loss, v> for two
-random parameter directions v agree with ``loss_and_grad`` to 1e-12 (tests/test_energy_reference_vectors.py).  Further pins:
+random parameter directions v agree with ``loss_and_grad`` to 1e-12 -- also for a three-layer D = 4 model, where the clamp of
+table index 4 to 3 (quirk Q5) is reached (tests/test_energy_reference_vectors.py).  Further pins:
 the chain psi-KAT -> Laplacian oracles -> this function, and a finite-difference check of the surrogate on the parameters
 whose gradient does not pass through a table argument (tests/test_oracle_golden.py).
 """

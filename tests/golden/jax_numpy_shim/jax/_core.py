@@ -40,6 +40,35 @@ class JArr(_np.ndarray):
     def at(self):
         return _At(self)
 
+    def __getitem__(self, idx):
+        """jax's out-of-bounds rule for retrieval: integer indices are CLAMPED into the axis (negative ones wrap first) instead of
+        raising -- `tables[n_derivative + 1]` with n_derivative = 3 reads table 3, a mesh index above T - 1 reads
+        the last node (Q3)."""
+        parts = idx if isinstance(idx, tuple) else (idx,)
+        if not any(p is Ellipsis for p in parts):
+            fixed, axis = [], 0
+            for p_ in parts:
+                if p_ is None:
+                    fixed.append(p_)
+                    continue
+                n = self.shape[axis] if axis < self.ndim else 1
+                if isinstance(p_, _np.ndarray) and p_.ndim == 0 and p_.dtype.kind in "iu":
+                    p_ = int(p_)
+                if isinstance(p_, (int, _np.integer)) and not isinstance(p_, (bool, _np.bool_)):
+                    q = int(p_) + n if p_ < 0 else int(p_)
+                    p_ = min(max(q, 0), n - 1)
+                elif isinstance(p_, _np.ndarray) and p_.dtype.kind in "iu":
+                    q = p_.view(_np.ndarray)
+                    p_ = _np.clip(_np.where(q < 0, q + n, q), 0, n - 1)
+                fixed.append(p_)
+                axis += 1
+            idx = tuple(fixed) if isinstance(idx, tuple) else fixed[0]
+        return super().__getitem__(idx)
+
+    def __iter__(self):                      # by length (the sequence protocol would wait for an IndexError that clamping never raises)
+        for i in range(len(self)):
+            yield super().__getitem__(i)
+
     # jax arrays are immutable: `a += b` rebinds the name to a new array (and may change its dtype)
     def __iadd__(self, o): return self + o
     def __isub__(self, o): return self - o

@@ -77,17 +77,18 @@ def main():
             out[f"{tag}_param{i:03d}"] = leaf
         out[f"{tag}_treedef"] = np.array(json.dumps(structure(params)))
         print(tag, "psi", p[:3], "hpsi", hp[:3], flush=True)
-        if tag == "d2_mean":
+        if tag in ("d2_mean", "d4_mean_l3"):
             # ---- the training loss of vqmc.py:192-212 and its derivative along random PARAMETER directions: the parameters are
             # seeded with dual numbers (the lowest differentiation level) and the reference's own loss_fn_efficient -- with the
             # gradient estimator it registers through custom_jvp -- is evaluated on them; <grad loss, v> is the tangent of the result
             from waveflow import vqmc as ref_vqmc
             from jax._core import Dual, JArr, new_tag
             xb, ra = x[:4], -0.3
+            n_dirs = 2 if tag == "d2_mean" else 1
             out[f"{tag}_loss_x"], out[f"{tag}_loss_running_average"] = xb, np.float64(ra)
             out[f"{tag}_loss"] = np.float64(np.asarray(ref_vqmc.loss_fn_efficient(params, psi, h_fn, xb, ra)))
             drng = np.random.default_rng(77)
-            for k in range(2):
+            for k in range(n_dirs):
                 tagp = new_tag()
                 dirs = [drng.standard_normal(leaf.shape) for leaf in leaves(params)]
                 it = iter(dirs)
