@@ -1,5 +1,7 @@
-"""Array wrapper with jax's functional `.at[...]` updates, a one-level dual number for `grad` of scalar functions, and the
-function transformations the reference's spline modules use (jit, vmap, grad, custom_jvp).  Test infrastructure (see README.md)."""
+"""Core of the numpy stand-in for jax (test infrastructure, see ../README.md): an array class with jax's dtype rule, functional
+`.at[...]` updates, immutable in-place operators and clamped out-of-range indexing; level-tagged dual numbers for forward-mode
+differentiation (nested for second order); and the function transformations the reference's files use -- jit, vmap, grad,
+hessian, custom_jvp (the registered rule is applied whenever a dual number reaches the function)."""
 import math as _math
 import os as _os
 
