@@ -430,7 +430,7 @@ def run_b200(args):
     # DEPTH - 1 steps later, so a host hiccup of a millisecond or two does not drain the GPU queue (with two steps in flight the
     # end-to-end figure moved between 96 % and 99 % of the device figure from run to run).
     # Every step still does its own H2D copy of the inputs and its own D2H read of the result inside the timed region.
-    DEPTH = 4
+    DEPTH = 4 if world == 1 else 2          # the multi-GPU runs of the round were taken (and were stable) with two steps in flight
     copy_stream = torch.cuda.Stream(device=dev)
     xbuf = [torch.empty_like(x_dev) for _ in range(DEPTH)]
     sbuf = [torch.zeros(4, dtype=torch.float64, device=dev) for _ in range(DEPTH)]
@@ -908,7 +908,7 @@ def run_b200(args):
                     "api": "h_fn = utils.physics.construct_hamiltonian_function(psi, protons); h_fn(params, walkers, sums=...) -- the reference's "
                            "signature with the raw parameter pytree on every call (packed layout from the per-model cache)",
                     "ms_per_step": e2e_s / steps * 1e3,
-                    "pipelining": "four steps in flight: the H2D copy of step i + 1 and the D2H read of step i overlap the kernel of the "
+                    "pipelining": ("four" if world == 1 else "two") + " steps in flight: the H2D copy of step i + 1 and the D2H read of step i overlap the kernel of the "
                                   "neighbouring step (copy stream + events); every step performs its own copies inside the timed region"},
             # launches of this repo's kernels inside the timed region: the local-energy kernel, + the 32-thread exchange kernel
             # when it is not fused into the kernel tail
